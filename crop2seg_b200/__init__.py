@@ -1,0 +1,18 @@
+"""crop2seg_b200 -- B200-native (sm_100a) L-TAE + TemporalAggregator hot path of Many98/Crop2Seg.
+
+Public surface (mirrors the reference's interface for this path):
+
+    LTAE, LTAE4WTAE, TemporalAggregator     drop-in nn.Modules (modules.py)
+    ops.ltae_forward, ops.temporal_aggregate tensor-level calls over the C ABI (ops.py)
+    install()                               swap the three classes into the reference's model files
+    shard_patches()                         patch sharding for multi-GPU inference (sharding.py)
+
+The arithmetic lives in ``lib/libcrop2seg_b200.so`` (``include/crop2seg_b200.h``), built in-tree by
+``python -m crop2seg_b200.build``.  There is no CPU or PyTorch fallback.
+"""
+from .modules import LTAE, LTAE4WTAE, TemporalAggregator  # noqa: F401
+from .install import install, uninstall  # noqa: F401
+from .sharding import shard_patches, shard_bounds  # noqa: F401
+from . import ops  # noqa: F401
+
+__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "ops"]

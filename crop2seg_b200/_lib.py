@@ -1,0 +1,108 @@
+"""ctypes binding of the C ABI declared in ``include/crop2seg_b200.h``.
+
+The library is the product: if it is missing or fails to load, every operator raises.  There is
+no PyTorch / CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+from .build import LIB_PATH
+
+C2S_ABI_VERSION = 1
+
+# enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
+F32, BF16 = 0, 1
+AGG_ATT_GROUP, AGG_ATT_MEAN, AGG_MEAN = 0, 1, 2
+PE_NONE, PE_SINUSOID, PE_SINUSOID_LINEAR, PE_DOY_TABLE = 0, 1, 2, 3
+LTAE_ATTN_ONLY, LTAE_SKIP_ATTN_STORE, LTAE_ZERO_PADDED, LTAE_BN_BATCH_STATS = 1, 2, 4, 8
+
+EXPORTS = (
+    "c2s_abi_version", "c2s_last_error", "c2s_launch_count", "c2s_reset_launch_count", "c2s_last_kernel",
+    "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_ltae_workspace_bytes", "c2s_ltae_forward",
+)
+
+
+class AggDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "C", "H", "W", "n_heads", "ha", "wa", "mode", "dtype")]
+
+
+class LtaeDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "B", "T", "C", "H", "W", "n_head", "d_k", "d_model", "c_out", "has_inconv", "pe_mode", "pe_abs",
+        "pos_dtype", "dtype", "flags")] + [("gn_eps", ctypes.c_float), ("bn_eps", ctypes.c_float)]
+
+
+LTAE_PARAM_FIELDS = (
+    "in_norm_weight", "in_norm_bias", "inconv_weight", "inconv_bias", "query", "key_weight", "key_bias",
+    "mlp_weight", "mlp_bias", "bn_weight", "bn_bias", "bn_running_mean", "bn_running_var",
+    "out_norm_weight", "out_norm_bias", "pe_denom", "pe_fc_weight", "pe_fc_bias", "pe_abs_fc_weight",
+    "pe_abs_fc_bias",
+)
+
+
+class LtaeParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_PARAM_FIELDS]
+
+
+class C2SError(RuntimeError):
+    """A C-ABI call returned a non-zero status (message from ``c2s_last_error``)."""
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load ``libcrop2seg_b200.so`` (once).  Raises if it was not built -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise C2SError(
+                f"{LIB_PATH} not found: build the CUDA library first "
+                "(python -m crop2seg_b200.build, or __graft_entry__.build()). crop2seg_b200 has no fallback path.")
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        lib.c2s_abi_version.restype = i32
+        lib.c2s_last_error.restype = ctypes.c_char_p
+        lib.c2s_last_kernel.restype = ctypes.c_char_p
+        lib.c2s_launch_count.restype = ctypes.c_int64
+        lib.c2s_reset_launch_count.restype = None
+        lib.c2s_agg_workspace_bytes.restype = sz
+        lib.c2s_agg_workspace_bytes.argtypes = [ctypes.POINTER(AggDesc)]
+        lib.c2s_agg_forward.restype = i32
+        lib.c2s_agg_forward.argtypes = [ctypes.POINTER(AggDesc), vp, vp, vp, vp, vp, sz, vp]
+        lib.c2s_ltae_workspace_bytes.restype = sz
+        lib.c2s_ltae_workspace_bytes.argtypes = [ctypes.POINTER(LtaeDesc)]
+        lib.c2s_ltae_forward.restype = i32
+        lib.c2s_ltae_forward.argtypes = [ctypes.POINTER(LtaeDesc), ctypes.POINTER(LtaeParams), vp, vp, vp, vp, vp,
+                                         vp, vp, vp, sz, vp]
+        got = lib.c2s_abi_version()
+        if got != C2S_ABI_VERSION:
+            raise C2SError(f"ABI mismatch: library reports version {got}, binding expects {C2S_ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().c2s_last_error().decode("utf-8", "replace")
+        raise C2SError(f"{what} failed with status {status}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().c2s_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().c2s_reset_launch_count()
+
+
+def last_kernel() -> str:
+    return load().c2s_last_kernel().decode("utf-8", "replace")

@@ -1,0 +1,416 @@
+// TemporalAggregator forward for sm_100a.
+//
+// Replaces TemporalAggregator.forward (reference src/backbones/temporal_aggregator.py:14-77):
+//   out[b,c,y,x] = sum_t  resize(attn)[c / (C/h), b, t, y, x] * (pad[b,t] ? 0 : 1) * x[b,t,c,y,x]
+// The reference materialises the up-sampled attention (nn.Upsample, :17-19,27), a head-major copy
+// of x (torch.stack(x.chunk), :35) and the full-size product (:37) in HBM.  Here every byte of x is
+// read exactly once with 128-bit streaming loads, the bilinear weights are rebuilt in registers
+// from the low-resolution attention map (which stays L1/L2 resident: h*T*ha*wa*4 B = 1 MB per
+// sample at the shipped shapes), padded frames are never read, and only out[B,C,H,W] is written.
+//
+// Work decomposition: one thread owns VEC consecutive pixels (one 16-byte vector) of CPT
+// consecutive channels that share one attention head, loops over the valid frames of its sample
+// and keeps VEC*CPT fp32 accumulators in registers.  A warp therefore reads 512 contiguous bytes
+// per (frame, channel); CPT*U independent 16-byte loads are in flight per thread.
+//
+// HBM roofline: algorithmic bytes = e*T_valid*C*H*W (x) + e*C*H*W (out) per sample, see DESIGN.md.
+#include <type_traits>
+
+#include "c2s_common.cuh"
+
+namespace c2s {
+namespace {
+
+constexpr int kAggThreads = 256;
+constexpr int kAggMaxT = 1024;  // frames per series the frame list in shared memory can hold
+
+struct AggArgs {
+  const void* x;
+  const float* attn;  // [n_heads, B, T, ha, wa] or nullptr (uniform weights)
+  const uint8_t* pad;  // [B, T] or nullptr
+  void* out;
+  int B, T, C, H, W;
+  int n_heads, ha, wa;
+  int cpg;           // channels per attention head = C / n_heads
+  int uniform_div;   // 'mean' mode: weights are 1 and the sum is divided by the number of frames read
+  float sy, sx;      // ATen's area_pixel_compute_scale: float(in) / out
+  int hw;            // H * W
+  int pv_per_plane;  // hw / VEC
+  int items_per_b;   // (C / CPT) * pv_per_plane
+};
+
+// ATen area_pixel_compute_source_index(scale, dst, align_corners=false) + the i0/i1/lambda split
+// of upsample_bilinear2d (called through nn.Upsample at temporal_aggregator.py:17-19).
+__device__ __forceinline__ void source_index(float scale, int dst, int in_size, int& i0, int& i1, float& l1) {
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  i0 = i0 < in_size - 1 ? i0 : in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+}
+
+template <typename T, int VEC>
+struct PixelVec;  // VEC pixels of one channel
+
+template <>
+struct PixelVec<float, 4> {
+  uint4 v;
+  __device__ __forceinline__ void load(const float* p) { v = ld_stream_v4(p); }
+  __device__ __forceinline__ void get(float (&f)[4]) const { Elem<float>::unpack(v, f); }
+  __device__ static __forceinline__ void store(float* p, const float (&f)[4]) { st_stream_v4(p, Elem<float>::pack(f)); }
+};
+template <>
+struct PixelVec<__nv_bfloat16, 8> {
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = ld_stream_v4(p); }
+  __device__ __forceinline__ void get(float (&f)[8]) const { Elem<__nv_bfloat16>::unpack(v, f); }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    st_stream_v4(p, Elem<__nv_bfloat16>::pack(f));
+  }
+};
+template <typename T>
+struct PixelVec<T, 1> {  // scalar fallback: any W, any alignment
+  T v;
+  __device__ __forceinline__ void load(const T* p) { v = *p; }
+  __device__ __forceinline__ void get(float (&f)[1]) const { f[0] = Elem<T>::load(&v); }
+  __device__ static __forceinline__ void store(T* p, const float (&f)[1]) { Elem<T>::store(p, f[0]); }
+};
+
+// S > 0 : H == S*ha and W == S*wa with S a power of two; the VEC pixels of a thread touch a
+//         compile-time window of NCOL low-resolution columns (2 rows x NCOL loads per frame).
+// S == 0: any size ratio; 4 attention loads per pixel and frame.
+// S == -1: no attention map (mode 'mean').
+template <int VEC, int S>
+struct Window {
+  static constexpr int kCols = (S > 0) ? ((VEC >= S) ? VEC / S + 2 : 2) : 1;
+};
+
+template <typename T, int VEC, int CPT, int S>
+__global__ void __launch_bounds__(kAggThreads) agg_forward_kernel(const AggArgs a) {
+  __shared__ short frames[kAggMaxT];
+  __shared__ int n_frames_s;
+
+  const int b = blockIdx.y;
+  if (threadIdx.x < 32) {  // ordered list of the frames that are not padded
+    int count = 0;
+    for (int base = 0; base < a.T; base += 32) {
+      const int t = base + threadIdx.x;
+      const bool valid = t < a.T && (a.pad == nullptr || a.pad[b * a.T + t] == 0);
+      const unsigned m = __ballot_sync(0xffffffffu, valid);
+      if (valid) frames[count + __popc(m & ((1u << threadIdx.x) - 1u))] = static_cast<short>(t);
+      count += __popc(m);
+    }
+    if (threadIdx.x == 0) n_frames_s = count;
+  }
+  __syncthreads();
+  const int n_frames = n_frames_s;
+
+  const int item = blockIdx.x * kAggThreads + threadIdx.x;
+  if (item >= a.items_per_b) return;
+  const int cchunk = item / a.pv_per_plane;
+  const int pv = item - cchunk * a.pv_per_plane;
+  const int c0 = cchunk * CPT;
+  const int p0 = pv * VEC;
+  const int y = p0 / a.W;
+  const int x0 = p0 - y * a.W;
+
+  constexpr int NCOL = Window<VEC, S>::kCols;
+  // vertical taps (shared by the VEC pixels) and horizontal taps
+  int row0 = 0, row1 = 0;
+  float ly1 = 0.f;
+  int col[(S > 0) ? NCOL : 1];
+  int gcol0[(S == 0) ? VEC : 1], gcol1[(S == 0) ? VEC : 1];
+  float lx1[VEC];
+  if constexpr (S >= 0) {
+    int iy0, iy1;
+    source_index(a.sy, y, a.ha, iy0, iy1, ly1);
+    row0 = iy0 * a.wa;
+    row1 = iy1 * a.wa;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      int i0, i1;
+      source_index(a.sx, x0 + j, a.wa, i0, i1, lx1[j]);
+      if constexpr (S == 0) {
+        gcol0[j] = i0;
+        gcol1[j] = i1;
+      }
+    }
+    if constexpr (S > 0) {
+      int cmin = x0 / S - 1;
+      if constexpr (VEC < S) cmin += ((x0 % S) >= S / 2) ? 1 : 0;
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) {
+        int cj = cmin + j;
+        cj = cj < 0 ? 0 : cj;
+        col[j] = cj > a.wa - 1 ? a.wa - 1 : cj;
+      }
+    }
+  }
+  const float ly0 = 1.f - ly1;
+
+  const size_t frame_stride = static_cast<size_t>(a.C) * a.hw;
+  const T* xb = static_cast<const T*>(a.x) + static_cast<size_t>(b) * a.T * frame_stride +
+                static_cast<size_t>(c0) * a.hw + p0;
+  const int amap = a.ha * a.wa;
+  const float* ab = nullptr;
+  if constexpr (S >= 0) {
+    const int g = c0 / a.cpg;
+    ab = a.attn + (static_cast<size_t>(g) * a.B + b) * a.T * amap;
+  }
+
+  float acc[CPT][VEC];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
+
+  // one group of U frames: all global loads are issued before the first use
+  auto step = [&](auto u_tag, int i) {
+    constexpr int U = decltype(u_tag)::value;
+    PixelVec<T, VEC> xv[U][CPT];
+    float top[U][(S > 0) ? NCOL : ((S == 0) ? 2 * VEC : 1)];
+    float bot[U][(S > 0) ? NCOL : ((S == 0) ? 2 * VEC : 1)];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = frames[i + u];
+      const T* xp = xb + static_cast<size_t>(t) * frame_stride;
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) xv[u][k].load(xp + static_cast<size_t>(k) * a.hw);
+      if constexpr (S > 0) {
+        const float* ap = ab + static_cast<size_t>(t) * amap;
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+          top[u][j] = __ldg(ap + row0 + col[j]);
+          bot[u][j] = __ldg(ap + row1 + col[j]);
+        }
+      } else if constexpr (S == 0) {
+        const float* ap = ab + static_cast<size_t>(t) * amap;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          top[u][2 * j] = __ldg(ap + row0 + gcol0[j]);
+          top[u][2 * j + 1] = __ldg(ap + row0 + gcol1[j]);
+          bot[u][2 * j] = __ldg(ap + row1 + gcol0[j]);
+          bot[u][2 * j + 1] = __ldg(ap + row1 + gcol1[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float w[VEC];
+      if constexpr (S > 0) {
+        float r[NCOL];
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) r[j] = fmaf(ly1, bot[u][j], ly0 * top[u][j]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const int i0w = (VEC >= S) ? (j / S + ((j % S) < S / 2 ? 0 : 1)) : 0;
+          w[j] = fmaf(lx1[j], r[i0w + 1], (1.f - lx1[j]) * r[i0w]);
+        }
+      } else if constexpr (S == 0) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float l0 = 1.f - lx1[j];
+          const float tp = fmaf(lx1[j], top[u][2 * j + 1], l0 * top[u][2 * j]);
+          const float bt = fmaf(lx1[j], bot[u][2 * j + 1], l0 * bot[u][2 * j]);
+          w[j] = fmaf(ly1, bt, ly0 * tp);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        float f[VEC];
+        xv[u][k].get(f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          if constexpr (S >= 0)
+            acc[k][j] = fmaf(w[j], f[j], acc[k][j]);
+          else
+            acc[k][j] += f[j];
+        }
+      }
+    }
+  };
+
+  constexpr int U = (sizeof(T) * VEC * CPT >= 64) ? 2 : 4;  // >= 128 B of x in flight per thread
+  int i = 0;
+  for (; i + U <= n_frames; i += U) step(std::integral_constant<int, U>{}, i);
+  for (; i < n_frames; ++i) step(std::integral_constant<int, 1>{}, i);
+
+  T* op = static_cast<T*>(a.out) + (static_cast<size_t>(b) * a.C + c0) * a.hw + p0;
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    if (a.uniform_div) {  // no valid frame: 0 / 0 = nan, as in the reference
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[k][j] = acc[k][j] / static_cast<float>(n_frames);
+    }
+    PixelVec<T, VEC>::store(op + static_cast<size_t>(k) * a.hw, acc[k]);
+  }
+}
+
+// attn_mean[b,t,y,x] = mean_h attn[h,b,t,y,x]          (temporal_aggregator.py:48 / :72)
+__global__ void head_mean_kernel(const float* __restrict__ attn, float* __restrict__ out, int n_heads, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int h = 0; h < n_heads; ++h) s += attn[static_cast<size_t>(h) * n + i];
+  out[i] = s / static_cast<float>(n_heads);
+}
+
+// nn.AvgPool2d(kernel_size=k) on the last two axes (temporal_aggregator.py:29): stride k, floor.
+__global__ void avg_pool_kernel(const float* __restrict__ in, float* __restrict__ out, int hi, int wi, int ho,
+                                int wo, int k, size_t n_out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int x = static_cast<int>(i % wo);
+  const int y = static_cast<int>((i / wo) % ho);
+  const size_t map = i / (static_cast<size_t>(wo) * ho);
+  const float* p = in + map * hi * wi + static_cast<size_t>(y) * k * wi + static_cast<size_t>(x) * k;
+  float s = 0.f;
+  for (int dy = 0; dy < k; ++dy)
+    for (int dx = 0; dx < k; ++dx) s += p[dy * wi + dx];
+  out[i] = s / static_cast<float>(k * k);
+}
+
+template <typename T, int VEC, int CPT, int S>
+int launch_variant(const AggArgs& a, cudaStream_t stream, const char* name) {
+  dim3 grid(ceil_div(a.items_per_b, kAggThreads), a.B);
+  agg_forward_kernel<T, VEC, CPT, S><<<grid, kAggThreads, 0, stream>>>(a);
+  C2S_LAUNCH_CHECK(name);
+  return C2S_OK;
+}
+
+template <typename T, int VEC, int CPT>
+int launch_scale(const AggArgs& a, int s, cudaStream_t stream) {
+  if constexpr (VEC > 1) {
+    switch (s) {
+      case 2: return launch_variant<T, VEC, CPT, 2>(a, stream, "agg_forward<x2>");
+      case 4: return launch_variant<T, VEC, CPT, 4>(a, stream, "agg_forward<x4>");
+      case 8: return launch_variant<T, VEC, CPT, 8>(a, stream, "agg_forward<x8>");
+      default: break;
+    }
+  }
+  if (s == -1) return launch_variant<T, VEC, CPT, -1>(a, stream, "agg_forward<mean>");
+  return launch_variant<T, VEC, CPT, 0>(a, stream, "agg_forward<generic>");
+}
+
+template <typename T, int VEC>
+int launch_cpt(const AggArgs& a, int cpt, int s, cudaStream_t stream) {
+  switch (cpt) {
+    case 4: return launch_scale<T, VEC, 4>(a, s, stream);
+    case 2: return launch_scale<T, VEC, 2>(a, s, stream);
+    default: return launch_scale<T, VEC, 1>(a, s, stream);
+  }
+}
+
+size_t attn_elems(const c2s_agg_desc* d, int heads, int h, int w) {
+  return static_cast<size_t>(heads) * d->B * d->T * h * w;
+}
+
+// The AvgPool2d branch is taken when x is not taller than the attention map is wide
+// (temporal_aggregator.py:26-29 compares x.shape[-2] with the attention width).
+bool uses_pool(const c2s_agg_desc* d) { return d->mode == C2S_AGG_ATT_GROUP && !(d->H > d->wa); }
+
+}  // namespace
+}  // namespace c2s
+
+extern "C" {
+
+size_t c2s_agg_workspace_bytes(const c2s_agg_desc* d) {
+  if (d == nullptr) return 0;
+  size_t n = 0;
+  if (d->mode == C2S_AGG_ATT_MEAN) n = c2s::attn_elems(d, 1, d->ha, d->wa);
+  if (c2s::uses_pool(d)) {
+    const int k = d->wa / (d->H > 0 ? d->H : 1);
+    if (k >= 1) n = c2s::attn_elems(d, d->n_heads, d->ha / k, d->wa / k);
+  }
+  return n * sizeof(float);
+}
+
+int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, const uint8_t* pad_mask, void* out,
+                    void* workspace, size_t workspace_bytes, void* stream_ptr) {
+  using namespace c2s;
+  C2S_CHECK_ARG(d != nullptr, "c2s_agg_forward: desc is NULL");
+  C2S_CHECK_ARG(x != nullptr && out != nullptr, "c2s_agg_forward: x/out is NULL");
+  C2S_CHECK_ARG(d->B > 0 && d->T > 0 && d->C > 0 && d->H > 0 && d->W > 0,
+                "c2s_agg_forward: non-positive dimension in x[%d,%d,%d,%d,%d]", d->B, d->T, d->C, d->H, d->W);
+  C2S_CHECK_ARG(d->dtype == C2S_F32 || d->dtype == C2S_BF16, "c2s_agg_forward: unknown dtype %d", d->dtype);
+  C2S_CHECK_ARG(d->mode >= C2S_AGG_ATT_GROUP && d->mode <= C2S_AGG_MEAN, "c2s_agg_forward: unknown mode %d", d->mode);
+  if (d->T > kAggMaxT) C2S_UNSUPPORTED("c2s_agg_forward: T=%d exceeds the supported %d frames", d->T, kAggMaxT);
+  if (d->B > 65535) C2S_UNSUPPORTED("c2s_agg_forward: B=%d exceeds 65535 samples per call", d->B);
+  if (static_cast<long long>(d->H) * d->W > (1ll << 30)) C2S_UNSUPPORTED("c2s_agg_forward: H*W too large");
+  int status = check_device();
+  if (status != C2S_OK) return status;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_ptr);
+
+  AggArgs a{};
+  a.x = x;
+  a.pad = pad_mask;
+  a.out = out;
+  a.B = d->B, a.T = d->T, a.C = d->C, a.H = d->H, a.W = d->W;
+  a.hw = d->H * d->W;
+  int scale_class = 0;
+
+  if (d->mode == C2S_AGG_MEAN) {
+    a.attn = nullptr;
+    a.n_heads = 1, a.ha = 1, a.wa = 1, a.cpg = d->C;
+    // masked: sum / count (temporal_aggregator.py:54-55); unmasked: x.mean(dim=1) (:77)
+    a.uniform_div = 1;
+    scale_class = -1;
+  } else {
+    C2S_CHECK_ARG(attn != nullptr, "c2s_agg_forward: attn is NULL for an attention mode");
+    C2S_CHECK_ARG(d->n_heads > 0 && d->ha > 0 && d->wa > 0, "c2s_agg_forward: bad attention shape [%d,.,.,%d,%d]",
+                  d->n_heads, d->ha, d->wa);
+    const float* amap = attn;
+    int heads = d->n_heads, ha = d->ha, wa = d->wa;
+    if (d->mode == C2S_AGG_ATT_MEAN) {
+      const size_t n = attn_elems(d, 1, ha, wa);
+      C2S_CHECK_ARG(workspace != nullptr && workspace_bytes >= n * sizeof(float),
+                    "c2s_agg_forward: att_mean needs %zu workspace bytes", n * sizeof(float));
+      head_mean_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(attn, static_cast<float*>(workspace), heads, n);
+      C2S_LAUNCH_CHECK("head_mean");
+      amap = static_cast<const float*>(workspace);
+      heads = 1;
+    } else if (uses_pool(d)) {
+      const int k = d->wa / d->H;
+      C2S_CHECK_ARG(k >= 1, "c2s_agg_forward: AvgPool2d kernel size would be 0");
+      const int ho = ha / k, wo = wa / k;
+      C2S_CHECK_ARG(ho == d->H && wo == d->W,
+                    "c2s_agg_forward: pooled attention %dx%d does not match x %dx%d (the reference fails to broadcast)",
+                    ho, wo, d->H, d->W);
+      if (k > 1) {
+        const size_t n = attn_elems(d, heads, ho, wo);
+        C2S_CHECK_ARG(workspace != nullptr && workspace_bytes >= n * sizeof(float),
+                      "c2s_agg_forward: pooled attention needs %zu workspace bytes", n * sizeof(float));
+        avg_pool_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(attn, static_cast<float*>(workspace), ha, wa, ho, wo,
+                                                              k, n);
+        C2S_LAUNCH_CHECK("avg_pool");
+        amap = static_cast<const float*>(workspace);
+      }
+      ha = ho, wa = wo;
+    }
+    C2S_CHECK_ARG(d->C % heads == 0, "c2s_agg_forward: C=%d is not divisible by n_heads=%d", d->C, heads);
+    a.attn = amap;
+    a.n_heads = heads, a.ha = ha, a.wa = wa, a.cpg = d->C / heads;
+    a.sy = static_cast<float>(ha) / static_cast<float>(d->H);
+    a.sx = static_cast<float>(wa) / static_cast<float>(d->W);
+    for (int s : {2, 4, 8})
+      if (d->H == s * ha && d->W == s * wa) scale_class = s;
+  }
+
+  const int cpt = (a.cpg % 4 == 0) ? 4 : (a.cpg % 2 == 0 ? 2 : 1);
+  const bool bf16 = d->dtype == C2S_BF16;
+  const int vec_full = bf16 ? 8 : 4;
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  const int vec = (d->W % vec_full == 0 && aligned) ? vec_full : 1;
+  a.pv_per_plane = a.hw / vec;
+  a.items_per_b = (d->C / cpt) * a.pv_per_plane;
+  if (vec == 1 && scale_class > 0) scale_class = 0;
+
+  if (bf16) {
+    return vec == 8 ? launch_cpt<__nv_bfloat16, 8>(a, cpt, scale_class, stream)
+                    : launch_cpt<__nv_bfloat16, 1>(a, cpt, scale_class, stream);
+  }
+  return vec == 4 ? launch_cpt<float, 4>(a, cpt, scale_class, stream) : launch_cpt<float, 1>(a, cpt, scale_class, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+// Device-side weight folding and positional tables for the L-TAE kernels; see c2s_ltae_prep.cuh.
+#include "c2s_ltae_prep.cuh"
+
+namespace c2s {
+namespace {
+
+constexpr int kPrepThreads = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (blockDim.x + 31) / 32; ++i) r += scratch[i];
+  return r;
+}
+
+// qk[h,d] = sum_j Q[h,0,j] * Wk[h*dk + j, d] / sqrt(dk)        (tae.py:768, :827-828)
+__global__ void fold_qk_kernel(const float* __restrict__ q, const float* __restrict__ wk, float* __restrict__ qk,
+                               int n_head, int dk, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_head * D) return;
+  const int h = i / D, d = i - h * D;
+  float s = 0.f;
+  for (int j = 0; j < dk; ++j) s = fmaf(q[h * dk + j], wk[static_cast<size_t>(h * dk + j) * D + d], s);
+  qk[i] = s / sqrtf(static_cast<float>(dk));
+}
+
+// u[c, hh] = in_norm.weight[c] * sum_d qk[hh,d] Wc[d,c]   (zero for hh >= n_head)
+__global__ void fold_u_kernel(const float* __restrict__ qk, const float* __restrict__ wc,
+                              const float* __restrict__ gamma, float* __restrict__ u, int n_head, int C, int D,
+                              int has_inconv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * kMaxHeads) return;
+  const int c = i / kMaxHeads, hh = i - c * kMaxHeads;
+  float s = 0.f;
+  if (hh < n_head) {
+    if (has_inconv) {
+      for (int d = 0; d < D; ++d) s = fmaf(qk[hh * D + d], wc[static_cast<size_t>(d) * C + c], s);
+    } else {
+      s = qk[hh * D + c];
+    }
+    s *= gamma[c];
+  }
+  u[i] = s;
+}
+
+// ub[hh] = sum_d qk[hh,d] * (bc[d] + sum_c Wc[d,c] beta[c]) + q_h . bk[h-block] / sqrt(dk); one block per head
+__global__ void fold_ub_kernel(const float* __restrict__ qk, const float* __restrict__ wc,
+                               const float* __restrict__ bc, const float* __restrict__ beta,
+                               const float* __restrict__ q, const float* __restrict__ bk, float* __restrict__ ub,
+                               int n_head, int dk, int C, int D, int has_inconv) {
+  __shared__ float scratch[32];
+  const int hh = blockIdx.x;
+  float s = 0.f;
+  if (hh < n_head) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float v;
+      if (has_inconv) {
+        v = bc[d];
+        for (int c = 0; c < C; ++c) v = fmaf(wc[static_cast<size_t>(d) * C + c], beta[c], v);
+      } else {
+        v = beta[d];
+      }
+      s = fmaf(qk[hh * D + d], v, s);
+    }
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    if (hh < n_head) {
+      float qb = 0.f;
+      for (int j = 0; j < dk; ++j) qb = fmaf(q[hh * dk + j], bk[hh * dk + j], qb);
+      r = s + qb / sqrtf(static_cast<float>(dk));
+    }
+    ub[hh] = r;
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  // out[c, r] = in[r, c]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int c = i / rows, r = i - c * rows;
+  out[i] = in[static_cast<size_t>(r) * cols + c];
+}
+
+// eval BatchNorm1d folded to y * scale + shift                       (tae.py:445)
+__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                               const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                               float* __restrict__ bnf, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float sc = w[i] / sqrtf(rv[i] + eps);
+  bnf[i] = sc;
+  bnf[n + i] = b[i] - rm[i] * sc;
+}
+
+template <typename P>
+__device__ __forceinline__ float pos_as_float(const P* pos, size_t i) {
+  return static_cast<float>(pos[i]);
+}
+template <typename P>
+__device__ __forceinline__ int pos_as_doy(const P* pos, size_t i) {
+  long long v = static_cast<long long>(pos[i]);  // .to(torch.int64) truncates (positional_encoding.py:63)
+  v = v < 0 ? 0 : v;
+  return static_cast<int>(v > 364 ? 364 : v);
+}
+
+// pe[b,t,d] for one (b,t) per block                                  (positional_encoding.py:25-43, 58-73)
+template <typename P>
+__global__ void pos_table_kernel(const P* __restrict__ pos, int pos_stride, const float* __restrict__ denom,
+                                 const float* __restrict__ fc_w, const float* __restrict__ fc_b,
+                                 const float* __restrict__ abs_w, const float* __restrict__ abs_b,
+                                 float* __restrict__ pe, int D, int dh, int pe_mode, int pe_abs) {
+  extern __shared__ float base[];  // [dh] un-tiled sinusoid table (add_linear only)
+  const size_t bt = blockIdx.x;
+  const size_t pi = bt * pos_stride;
+  if (pe_mode == C2S_PE_SINUSOID_LINEAR) {
+    const float p = pos_as_float(pos, pi);
+    for (int i = threadIdx.x; i < dh; i += blockDim.x) {
+      const float a = p / denom[i];
+      base[i] = (i & 1) ? cosf(a) : sinf(a);
+    }
+    __syncthreads();
+  }
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const int i = d % dh;
+    float v = 0.f;
+    if (pe_mode == C2S_PE_SINUSOID) {
+      const float a = pos_as_float(pos, pi) / denom[i];
+      v = (i & 1) ? cosf(a) : sinf(a);
+    } else if (pe_mode == C2S_PE_SINUSOID_LINEAR) {
+      v = fc_b[d];
+      for (int k = 0; k < D; ++k) v = fmaf(fc_w[static_cast<size_t>(d) * D + k], base[k % dh], v);
+    } else if (pe_mode == C2S_PE_DOY_TABLE) {
+      v = fc_w[static_cast<size_t>(i) * 365 + pos_as_doy(pos, pi)] + fc_b[i];
+    }
+    if (pe_abs) v += abs_w[static_cast<size_t>(i) * 365 + pos_as_doy(pos, pi + 1)] + abs_b[i];
+    pe[bt * D + d] = v;
+  }
+}
+
+// cpos[b,t,hh] = ub[hh] + qk[hh,:] . pe[b,t,:]
+__global__ void fold_cpos_kernel(const float* __restrict__ qk, const float* __restrict__ ub,
+                                 const float* __restrict__ pe, float* __restrict__ cpos, int n_head, int D,
+                                 size_t n_bt, int has_pe) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_bt * kMaxHeads) return;
+  const size_t bt = i / kMaxHeads;
+  const int hh = static_cast<int>(i - bt * kMaxHeads);
+  float s = 0.f;
+  if (hh < n_head) {
+    s = ub[hh];
+    if (has_pe)
+      for (int d = 0; d < D; ++d) s = fmaf(qk[hh * D + d], pe[bt * D + d], s);
+  }
+  cpos[i] = s;
+}
+
+}  // namespace
+
+int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* positions, float* ws,
+                 const LtaeWorkspace& lay, cudaStream_t stream) {
+  const int h = d.n_head, D = d.d_model, C = d.C, dk = d.d_k, dh = D / h;
+  const bool attn_only = (d.flags & C2S_LTAE_ATTN_ONLY) != 0;
+  const bool has_pe = d.pe_mode != C2S_PE_NONE;
+  float* qk = ws + lay.qk;
+
+  fold_qk_kernel<<<ceil_div(h * D, kPrepThreads), kPrepThreads, 0, stream>>>(p.query, p.key_weight, qk, h, dk, D);
+  C2S_LAUNCH_CHECK("ltae_fold_qk");
+  fold_u_kernel<<<ceil_div(C * kMaxHeads, kPrepThreads), kPrepThreads, 0, stream>>>(
+      qk, p.inconv_weight, p.in_norm_weight, ws + lay.u, h, C, D, d.has_inconv);
+  C2S_LAUNCH_CHECK("ltae_fold_u");
+  fold_ub_kernel<<<kMaxHeads, kPrepThreads, 0, stream>>>(qk, p.inconv_weight, p.inconv_bias, p.in_norm_bias,
+                                                         p.query, p.key_bias, ws + lay.ub, h, dk, C, D,
+                                                         d.has_inconv);
+  C2S_LAUNCH_CHECK("ltae_fold_ub");
+  if (!attn_only) {
+    if (d.has_inconv) {
+      transpose_kernel<<<ceil_div(D * C, kPrepThreads), kPrepThreads, 0, stream>>>(p.inconv_weight, ws + lay.wct, D, C);
+      C2S_LAUNCH_CHECK("ltae_transpose_inconv");
+    }
+    transpose_kernel<<<ceil_div(d.c_out * D, kPrepThreads), kPrepThreads, 0, stream>>>(p.mlp_weight, ws + lay.wmt,
+                                                                                      d.c_out, D);
+    C2S_LAUNCH_CHECK("ltae_transpose_mlp");
+    if (!(d.flags & C2S_LTAE_BN_BATCH_STATS)) {
+      fold_bn_kernel<<<ceil_div(d.c_out, kPrepThreads), kPrepThreads, 0, stream>>>(
+          p.bn_weight, p.bn_bias, p.bn_running_mean, p.bn_running_var, d.bn_eps, ws + lay.bnf, d.c_out);
+      C2S_LAUNCH_CHECK("ltae_fold_bn");
+    }
+  }
+  const size_t n_bt = static_cast<size_t>(d.B) * d.T;
+  if (has_pe) {
+    const int stride = d.pe_abs ? 2 : 1;
+    const size_t smem = static_cast<size_t>(dh) * sizeof(float);
+    if (d.pos_dtype == 0) {
+      pos_table_kernel<long long><<<static_cast<unsigned>(n_bt), kPrepThreads, smem, stream>>>(
+          static_cast<const long long*>(positions), stride, p.pe_denom, p.pe_fc_weight, p.pe_fc_bias,
+          p.pe_abs_fc_weight, p.pe_abs_fc_bias, ws + lay.pe, D, dh, d.pe_mode, d.pe_abs);
+    } else {
+      pos_table_kernel<float><<<static_cast<unsigned>(n_bt), kPrepThreads, smem, stream>>>(
+          static_cast<const float*>(positions), stride, p.pe_denom, p.pe_fc_weight, p.pe_fc_bias,
+          p.pe_abs_fc_weight, p.pe_abs_fc_bias, ws + lay.pe, D, dh, d.pe_mode, d.pe_abs);
+    }
+    C2S_LAUNCH_CHECK("ltae_pos_table");
+  }
+  fold_cpos_kernel<<<ceil_div(n_bt * kMaxHeads, kPrepThreads), kPrepThreads, 0, stream>>>(
+      qk, ws + lay.ub, ws + lay.pe, ws + lay.cpos, h, D, n_bt, has_pe ? 1 : 0);
+  C2S_LAUNCH_CHECK("ltae_fold_cpos");
+  return C2S_OK;
+}
+
+}  // namespace c2s

@@ -1,0 +1,161 @@
+"""Tensor-level entry points over the C ABI (``include/crop2seg_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every arithmetic step runs
+in ``libcrop2seg_b200.so``.  Inputs must live on a CUDA device -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_AGG_MODES = {"att_group": _lib.AGG_ATT_GROUP, "att_mean": _lib.AGG_ATT_MEAN, "mean": _lib.AGG_MEAN}
+_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"crop2seg_b200: {name} is on {t.device}; the operators are CUDA (sm_100a) only and have no CPU fallback")
+
+
+def _dtype_code(t: torch.Tensor, name: str) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"crop2seg_b200: {name} has dtype {t.dtype}; supported: float32, bfloat16") from None
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _mask_u8(pad_mask: Optional[torch.Tensor], b: int, t: int, device) -> Optional[torch.Tensor]:
+    if pad_mask is None:
+        return None
+    if tuple(pad_mask.shape) != (b, t):
+        raise RuntimeError(f"crop2seg_b200: pad_mask has shape {tuple(pad_mask.shape)}, expected {(b, t)}")
+    m = pad_mask.to(device=device)
+    if m.dtype != torch.bool:
+        m = m != 0
+    return m.contiguous().view(torch.uint8)
+
+
+def temporal_aggregate(x: torch.Tensor, pad_mask: Optional[torch.Tensor] = None,
+                       attn_mask: Optional[torch.Tensor] = None, mode: str = "mean") -> torch.Tensor:
+    """``TemporalAggregator(mode).forward(x, pad_mask, attn_mask)`` (temporal_aggregator.py:14-77).
+
+    x[B,T,C,H,W] float32/bfloat16, attn_mask[h,B,T,ha,wa] (float32 used as is), pad_mask[B,T] bool.
+    Returns out[B,C,H,W] in x's dtype.  One kernel launch; no host synchronisation.
+    """
+    if mode not in _AGG_MODES:
+        raise ValueError(f"unknown aggregation mode {mode!r}")
+    if x.dim() != 5:
+        raise RuntimeError(f"crop2seg_b200: x must be [B,T,C,H,W], got {tuple(x.shape)}")
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    b, t, c, h, w = x.shape
+    desc = _lib.AggDesc(B=b, T=t, C=c, H=h, W=w, n_heads=1, ha=1, wa=1, mode=_AGG_MODES[mode],
+                        dtype=_dtype_code(x, "x"))
+    attn = None
+    if mode != "mean":
+        if attn_mask is None:
+            raise RuntimeError(f"crop2seg_b200: mode {mode!r} needs attn_mask")
+        if attn_mask.dim() != 5 or attn_mask.shape[1] != b or attn_mask.shape[2] != t:
+            raise RuntimeError(
+                f"crop2seg_b200: attn_mask must be [h,{b},{t},ha,wa], got {tuple(attn_mask.shape)}")
+        attn = attn_mask.to(device=x.device, dtype=torch.float32).contiguous()
+        desc.n_heads, desc.ha, desc.wa = attn.shape[0], attn.shape[3], attn.shape[4]
+    pad = _mask_u8(pad_mask, b, t, x.device)
+    out = torch.empty((b, c, h, w), dtype=x.dtype, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.c2s_agg_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+        status = lib.c2s_agg_forward(ctypes.byref(desc), x.data_ptr(), _ptr(attn), _ptr(pad), out.data_ptr(),
+                                     _ptr(ws), ws_bytes, _stream(x.device))
+    _lib.check(status, "c2s_agg_forward")
+    return out
+
+
+def _f32(t: Optional[torch.Tensor], device, keep) -> Optional[int]:
+    """Device pointer of a float32, contiguous view of a parameter (kept alive in ``keep``)."""
+    if t is None:
+        return None
+    v = t.detach()
+    if v.device != device or v.dtype != torch.float32 or not v.is_contiguous():
+        v = v.to(device=device, dtype=torch.float32).contiguous()
+    keep.append(v)
+    return v.data_ptr()
+
+
+def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: Optional[torch.Tensor],
+                 params: Dict[str, Optional[torch.Tensor]], *, n_head: int, d_k: int, d_model: int,
+                 has_inconv: bool, c_out: int, pe_mode: int, pe_abs: bool = False, attn_only: bool = False,
+                 need_attn: bool = True, zero_padded: bool = False, bn_batch_stats: bool = False,
+                 gn_eps: float = 1e-5, bn_eps: float = 1e-5
+                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[Tuple[torch.Tensor, torch.Tensor]]]:
+    """Fused ``LTAE.forward`` / ``LTAE4WTAE.forward`` (tae.py:451-504, 589-635).
+
+    ``params`` maps the field names of ``c2s_ltae_params`` to tensors (or None).
+    Returns ``(out[B,c_out,H,W] | None, attn[h,B,T,H,W] | None, (batch_mean, batch_var) | None)``.
+    """
+    if x.dim() != 5:
+        raise RuntimeError(f"crop2seg_b200: x must be [B,T,C,H,W], got {tuple(x.shape)}")
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    dev = x.device
+    b, t, c, h, w = x.shape
+    flags = 0
+    if attn_only:
+        flags |= _lib.LTAE_ATTN_ONLY
+    if not need_attn:
+        flags |= _lib.LTAE_SKIP_ATTN_STORE
+    if zero_padded:
+        flags |= _lib.LTAE_ZERO_PADDED
+    if bn_batch_stats and not attn_only:
+        flags |= _lib.LTAE_BN_BATCH_STATS
+    pos = None
+    pos_dtype = 0
+    if pe_mode != _lib.PE_NONE:
+        if positions is None:
+            raise RuntimeError("crop2seg_b200: batch_positions is required when positional encoding is enabled")
+        want = (b, t, 2) if pe_abs else (b, t)
+        if tuple(positions.shape) != want:
+            raise RuntimeError(f"crop2seg_b200: batch_positions has shape {tuple(positions.shape)}, expected {want}")
+        pos = positions.to(device=dev)
+        if pos.dtype.is_floating_point:
+            pos = pos.to(torch.float32)
+            pos_dtype = 1
+        else:
+            pos = pos.to(torch.int64)
+        pos = pos.contiguous()
+    desc = _lib.LtaeDesc(B=b, T=t, C=c, H=h, W=w, n_head=n_head, d_k=d_k, d_model=d_model,
+                         c_out=0 if attn_only else c_out, has_inconv=int(has_inconv), pe_mode=pe_mode,
+                         pe_abs=int(pe_abs), pos_dtype=pos_dtype, dtype=_dtype_code(x, "x"), flags=flags,
+                         gn_eps=gn_eps, bn_eps=bn_eps)
+    keep = []
+    cparams = _lib.LtaeParams(**{k: _f32(params.get(k), dev, keep) for k in _lib.LTAE_PARAM_FIELDS})
+    pad = _mask_u8(pad_mask, b, t, dev)
+    out = None if attn_only else torch.empty((b, c_out, h, w), dtype=x.dtype, device=dev)
+    attn = torch.empty((n_head, b, t, h, w), dtype=torch.float32, device=dev) if need_attn else None
+    stats = None
+    if flags & _lib.LTAE_BN_BATCH_STATS:
+        stats = (torch.empty(c_out, dtype=torch.float32, device=dev),
+                 torch.empty(c_out, dtype=torch.float32, device=dev))
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.c2s_ltae_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        status = lib.c2s_ltae_forward(ctypes.byref(desc), ctypes.byref(cparams), x.data_ptr(), _ptr(pos), _ptr(pad),
+                                      _ptr(out), _ptr(attn), _ptr(stats[0]) if stats else None,
+                                      _ptr(stats[1]) if stats else None, ws.data_ptr(), ws_bytes, _stream(dev))
+    _lib.check(status, "c2s_ltae_forward")
+    return out, attn, stats

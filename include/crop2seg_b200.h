@@ -1,0 +1,159 @@
+/*
+ * crop2seg_b200 -- C ABI of the B200-native L-TAE + TemporalAggregator hot path.
+ *
+ * Drop-in boundary for the temporal-attention bottleneck of Many98/Crop2Seg.  The
+ * reference has no native layer: its interface for this path is the Python
+ * nn.Module API.  Each entry point below names the reference
+ * call it replaces (paths relative to the reference checkout).  The Python modules
+ * in crop2seg_b200/ bind these symbols with ctypes and keep the reference's
+ * constructor / forward / state_dict contract; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense, row-major ("contiguous") in the shapes given;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success, a C2S_ERR_* code otherwise, never aborts;
+ *     c2s_last_error() returns a thread-local, human readable message;
+ *   - nothing here synchronises the host with the device.
+ */
+#ifndef CROP2SEG_B200_H_
+#define CROP2SEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2S_ABI_VERSION 1
+
+enum c2s_status {
+  C2S_OK = 0,
+  C2S_ERR_BAD_ARGUMENT = 1,  /* NULL pointer, non-positive size, inconsistent descriptor      */
+  C2S_ERR_UNSUPPORTED = 2,   /* valid but not implemented by the kernels (message says which) */
+  C2S_ERR_CUDA = 3,          /* a CUDA runtime call or kernel launch failed                   */
+  C2S_ERR_NO_DEVICE = 4      /* no sm_100 device / wrong architecture                         */
+};
+
+enum c2s_dtype { C2S_F32 = 0, C2S_BF16 = 1 };
+
+/* TemporalAggregator(mode) -- temporal_aggregator.py:10 */
+enum c2s_agg_mode { C2S_AGG_ATT_GROUP = 0, C2S_AGG_ATT_MEAN = 1, C2S_AGG_MEAN = 2 };
+
+/* positional encoder variant chosen by LTAE.__init__ -- tae.py:406-426 */
+enum c2s_pe_mode {
+  C2S_PE_NONE = 0,            /* positional_encoding=False                              */
+  C2S_PE_SINUSOID = 1,        /* PositionalEncoder                positional_encoding.py:7  */
+  C2S_PE_SINUSOID_LINEAR = 2, /* PositionalEncoder(add_linear)    positional_encoding.py:39 */
+  C2S_PE_DOY_TABLE = 3        /* AbsolutePositionalEncoder        positional_encoding.py:46 */
+};
+
+enum c2s_ltae_flags {
+  C2S_LTAE_ATTN_ONLY = 1 << 0,       /* LTAE4WTAE: return the attention masks only (tae.py:589-635) */
+  C2S_LTAE_SKIP_ATTN_STORE = 1 << 1, /* caller does not consume attn (model-level return_att=False)  */
+  C2S_LTAE_ZERO_PADDED = 1 << 2,     /* caller guarantees x == 0 on padded frames (temp_shared_block.py:30-40):
+                                        padded frames are then never read                             */
+  C2S_LTAE_BN_BATCH_STATS = 1 << 3   /* training: BatchNorm1d uses batch statistics (tae.py:445)     */
+};
+
+/* ------------------------------------------------------------------------------------------
+ * TemporalAggregator.forward(x, pad_mask, attn_mask)          temporal_aggregator.py:14-77
+ * ---------------------------------------------------------------------------------------- */
+typedef struct c2s_agg_desc {
+  int32_t B, T, C, H, W; /* x[B,T,C,H,W]                                                      */
+  int32_t n_heads;       /* attn[n_heads,B,T,ha,wa]  (ignored for C2S_AGG_MEAN)               */
+  int32_t ha, wa;        /* attention resolution                                              */
+  int32_t mode;          /* enum c2s_agg_mode                                                 */
+  int32_t dtype;         /* enum c2s_dtype of x and out; attn is always float32               */
+} c2s_agg_desc;
+
+/* Scratch bytes needed by c2s_agg_forward for this descriptor (0 for the shipped models:
+ * only att_mean and the AvgPool2d branch stage a reduced attention map). */
+size_t c2s_agg_workspace_bytes(const c2s_agg_desc* desc);
+
+/* out[B,C,H,W] = sum_t resize(attn)[c // (C/n_heads), b, t] * (pad ? 0 : 1) * x[b,t,c]
+ * pad_mask: uint8 [B,T] (non-zero = padded frame) or NULL.  Padded frames of x are not read. */
+int c2s_agg_forward(const c2s_agg_desc* desc, const void* x, const float* attn,
+                    const uint8_t* pad_mask, void* out, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LTAE / LTAE4WTAE                                             tae.py:349-635
+ * ---------------------------------------------------------------------------------------- */
+typedef struct c2s_ltae_desc {
+  int32_t B, T, C, H, W; /* x[B,T,C,H,W], C = in_channels                                     */
+  int32_t n_head;        /* tae.py:358                                                        */
+  int32_t d_k;           /* tae.py:359                                                        */
+  int32_t d_model;       /* width after inconv; == C when has_inconv == 0 (tae.py:398-403)    */
+  int32_t c_out;         /* mlp[-1]; ignored with C2S_LTAE_ATTN_ONLY                          */
+  int32_t has_inconv;    /* d_model is not None                                               */
+  int32_t pe_mode;       /* enum c2s_pe_mode                                                  */
+  int32_t pe_abs;        /* use_abs_rel_enc: add AbsolutePositionalEncoder(positions[...,1])  */
+  int32_t pos_dtype;     /* 0: int64 positions, 1: float32 positions                          */
+  int32_t dtype;         /* enum c2s_dtype of x and out; attn is always float32               */
+  int32_t flags;         /* enum c2s_ltae_flags                                               */
+  float gn_eps;          /* 1e-5 (nn.GroupNorm default)                                       */
+  float bn_eps;          /* 1e-5 (nn.BatchNorm1d default)                                     */
+} c2s_ltae_desc;
+
+/* state_dict tensors, float32, reference shapes. NULL where absent. */
+typedef struct c2s_ltae_params {
+  const float* in_norm_weight;   /* [C]                                                        */
+  const float* in_norm_bias;     /* [C]                                                        */
+  const float* inconv_weight;    /* [d_model, C]  (Conv1d weight [d_model,C,1])                */
+  const float* inconv_bias;      /* [d_model]                                                  */
+  const float* query;            /* attention_head.Q [n_head, 1, d_k]                          */
+  const float* key_weight;       /* attention_head.fc1_k.weight [n_head*d_k, d_model]          */
+  const float* key_bias;         /* attention_head.fc1_k.bias   [n_head*d_k]                   */
+  const float* mlp_weight;       /* mlp.0.weight [c_out, d_model]                              */
+  const float* mlp_bias;         /* mlp.0.bias   [c_out]                                       */
+  const float* bn_weight;        /* mlp.2.weight [c_out]                                       */
+  const float* bn_bias;          /* mlp.2.bias   [c_out]                                       */
+  const float* bn_running_mean;  /* mlp.2.running_mean [c_out]                                 */
+  const float* bn_running_var;   /* mlp.2.running_var  [c_out]                                 */
+  const float* out_norm_weight;  /* [c_out]                                                    */
+  const float* out_norm_bias;    /* [c_out]                                                    */
+  const float* pe_denom;         /* PositionalEncoder.denom [d_model/n_head] (plain attribute) */
+  const float* pe_fc_weight;     /* positional_encoder.fc.weight: [d_model,d_model] (add_linear)
+                                    or [d_model/n_head, 365] (C2S_PE_DOY_TABLE)                */
+  const float* pe_fc_bias;
+  const float* pe_abs_fc_weight; /* positional_encoder_abs.fc.weight [d_model/n_head, 365]     */
+  const float* pe_abs_fc_bias;
+} c2s_ltae_params;
+
+/* Scratch bytes for c2s_ltae_forward (folded weights + per-sample positional tables). */
+size_t c2s_ltae_workspace_bytes(const c2s_ltae_desc* desc);
+
+/* LTAE.forward(x, batch_positions, pad_mask) -> (out, attn)            tae.py:451-504
+ * LTAE4WTAE.forward(...) -> attn   (flags & C2S_LTAE_ATTN_ONLY)         tae.py:589-635
+ *   positions : int64 or float32 [B,T] ([B,T,2] when pe_abs), NULL iff pe_mode == NONE
+ *   pad_mask  : uint8 [B,T] or NULL
+ *   out       : [B,c_out,H,W] in desc->dtype (NULL with ATTN_ONLY)
+ *   attn      : float32 [n_head,B,T,H,W] (may be NULL with SKIP_ATTN_STORE)
+ *   bn_batch_mean/var : float32 [c_out], written only with BN_BATCH_STATS (biased variance);
+ *                       the caller updates the running statistics (tae.py:445 semantics)
+ * Day-of-year positions outside [0,364] make the call fail with C2S_ERR_BAD_ARGUMENT only
+ * when they can be checked on the host; on the device they are clamped -- the Python
+ * wrapper validates the range like F.one_hot does (positional_encoding.py:63). */
+int c2s_ltae_forward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const void* x,
+                     const void* positions, const uint8_t* pad_mask, void* out, float* attn,
+                     float* bn_batch_mean, float* bn_batch_var, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * library services
+ * ---------------------------------------------------------------------------------------- */
+int c2s_abi_version(void);
+const char* c2s_last_error(void);
+/* Number of kernels this library launched on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t c2s_launch_count(void);
+void c2s_reset_launch_count(void);
+/* Name of the kernel variant the last forward call on this thread selected (diagnostics). */
+const char* c2s_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROP2SEG_B200_H_ */

@@ -59,3 +59,29 @@ def test_softmax_sums_to_one():
     _, attn = ltae_forward(_cfg(cfg["kwargs"]), params, inp["x"], inp["positions"], inp["pad_mask"])
     s = attn.sum(axis=2)
     assert np.all(np.abs(s - 1.0) < 1e-5)
+
+
+# ---- the torch-CPU port (bench.py's cpu_baseline and a second oracle) is pinned the same way -------------
+@pytest.mark.parametrize("name", [n for n in fixture_names(["ltae_", "wtae_"])
+                                  if n not in ("ltae_two_queries", "ltae_train_bn")])
+def test_torch_port_ltae_matches_reference(name):
+    from oracle.torch_port import ltae_forward_torch
+    cfg, inp, params, outs = load(name)
+    kw = dict(cfg["kwargs"])
+    if cfg["kind"] != "ltae":
+        kw["mlp"] = [kw.get("d_model") or kw["in_channels"], 1]
+    res = ltae_forward_torch(_cfg(kw), params, inp["x"], inp.get("positions"), inp.get("pad_mask"),
+                             attn_only=cfg["kind"] != "ltae")
+    if cfg["kind"] == "ltae":
+        assert rel_err(res[0].numpy(), outs["out"]) < 2e-5
+        assert rel_err(res[1].numpy(), outs["attn"]) < TOL
+    else:
+        assert rel_err(res.numpy(), outs["attn"]) < TOL
+
+
+@pytest.mark.parametrize("name", fixture_names(["agg_"]))
+def test_torch_port_aggregator_matches_reference(name):
+    from oracle.torch_port import temporal_aggregator_torch
+    cfg, inp, _, outs = load(name)
+    out = temporal_aggregator_torch(inp["x"], inp.get("pad_mask"), inp["attn"], cfg["mode"])
+    assert rel_err(out.numpy(), outs["out"]) < TOL
