@@ -14,6 +14,7 @@
 // per (frame, channel); CPT*U independent 16-byte loads are in flight per thread.
 //
 // HBM roofline: algorithmic bytes = e*T_valid*C*H*W (x) + e*C*H*W (out) per sample, see DESIGN.md.
+#include <cstdlib>
 #include <type_traits>
 
 #include "c2s_common.cuh"
@@ -271,6 +272,214 @@ __global__ void avg_pool_kernel(const float* __restrict__ in, float* __restrict_
   out[i] = s / static_cast<float>(k * k);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Pipelined variant: the feature stream goes HBM -> shared memory through the bulk-copy engine
+// (cp.async.bulk + mbarrier transaction counts), so the number of bytes in flight per SM is set by the
+// ring of stages (2 CTAs x 6 stages x 16 KB = 192 KB) instead of by registers.  One producer thread
+// issues four 4 KB row copies (the 4 channels of one attention head x PB pixels) per frame; the
+// consumer warps read their 16-byte vectors back with conflict-free LDS.128 and release the stage.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPipeCPT = 4;
+constexpr int kPipeMaxConsumers = 256;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, UBLKCP in SASS)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+template <typename T, int S>
+__global__ void __launch_bounds__(kPipeMaxConsumers + 32, 2) agg_pipe_kernel(const AggArgs a, int n_stages,
+                                                                            int n_consumers, int pblocks) {
+  constexpr int VEC = Elem<T>::kVec;
+  constexpr int NCOL = Window<VEC, S>::kCols;
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  __shared__ short frames[kAggMaxT];
+  __shared__ int n_frames_s;
+  __shared__ __align__(8) unsigned long long bars[2 * 16];  // full[0..15], empty[0..15]
+
+  const int b = blockIdx.y;
+  const int cchunk = blockIdx.x / pblocks;
+  const int pblk = blockIdx.x - cchunk * pblocks;
+  const int c0 = cchunk * kPipeCPT;
+  const int pb = n_consumers * VEC;                 // pixels per block
+  const uint32_t row_bytes = pb * sizeof(T);        // one channel row of the block
+  const uint32_t stage_bytes = kPipeCPT * row_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cwarps = n_consumers >> 5;
+
+  if (threadIdx.x < 32) {
+    int count = 0;
+    for (int base = 0; base < a.T; base += 32) {
+      const int t = base + threadIdx.x;
+      const bool valid = t < a.T && (a.pad == nullptr || a.pad[b * a.T + t] == 0);
+      const unsigned m = __ballot_sync(0xffffffffu, valid);
+      if (valid) frames[count + __popc(m & ((1u << threadIdx.x) - 1u))] = static_cast<short>(t);
+      count += __popc(m);
+    }
+    if (threadIdx.x == 0) {
+      n_frames_s = count;
+      for (int s = 0; s < n_stages; ++s) {
+        mbar_init(smem_addr(&bars[s]), 1);
+        mbar_init(smem_addr(&bars[16 + s]), n_cwarps);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  const int n_frames = n_frames_s;
+  const size_t frame_stride = static_cast<size_t>(a.C) * a.hw;
+  const uint32_t stage0 = smem_addr(pipe_smem);
+
+  if (warp == n_cwarps) {  // ---- producer -------------------------------------------------------------
+    if (lane == 0) {
+      const T* src = static_cast<const T*>(a.x) + static_cast<size_t>(b) * a.T * frame_stride +
+                     static_cast<size_t>(c0) * a.hw + static_cast<size_t>(pblk) * pb;
+      for (int i = 0; i < n_frames; ++i) {
+        const int s = i % n_stages, round = i / n_stages;
+        if (round > 0) mbar_wait(smem_addr(&bars[16 + s]), (round - 1) & 1);
+        const uint32_t full = smem_addr(&bars[s]);
+        mbar_expect_tx(full, stage_bytes);
+        const T* fp = src + static_cast<size_t>(frames[i]) * frame_stride;
+#pragma unroll
+        for (int k = 0; k < kPipeCPT; ++k)
+          bulk_g2s(stage0 + s * stage_bytes + k * row_bytes, fp + static_cast<size_t>(k) * a.hw, row_bytes, full);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers -------------------------------------------------------------------------------------
+  const int p0 = pblk * pb + threadIdx.x * VEC;
+  const int y = p0 / a.W;
+  const int x0 = p0 - y * a.W;
+  int iy0, iy1;
+  float ly1;
+  source_index(a.sy, y, a.ha, iy0, iy1, ly1);
+  const float ly0 = 1.f - ly1;
+  const int row0 = iy0 * a.wa, row1 = iy1 * a.wa;
+  float lx1[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    int i0, i1;
+    source_index(a.sx, x0 + j, a.wa, i0, i1, lx1[j]);
+  }
+  int col[NCOL];
+  {
+    int cmin = x0 / S - 1;
+    if constexpr (VEC < S) cmin += ((x0 % S) >= S / 2) ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+      int cj = cmin + j;
+      cj = cj < 0 ? 0 : cj;
+      col[j] = cj > a.wa - 1 ? a.wa - 1 : cj;
+    }
+  }
+  const int amap = a.ha * a.wa;
+  const float* ab = a.attn + (static_cast<size_t>(c0 / a.cpg) * a.B + b) * a.T * amap;
+
+  float acc[kPipeCPT][VEC];
+#pragma unroll
+  for (int k = 0; k < kPipeCPT; ++k)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
+
+  float top_n[NCOL], bot_n[NCOL];
+  if (n_frames > 0) {
+    const float* ap = ab + static_cast<size_t>(frames[0]) * amap;
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) top_n[j] = __ldg(ap + row0 + col[j]), bot_n[j] = __ldg(ap + row1 + col[j]);
+  }
+  const uint32_t my_off = threadIdx.x * 16;
+  for (int i = 0; i < n_frames; ++i) {
+    float r[NCOL];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) r[j] = fmaf(ly1, bot_n[j], ly0 * top_n[j]);
+    if (i + 1 < n_frames) {  // attention taps of the next frame travel while this one is consumed
+      const float* ap = ab + static_cast<size_t>(frames[i + 1]) * amap;
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) top_n[j] = __ldg(ap + row0 + col[j]), bot_n[j] = __ldg(ap + row1 + col[j]);
+    }
+    const int s = i % n_stages;
+    mbar_wait(smem_addr(&bars[s]), (i / n_stages) & 1);
+    uint4 xv[kPipeCPT];
+    const uint32_t base = stage0 + s * stage_bytes + my_off;
+#pragma unroll
+    for (int k = 0; k < kPipeCPT; ++k) xv[k] = lds_v4(base + k * row_bytes);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_addr(&bars[16 + s]));  // the stage's data now lives in registers
+
+    float w[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int i0w = (VEC >= S) ? (j / S + ((j % S) < S / 2 ? 0 : 1)) : 0;
+      w[j] = fmaf(lx1[j], r[i0w + 1], (1.f - lx1[j]) * r[i0w]);
+    }
+#pragma unroll
+    for (int k = 0; k < kPipeCPT; ++k) {
+      float f[VEC];
+      Elem<T>::unpack(xv[k], f);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[k][j] = fmaf(w[j], f[j], acc[k][j]);
+    }
+  }
+  T* op = static_cast<T*>(a.out) + (static_cast<size_t>(b) * a.C + c0) * a.hw + p0;
+#pragma unroll
+  for (int k = 0; k < kPipeCPT; ++k) PixelVec<T, VEC>::store(op + static_cast<size_t>(k) * a.hw, acc[k]);
+}
+
+template <typename T, int S>
+int launch_pipe_s(const AggArgs& a, int n_consumers, int n_stages, cudaStream_t stream, const char* name) {
+  constexpr int VEC = Elem<T>::kVec;
+  const int pblocks = a.hw / (n_consumers * VEC);
+  const size_t smem = static_cast<size_t>(n_stages) * kPipeCPT * n_consumers * 16;
+  static bool attr_done = false;  // per instantiation; the value is the same on every call
+  if (!attr_done) {
+    C2S_CUDA(cudaFuncSetAttribute(agg_pipe_kernel<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 16384));
+    attr_done = true;
+  }
+  dim3 grid((a.C / kPipeCPT) * pblocks, a.B);
+  agg_pipe_kernel<T, S><<<grid, n_consumers + 32, smem, stream>>>(a, n_stages, n_consumers, pblocks);
+  C2S_LAUNCH_CHECK(name);
+  return C2S_OK;
+}
+
+template <typename T>
+int launch_pipe(const AggArgs& a, int s, int n_consumers, int n_stages, cudaStream_t stream) {
+  switch (s) {
+    case 2: return launch_pipe_s<T, 2>(a, n_consumers, n_stages, stream, "agg_forward_pipe<x2>");
+    case 4: return launch_pipe_s<T, 4>(a, n_consumers, n_stages, stream, "agg_forward_pipe<x4>");
+    default: return launch_pipe_s<T, 8>(a, n_consumers, n_stages, stream, "agg_forward_pipe<x8>");
+  }
+}
+
 template <typename T, int VEC, int CPT, int S>
 int launch_variant(const AggArgs& a, cudaStream_t stream, const char* name) {
   dim3 grid(ceil_div(a.items_per_b, kAggThreads), a.B);
@@ -405,6 +614,21 @@ int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, con
   a.pv_per_plane = a.hw / vec;
   a.items_per_b = (d->C / cpt) * a.pv_per_plane;
   if (vec == 1 && scale_class > 0) scale_class = 0;
+
+  // pipelined (bulk-copy) variant: power-of-two up-sampling, 4-channel head groups, whole 16-byte vectors
+  const bool no_pipe = getenv("C2S_AGG_NO_PIPE") != nullptr;  // test hook: A/B against the register kernel
+  const int env_stages = getenv("C2S_AGG_STAGES") ? atoi(getenv("C2S_AGG_STAGES")) : 0;
+  if (!no_pipe && scale_class > 0 && vec == vec_full && a.cpg % kPipeCPT == 0) {
+    const int vecs = a.hw / vec;
+    int n_consumers = vecs < kPipeMaxConsumers ? vecs : kPipeMaxConsumers;
+    if (n_consumers >= 64 && n_consumers % 32 == 0 && vecs % n_consumers == 0) {
+      int n_stages = env_stages > 0 ? env_stages : (6 * kPipeMaxConsumers) / n_consumers;
+      n_stages = n_stages > 16 ? 16 : (n_stages < 2 ? 2 : n_stages);
+      while (static_cast<size_t>(n_stages) * kPipeCPT * n_consumers * 16 > 12 * 16384) --n_stages;
+      return bf16 ? launch_pipe<__nv_bfloat16>(a, scale_class, n_consumers, n_stages, stream)
+                  : launch_pipe<float>(a, scale_class, n_consumers, n_stages, stream);
+    }
+  }
 
   if (bf16) {
     return vec == 8 ? launch_cpt<__nv_bfloat16, 8>(a, cpt, scale_class, stream)

