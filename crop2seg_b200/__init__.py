@@ -12,7 +12,7 @@ The arithmetic lives in ``lib/libcrop2seg_b200.so`` (``include/crop2seg_b200.h``
 """
 from .modules import LTAE, LTAE4WTAE, TemporalAggregator  # noqa: F401
 from .install import install, uninstall  # noqa: F401
-from .sharding import shard_patches, shard_bounds  # noqa: F401
+from .sharding import gather_shards, shard_bounds, shard_patches  # noqa: F401
 from . import ops  # noqa: F401
 
-__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "ops"]
+__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "ops"]
