@@ -622,7 +622,7 @@ int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, con
     const int vecs = a.hw / vec;
     int n_consumers = vecs < kPipeMaxConsumers ? vecs : kPipeMaxConsumers;
     if (n_consumers >= 64 && n_consumers % 32 == 0 && vecs % n_consumers == 0) {
-      int n_stages = env_stages > 0 ? env_stages : (6 * kPipeMaxConsumers) / n_consumers;
+      int n_stages = env_stages > 0 ? env_stages : 4;  // 4 x 16 KB: three CTAs per SM, 192 KB of loads in flight
       n_stages = n_stages > 16 ? 16 : (n_stages < 2 ? 2 : n_stages);
       while (static_cast<size_t>(n_stages) * kPipeCPT * n_consumers * 16 > 12 * 16384) --n_stages;
       return bf16 ? launch_pipe<__nv_bfloat16>(a, scale_class, n_consumers, n_stages, stream)

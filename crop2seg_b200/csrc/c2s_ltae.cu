@@ -562,13 +562,14 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
                 "c2s_ltae_forward: workspace of %zu bytes needed, %zu given", lay.total * sizeof(float),
                 workspace_bytes);
   float* ws = static_cast<float*>(workspace);
-  status = ltae_prepare(d, p, positions, ws, lay, stream);
+  const bool force_general = getenv("C2S_LTAE_FORCE_GENERAL") != nullptr;  // test hook: compare both kernels
+  const bool use_mma = !force_general && ltae_mma_eligible(d, x, out);
+  status = ltae_prepare(d, p, positions, ws, lay, /*need_transposed=*/!use_mma, stream);
   if (status != C2S_OK) return status;
 
   const int hw = d.H * d.W;
   float* ypre = train ? ws + lay.ypre : nullptr;
-  const bool force_general = getenv("C2S_LTAE_FORCE_GENERAL") != nullptr;  // test hook: compare both kernels
-  if (!force_general && ltae_mma_eligible(d, x, out)) {
+  if (use_mma) {
     status = ltae_mma_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.frag, stream);
     if (status != C2S_OK) return status;
   } else {

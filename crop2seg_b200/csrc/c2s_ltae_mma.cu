@@ -73,8 +73,8 @@ struct Smem {
   static constexpr int oOsHi = oPa + kH * 16 * kPix * 4;        // bf16 [8][kOsRow]
   static constexpr int oOsLo = oOsHi + kPix * kOsRow * 2;
   static constexpr int oYs = oOsLo + kPix * kOsRow * 2;         // float [256][8]
-  static constexpr int oMisc = oYs + 256 * kPix * 4;            // masks, frame count
-  static constexpr int kTotal = oMisc + 64;
+  static constexpr int oUf = oYs + 256 * kPix * 4;              // float [C/16][32][8] score weights (A-fragment order)
+  static constexpr int kTotal = oUf + (C / 16) * 32 * 8 * 4;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   __nv_bfloat16* s_os_hi = reinterpret_cast<__nv_bfloat16*>(smem + S::oOsHi);
   __nv_bfloat16* s_os_lo = reinterpret_cast<__nv_bfloat16*>(smem + S::oOsLo);
   float* s_ys = reinterpret_cast<float*>(smem + S::oYs);
-  unsigned long long* s_masks = reinterpret_cast<unsigned long long*>(smem + S::oMisc);  // [0] live, [1] padded
+  float* s_uf = reinterpret_cast<float*>(smem + S::oUf);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / a.tiles_per_b;
@@ -137,94 +137,95 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   const size_t frame_stride = static_cast<size_t>(C) * a.hw;
   const __nv_bfloat16* xb = a.x + static_cast<size_t>(b) * a.T * frame_stride + pix0;
 
-  // ---- phase 0: frame masks, per-sample score constants and positional table ------------------------
-  if (warp == 0) {
-    unsigned long long live = 0, padded = 0;
-    for (int base = 0; base < kTP; base += 32) {
-      const int t = base + lane;
-      const bool pd = t < a.T && a.pad != nullptr && a.pad[b * a.T + t] != 0;
-      const bool lv = t < a.T && !(pd && a.zero_padded);
-      live |= static_cast<unsigned long long>(__ballot_sync(0xffffffffu, lv)) << base;
-      padded |= static_cast<unsigned long long>(__ballot_sync(0xffffffffu, pd)) << base;
-    }
-    if (lane == 0) s_masks[0] = live, s_masks[1] = padded;
+  // ---- phase 0: frame masks (every warp derives them itself: no block barrier before the loads go out) ----
+  unsigned long long live_mask = 0, pad_mask = 0;
+#pragma unroll
+  for (int base = 0; base < kTP; base += 32) {
+    const int t = base + lane;
+    const bool pd = t < a.T && a.pad != nullptr && __ldg(a.pad + b * a.T + t) != 0;
+    const bool lv = t < a.T && !(pd && a.zero_padded);
+    live_mask |= static_cast<unsigned long long>(__ballot_sync(0xffffffffu, lv)) << base;
+    pad_mask |= static_cast<unsigned long long>(__ballot_sync(0xffffffffu, pd)) << base;
   }
-  for (int i = tid; i < kH * kTP; i += kThreads) {
-    const int t = i / kH, h = i - t * kH;
-    s_cpos[h * 66 + t] = t < a.T ? __ldg(a.cpos + (static_cast<size_t>(b) * a.T + t) * kMaxHeads + h) : 0.f;
-  }
-  if (!a.attn_only) {
-    for (int i = tid; i < 16 * kTP; i += kThreads) {
-      const int t = i / 16, d = i - t * 16;
-      const float v = (a.pe != nullptr && t < a.T) ? __ldg(a.pe + (static_cast<size_t>(b) * a.T + t) * kD + d) : 0.f;
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      s_pe_hi[d * kRow + t] = hi;
-      s_pe_lo[d * kRow + t] = __float2bfloat16_rn(v - __bfloat162float(hi));
-    }
-  }
-  __syncthreads();
-  const unsigned long long live_mask = s_masks[0], pad_mask = s_masks[1];
   const int n_live = __popcll(live_mask);
 
   // ---- phase 1: stage x transposed into X2[p][c][t] and accumulate GroupNorm statistics -------------
   {
+    constexpr int NCB = C / 64;  // 8-channel blocks per warp
     const int cc = lane & 7, tp = lane >> 3;
-    for (int cb = warp; cb < C / 8; cb += kThreads / 32) {
-      const int c = cb * 8 + cc;
+    // 1a: every global load of this warp's share is issued before anything is consumed (one latency per CTA)
+    uint4 v[NCB][8][2];
+    uint4 pv[NCB];
+#pragma unroll
+    for (int n = 0; n < NCB; ++n) {
+      const int c = (warp + 8 * n) * 8 + cc;
       const int g = c / CPG;
       const __nv_bfloat16* xc = xb + static_cast<size_t>(c) * a.hw;
-      // pivot of the shifted sums: first live frame, first channel of the group (same for all lanes of a group)
-      float pivot[8];
-      {
-        uint4 pv = make_uint4(0, 0, 0, 0);
-        if (n_live > 0) {
-          const int t0 = __ffsll(static_cast<long long>(live_mask)) - 1;
-          pv = ld_stream_v4(xb + static_cast<size_t>(t0) * frame_stride + static_cast<size_t>(g * CPG) * a.hw);
-        }
-        Elem<__nv_bfloat16>::unpack(pv, pivot);
+      pv[n] = make_uint4(0, 0, 0, 0);
+      if (n_live > 0) {  // pivot of the shifted sums: first live frame, first channel of the group
+        const int t0 = __ffsll(static_cast<long long>(live_mask)) - 1;
+        pv[n] = ld_stream_v4(xb + static_cast<size_t>(t0) * frame_stride + static_cast<size_t>(g * CPG) * a.hw);
       }
+#pragma unroll
+      for (int tb = 0; tb < 8; ++tb) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int t = tb * 8 + tp * 2 + e;
+          v[n][tb][e] = make_uint4(0, 0, 0, 0);
+          if ((live_mask >> t) & 1ull) v[n][tb][e] = ld_stream_v4(xc + static_cast<size_t>(t) * frame_stride);
+        }
+      }
+    }
+    // 1b: per-sample constants go to shared memory while the feature loads are in flight
+    for (int i = tid; i < kH * kTP; i += kThreads) {
+      const int t = i / kH, h = i - t * kH;
+      s_cpos[h * 66 + t] = t < a.T ? __ldg(a.cpos + (static_cast<size_t>(b) * a.T + t) * kMaxHeads + h) : 0.f;
+    }
+    for (int i = tid; i < KS * 32 * 2; i += kThreads)
+      reinterpret_cast<float4*>(s_uf)[i] = __ldg(reinterpret_cast<const float4*>(a.ufrag) + i);
+    if (!a.attn_only) {
+      for (int i = tid; i < 16 * kTP; i += kThreads) {
+        const int t = i / 16, d = i - t * 16;
+        const float pe = (a.pe != nullptr && t < a.T) ? __ldg(a.pe + (static_cast<size_t>(b) * a.T + t) * kD + d) : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(pe);
+        s_pe_hi[d * kRow + t] = hi;
+        s_pe_lo[d * kRow + t] = __float2bfloat16_rn(pe - __bfloat162float(hi));
+      }
+    }
+    // 1c: statistics + transposed stores
+#pragma unroll
+    for (int n = 0; n < NCB; ++n) {
+      const int c = (warp + 8 * n) * 8 + cc;
+      const int g = c / CPG;
+      float pivot[8];
+      Elem<__nv_bfloat16>::unpack(pv[n], pivot);
       float s1[8], s2[8];
 #pragma unroll
       for (int p = 0; p < 8; ++p) s1[p] = 0.f, s2[p] = 0.f;
       __nv_bfloat16* xrow = X2 + static_cast<size_t>(c) * kRow;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint4 v[4][2];
-        bool lv[4][2];
+      for (int tb = 0; tb < 8; ++tb) {
+        const int t = tb * 8 + tp * 2;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int e = 0; e < 2; ++e) {
+          if ((live_mask >> (t + e)) & 1ull) {
+            float f[8];
+            Elem<__nv_bfloat16>::unpack(v[n][tb][e], f);
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int t = (half * 4 + q) * 8 + tp * 2 + e;
-            lv[q][e] = (live_mask >> t) & 1ull;
-            v[q][e] = make_uint4(0, 0, 0, 0);
-            if (lv[q][e]) v[q][e] = ld_stream_v4(xc + static_cast<size_t>(t) * frame_stride);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int t = (half * 4 + q) * 8 + tp * 2;
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            if (lv[q][e]) {
-              float f[8];
-              Elem<__nv_bfloat16>::unpack(v[q][e], f);
-#pragma unroll
-              for (int p = 0; p < 8; ++p) {
-                const float d = f[p] - pivot[p];
-                s1[p] += d;
-                s2[p] = fmaf(d, d, s2[p]);
-              }
+            for (int p = 0; p < 8; ++p) {
+              const float d = f[p] - pivot[p];
+              s1[p] += d;
+              s2[p] = fmaf(d, d, s2[p]);
             }
           }
-          const uint32_t wa[4] = {v[q][0].x, v[q][0].y, v[q][0].z, v[q][0].w};
-          const uint32_t wb[4] = {v[q][1].x, v[q][1].y, v[q][1].z, v[q][1].w};
+        }
+        const uint32_t wa[4] = {v[n][tb][0].x, v[n][tb][0].y, v[n][tb][0].z, v[n][tb][0].w};
+        const uint32_t wb[4] = {v[n][tb][1].x, v[n][tb][1].y, v[n][tb][1].z, v[n][tb][1].w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            // pixel 2i: low halves of (frame t, frame t+1); pixel 2i+1: high halves
-            *reinterpret_cast<uint32_t*>(xrow + static_cast<size_t>(2 * i) * C * kRow + t) = __byte_perm(wa[i], wb[i], 0x5410);
-            *reinterpret_cast<uint32_t*>(xrow + static_cast<size_t>(2 * i + 1) * C * kRow + t) = __byte_perm(wa[i], wb[i], 0x7632);
-          }
+        for (int i = 0; i < 4; ++i) {
+          // pixel 2i: low halves of (frame t, frame t+1); pixel 2i+1: high halves
+          *reinterpret_cast<uint32_t*>(xrow + static_cast<size_t>(2 * i) * C * kRow + t) = __byte_perm(wa[i], wb[i], 0x5410);
+          *reinterpret_cast<uint32_t*>(xrow + static_cast<size_t>(2 * i + 1) * C * kRow + t) = __byte_perm(wa[i], wb[i], 0x7632);
         }
       }
       // reduce over the lanes that share a group: all 32 (CPG = 8) or the 16 with the same cc / 4 (CPG = 4)
@@ -272,8 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
     const int mat = lane >> 3, mr = lane & 7;
 #pragma unroll 1
     for (int ks = 0; ks < KS; ++ks) {
-      const float4* up = reinterpret_cast<const float4*>(a.ufrag + (static_cast<size_t>(ks) * 32 + lane) * 8);
-      const float4 u0 = __ldg(up), u1 = __ldg(up + 1);
+      const float4* up = reinterpret_cast<const float4*>(s_uf + (ks * 32 + lane) * 8);
+      const float4 u0 = up[0], u1 = up[1];
       const int c_lo = ks * 16 + 2 * j;
       const int g0 = c_lo / CPG, g1 = (c_lo + 8) / CPG;
       const float r0 = s_rstd[g0 * kPix + p], r1 = s_rstd[g1 * kPix + p];
@@ -339,12 +340,13 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
     sa0 = 0.f, sa1 = 0.f;
+    const float inv0 = 1.f / d0, inv1 = 1.f / d1;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        sacc[nt][e] = sacc[nt][e] / d0;
-        sacc[nt][2 + e] = sacc[nt][2 + e] / d1;
+        sacc[nt][e] = sacc[nt][e] * inv0;
+        sacc[nt][2 + e] = sacc[nt][2 + e] * inv1;
         sa0 += sacc[nt][e], sa1 += sacc[nt][2 + e];
       }
     }
@@ -414,10 +416,11 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   __syncthreads();  // every warp is done with X2 (z tiles alias it) and the attention staging is complete
 
   if (store_attn) {  // attn[h, b, t, pix0 .. pix0 + 7]: 32-byte segments                    tae.py:490-493
-    for (int i = tid; i < kH * a.T * kPix; i += kThreads) {
-      const int pp = i & 7, ht = i >> 3;
-      const int h = ht / a.T, t = ht - h * a.T;
-      a.attn[((static_cast<size_t>(h) * a.B + b) * a.T + t) * a.hw + pix0 + pp] = s_as[pp * kAsP + h * 66 + t];
+    const int pp = lane & 7, tq = lane >> 3;
+    for (int h = warp; h < kH; h += kThreads / 32) {
+      float* dst = a.attn + (static_cast<size_t>(h) * a.B + b) * a.T * a.hw + pix0 + pp;
+      const float* src = s_as + pp * kAsP + h * 66;
+      for (int t = tq; t < a.T; t += 4) dst[static_cast<size_t>(t) * a.hw] = src[t];
     }
   }
   if (a.attn_only) return;

@@ -29,44 +29,54 @@ __global__ void fold_qk_kernel(const float* __restrict__ q, const float* __restr
 }
 
 // u[c, hh] = in_norm.weight[c] * sum_d qk[hh,d] Wc[d,c]   (zero for hh >= n_head)
+// block = one head x 32 channels; 8 warps split d, lanes run over channels (coalesced Wc rows)
 __global__ void fold_u_kernel(const float* __restrict__ qk, const float* __restrict__ wc,
                               const float* __restrict__ gamma, float* __restrict__ u, int n_head, int C, int D,
                               int has_inconv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * kMaxHeads) return;
-  const int c = i / kMaxHeads, hh = i - c * kMaxHeads;
+  __shared__ float part[8][32];
+  const int hh = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), dpart = threadIdx.x >> 5;
   float s = 0.f;
-  if (hh < n_head) {
+  if (hh < n_head && c < C) {
     if (has_inconv) {
-      for (int d = 0; d < D; ++d) s = fmaf(qk[hh * D + d], wc[static_cast<size_t>(d) * C + c], s);
-    } else {
+      for (int d = dpart; d < D; d += 8) s = fmaf(qk[hh * D + d], wc[static_cast<size_t>(d) * C + c], s);
+    } else if (dpart == 0) {
       s = qk[hh * D + c];
     }
-    s *= gamma[c];
   }
-  u[i] = s;
+  part[dpart][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (dpart == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+    u[c * kMaxHeads + hh] = hh < n_head ? t * gamma[c] : 0.f;
+  }
 }
 
-// ub[hh] = sum_d qk[hh,d] * (bc[d] + sum_c Wc[d,c] beta[c]) + q_h . bk[h-block] / sqrt(dk); one block per head
-__global__ void fold_ub_kernel(const float* __restrict__ qk, const float* __restrict__ wc,
-                               const float* __restrict__ bc, const float* __restrict__ beta,
+// wb[d] = bc[d] + sum_c Wc[d,c] beta[c]  (without inconv: beta[d]); one warp per d
+__global__ void fold_wb_kernel(const float* __restrict__ wc, const float* __restrict__ bc,
+                               const float* __restrict__ beta, float* __restrict__ wb, int C, int D, int has_inconv) {
+  const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (d >= D) return;
+  if (!has_inconv) {
+    if (lane == 0) wb[d] = beta[d];
+    return;
+  }
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(wc[static_cast<size_t>(d) * C + c], beta[c], s);
+  s = warp_sum(s);
+  if (lane == 0) wb[d] = s + bc[d];
+}
+
+// ub[hh] = sum_d qk[hh,d] * wb[d] + q_h . bk[h-block] / sqrt(dk); one block per head
+__global__ void fold_ub_kernel(const float* __restrict__ qk, const float* __restrict__ wb,
                                const float* __restrict__ q, const float* __restrict__ bk, float* __restrict__ ub,
-                               int n_head, int dk, int C, int D, int has_inconv) {
+                               int n_head, int dk, int D) {
   __shared__ float scratch[32];
   const int hh = blockIdx.x;
   float s = 0.f;
-  if (hh < n_head) {
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-      float v;
-      if (has_inconv) {
-        v = bc[d];
-        for (int c = 0; c < C; ++c) v = fmaf(wc[static_cast<size_t>(d) * C + c], beta[c], v);
-      } else {
-        v = beta[d];
-      }
-      s = fmaf(qk[hh * D + d], v, s);
-    }
-  }
+  if (hh < n_head)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) s = fmaf(qk[hh * D + d], wb[d], s);
   s = block_sum(s, scratch);
   if (threadIdx.x == 0) {
     float r = 0.f;
@@ -114,8 +124,11 @@ template <typename P>
 __global__ void pos_table_kernel(const P* __restrict__ pos, int pos_stride, const float* __restrict__ denom,
                                  const float* __restrict__ fc_w, const float* __restrict__ fc_b,
                                  const float* __restrict__ abs_w, const float* __restrict__ abs_b,
-                                 float* __restrict__ pe, int D, int dh, int pe_mode, int pe_abs) {
-  extern __shared__ float base[];  // [dh] un-tiled sinusoid table (add_linear only)
+                                 float* __restrict__ pe, int D, int dh, int pe_mode, int pe_abs,
+                                 const float* __restrict__ qk, const float* __restrict__ ub,
+                                 float* __restrict__ cpos, int n_head) {
+  extern __shared__ float base[];  // [dh] un-tiled sinusoid table (add_linear only), then [D] the finished row
+  float* row = base + dh;
   const size_t bt = blockIdx.x;
   const size_t pi = bt * pos_stride;
   if (pe_mode == C2S_PE_SINUSOID_LINEAR) {
@@ -140,45 +153,48 @@ __global__ void pos_table_kernel(const P* __restrict__ pos, int pos_stride, cons
     }
     if (pe_abs) v += abs_w[static_cast<size_t>(i) * 365 + pos_as_doy(pos, pi + 1)] + abs_b[i];
     pe[bt * D + d] = v;
+    row[d] = v;
   }
+  __syncthreads();
+  // cpos[b,t,hh] = ub[hh] + qk[hh,:] . pe[b,t,:]: 16 lanes per head
+  const int hh = threadIdx.x >> 4, part = threadIdx.x & 15;
+  float s = 0.f;
+  if (hh < n_head)
+    for (int d = part; d < D; d += 16) s = fmaf(qk[hh * D + d], row[d], s);
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (part == 0 && hh < kMaxHeads) cpos[bt * kMaxHeads + hh] = hh < n_head ? s + ub[hh] : 0.f;
 }
 
-// cpos[b,t,hh] = ub[hh] + qk[hh,:] . pe[b,t,:]
-__global__ void fold_cpos_kernel(const float* __restrict__ qk, const float* __restrict__ ub,
-                                 const float* __restrict__ pe, float* __restrict__ cpos, int n_head, int D,
-                                 size_t n_bt, int has_pe) {
+// without a positional encoder: cpos[b,t,hh] = ub[hh]
+__global__ void fill_cpos_kernel(const float* __restrict__ ub, float* __restrict__ cpos, int n_head, size_t n_bt) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_bt * kMaxHeads) return;
-  const size_t bt = i / kMaxHeads;
-  const int hh = static_cast<int>(i - bt * kMaxHeads);
-  float s = 0.f;
-  if (hh < n_head) {
-    s = ub[hh];
-    if (has_pe)
-      for (int d = 0; d < D; ++d) s = fmaf(qk[hh * D + d], pe[bt * D + d], s);
-  }
-  cpos[i] = s;
+  const int hh = static_cast<int>(i % kMaxHeads);
+  cpos[i] = hh < n_head ? ub[hh] : 0.f;
 }
 
 }  // namespace
 
 int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* positions, float* ws,
-                 const LtaeWorkspace& lay, cudaStream_t stream) {
+                 const LtaeWorkspace& lay, bool need_transposed, cudaStream_t stream) {
   const int h = d.n_head, D = d.d_model, C = d.C, dk = d.d_k, dh = D / h;
   const bool attn_only = (d.flags & C2S_LTAE_ATTN_ONLY) != 0;
   const bool has_pe = d.pe_mode != C2S_PE_NONE;
   float* qk = ws + lay.qk;
+  if (has_pe && (h > kMaxHeads || kPrepThreads < 16 * h)) C2S_UNSUPPORTED("ltae_prepare: n_head=%d too large", h);
 
   fold_qk_kernel<<<ceil_div(h * D, kPrepThreads), kPrepThreads, 0, stream>>>(p.query, p.key_weight, qk, h, dk, D);
   C2S_LAUNCH_CHECK("ltae_fold_qk");
-  fold_u_kernel<<<ceil_div(C * kMaxHeads, kPrepThreads), kPrepThreads, 0, stream>>>(
-      qk, p.inconv_weight, p.in_norm_weight, ws + lay.u, h, C, D, d.has_inconv);
+  fold_u_kernel<<<dim3(ceil_div(C, 32), kMaxHeads), 256, 0, stream>>>(qk, p.inconv_weight, p.in_norm_weight, ws + lay.u,
+                                                                   h, C, D, d.has_inconv);
   C2S_LAUNCH_CHECK("ltae_fold_u");
-  fold_ub_kernel<<<kMaxHeads, kPrepThreads, 0, stream>>>(qk, p.inconv_weight, p.inconv_bias, p.in_norm_bias,
-                                                         p.query, p.key_bias, ws + lay.ub, h, dk, C, D,
-                                                         d.has_inconv);
+  fold_wb_kernel<<<ceil_div(D, 8), 256, 0, stream>>>(p.inconv_weight, p.inconv_bias, p.in_norm_bias, ws + lay.wb, C, D,
+                                                   d.has_inconv);
+  C2S_LAUNCH_CHECK("ltae_fold_wb");
+  fold_ub_kernel<<<kMaxHeads, kPrepThreads, 0, stream>>>(qk, ws + lay.wb, p.query, p.key_bias, ws + lay.ub, h, dk, D);
   C2S_LAUNCH_CHECK("ltae_fold_ub");
-  if (!attn_only) {
+  if (!attn_only && need_transposed) {
     if (d.has_inconv) {
       transpose_kernel<<<ceil_div(D * C, kPrepThreads), kPrepThreads, 0, stream>>>(p.inconv_weight, ws + lay.wct, D, C);
       C2S_LAUNCH_CHECK("ltae_transpose_inconv");
@@ -186,6 +202,8 @@ int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* p
     transpose_kernel<<<ceil_div(d.c_out * D, kPrepThreads), kPrepThreads, 0, stream>>>(p.mlp_weight, ws + lay.wmt,
                                                                                       d.c_out, D);
     C2S_LAUNCH_CHECK("ltae_transpose_mlp");
+  }
+  if (!attn_only) {
     if (!(d.flags & C2S_LTAE_BN_BATCH_STATS)) {
       fold_bn_kernel<<<ceil_div(d.c_out, kPrepThreads), kPrepThreads, 0, stream>>>(
           p.bn_weight, p.bn_bias, p.bn_running_mean, p.bn_running_var, d.bn_eps, ws + lay.bnf, d.c_out);
@@ -195,21 +213,25 @@ int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* p
   const size_t n_bt = static_cast<size_t>(d.B) * d.T;
   if (has_pe) {
     const int stride = d.pe_abs ? 2 : 1;
-    const size_t smem = static_cast<size_t>(dh) * sizeof(float);
+    const size_t smem = static_cast<size_t>(dh + D) * sizeof(float);
     if (d.pos_dtype == 0) {
       pos_table_kernel<long long><<<static_cast<unsigned>(n_bt), kPrepThreads, smem, stream>>>(
           static_cast<const long long*>(positions), stride, p.pe_denom, p.pe_fc_weight, p.pe_fc_bias,
-          p.pe_abs_fc_weight, p.pe_abs_fc_bias, ws + lay.pe, D, dh, d.pe_mode, d.pe_abs);
+          p.pe_abs_fc_weight, p.pe_abs_fc_bias, ws + lay.pe, D, dh, d.pe_mode, d.pe_abs, qk, ws + lay.ub,
+          ws + lay.cpos, h);
     } else {
       pos_table_kernel<float><<<static_cast<unsigned>(n_bt), kPrepThreads, smem, stream>>>(
           static_cast<const float*>(positions), stride, p.pe_denom, p.pe_fc_weight, p.pe_fc_bias,
-          p.pe_abs_fc_weight, p.pe_abs_fc_bias, ws + lay.pe, D, dh, d.pe_mode, d.pe_abs);
+          p.pe_abs_fc_weight, p.pe_abs_fc_bias, ws + lay.pe, D, dh, d.pe_mode, d.pe_abs, qk, ws + lay.ub,
+          ws + lay.cpos, h);
     }
     C2S_LAUNCH_CHECK("ltae_pos_table");
   }
-  fold_cpos_kernel<<<ceil_div(n_bt * kMaxHeads, kPrepThreads), kPrepThreads, 0, stream>>>(
-      qk, ws + lay.ub, ws + lay.pe, ws + lay.cpos, h, D, n_bt, has_pe ? 1 : 0);
-  C2S_LAUNCH_CHECK("ltae_fold_cpos");
+  if (!has_pe) {
+    fill_cpos_kernel<<<ceil_div(n_bt * kMaxHeads, kPrepThreads), kPrepThreads, 0, stream>>>(ws + lay.ub, ws + lay.cpos, h,
+                                                                                          n_bt);
+    C2S_LAUNCH_CHECK("ltae_fill_cpos");
+  }
   return C2S_OK;
 }
 

@@ -23,6 +23,7 @@ constexpr int kMaxHeads = 16;  // accumulators per thread in the attention kerne
 struct LtaeWorkspace {
   size_t qk;     // [h, D]
   size_t u;      // [C, kMaxHeads]   U transposed, in_norm.weight folded in, zero padded heads
+  size_t wb;     // [D]              bc + Wc beta
   size_t ub;     // [kMaxHeads]      sum_c U[h,c] * in_norm.bias[c]  (+ the constant part of cpos)
   size_t wct;    // [C, D]           inconv.weight transposed
   size_t wmt;    // [D, c_out]       mlp.0.weight transposed
@@ -51,6 +52,7 @@ inline LtaeWorkspace ltae_workspace(const c2s_ltae_desc& d) {
   };
   w.qk = take(h * D);
   w.u = take(C * kMaxHeads);
+  w.wb = take(D);
   w.ub = take(kMaxHeads);
   w.wct = take(d.has_inconv ? C * D : 0);
   w.wmt = take(D * co);
@@ -73,6 +75,6 @@ int ltae_mma_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const voi
                      cudaStream_t stream);
 
 int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* positions, float* ws,
-                 const LtaeWorkspace& lay, cudaStream_t stream);
+                 const LtaeWorkspace& lay, bool need_transposed, cudaStream_t stream);
 
 }  // namespace c2s
