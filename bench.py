@@ -40,7 +40,7 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="patches per GPU per step")
@@ -94,23 +94,61 @@ def agg128_bytes(lengths, elem):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML every 5 ms when
+    pynvml is importable, else the recipe's nvidia-smi query."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._thr = index, [], threading.Event(), None
+        self.index, self._stop, self._thr = index, threading.Event(), None
+        self.sm, self.max_sm, self.reasons, self.source = [], [], set(), "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)))
+        self.max_sm.append(float(n.nvmlDeviceGetMaxClockInfo(self._handle, n.NVML_CLOCK_SM)))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = get(self._handle)
+        for name, const in (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                            ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                            ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                            ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")):
+            if bits & getattr(n, const, 0):
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        if not out.strip():
+            return
+        r = [f.strip() for f in out.strip().splitlines()[0].split(",")]
+        self.sm.append(float(r[0]))
+        self.max_sm.append(float(r[1]))
+        for name, v in zip(self.NAMES, r[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                if out.strip():
-                    self.rows.append([f.strip() for f in out.strip().splitlines()[0].split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.005 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._thr = threading.Thread(target=self._run, daemon=True)
@@ -123,19 +161,9 @@ class ClockSampler:
 
     def summary(self):
         import statistics
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.max_sm) if self.max_sm else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -312,10 +340,15 @@ def run_b200(args):
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "B200_PROFILING.md fallback"
     a128 = agg128_bytes(lengths, elem) / (per[3] * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and B == 64 and args.dtype == "bf16":
+        traffic = json.load(open(tpath)).get("agg_pipe_x8_b64_bf16_dram_bytes")
     step_bytes = algorithmic_bytes(lengths, elem)
     roofline = {
         "bound": "hbm", "kernel": "agg_forward<x8> (TemporalAggregator att_group, x[B,61,64,128,128])",
-        "achieved": a128, "peak": peak, "unit": "GB/s", "frac": a128 / peak, "traffic": None,
+        "achieved": a128, "peak": peak, "unit": "GB/s", "frac": a128 / peak, "traffic": traffic,
+        "algorithmic_bytes": agg128_bytes(lengths, elem),
         "peak_source": peak_src, "kernel_ms": per[3],
         "step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9,
                  "frac": step_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9 / peak,

@@ -22,8 +22,9 @@
 namespace c2s {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kPix = 8;        // pixels per CTA == warps per CTA
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kPix = 8;        // pixels per CTA; two warps share a pixel in the attention part
 constexpr int kTP = 64;        // padded frame count
 constexpr int kRow = kTP + 8;  // X2 row pitch in elements (144 B: ldmatrix rows hit distinct banks)
 constexpr int kH = 16;         // heads
@@ -74,7 +75,8 @@ struct Smem {
   static constexpr int oOsLo = oOsHi + kPix * kOsRow * 2;
   static constexpr int oYs = oOsLo + kPix * kOsRow * 2;         // float [256][8]
   static constexpr int oUf = oYs + 256 * kPix * 4;              // float [C/16][32][8] score weights (A-fragment order)
-  static constexpr int kTotal = oUf + (C / 16) * 32 * 8 * 4;
+  static constexpr int oRed = oUf + (C / 16) * 32 * 8 * 4;      // float [8 pixels][2 warps][max | sum][16] softmax exchange
+  static constexpr int kTotal = oRed + kPix * 2 * 2 * kH * 4;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   __nv_bfloat16* s_os_lo = reinterpret_cast<__nv_bfloat16*>(smem + S::oOsLo);
   float* s_ys = reinterpret_cast<float*>(smem + S::oYs);
   float* s_uf = reinterpret_cast<float*>(smem + S::oUf);
+  float* s_red = reinterpret_cast<float*>(smem + S::oRed);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / a.tiles_per_b;
@@ -151,18 +154,20 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
 
   // ---- phase 1: stage x transposed into X2[p][c][t] and accumulate GroupNorm statistics -------------
   {
-    constexpr int NCB = C / 64;  // 8-channel blocks per warp
+    constexpr int NCB = (C / 8 + kWarps - 1) / kWarps;  // 8-channel blocks per warp
     const int cc = lane & 7, tp = lane >> 3;
     // 1a: every global load of this warp's share is issued before anything is consumed (one latency per CTA)
     uint4 v[NCB][8][2];
     uint4 pv[NCB];
 #pragma unroll
     for (int n = 0; n < NCB; ++n) {
-      const int c = (warp + 8 * n) * 8 + cc;
+      const int cb = warp + kWarps * n;
+      const bool has_work = cb < C / 8;  // warp-uniform
+      const int c = cb * 8 + cc;
       const int g = c / CPG;
       const __nv_bfloat16* xc = xb + static_cast<size_t>(c) * a.hw;
       pv[n] = make_uint4(0, 0, 0, 0);
-      if (n_live > 0) {  // pivot of the shifted sums: first live frame, first channel of the group
+      if (n_live > 0 && has_work) {  // pivot of the shifted sums: first live frame, first channel of the group
         const int t0 = __ffsll(static_cast<long long>(live_mask)) - 1;
         pv[n] = ld_stream_v4(xb + static_cast<size_t>(t0) * frame_stride + static_cast<size_t>(g * CPG) * a.hw);
       }
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
         for (int e = 0; e < 2; ++e) {
           const int t = tb * 8 + tp * 2 + e;
           v[n][tb][e] = make_uint4(0, 0, 0, 0);
-          if ((live_mask >> t) & 1ull) v[n][tb][e] = ld_stream_v4(xc + static_cast<size_t>(t) * frame_stride);
+          if (has_work && ((live_mask >> t) & 1ull)) v[n][tb][e] = ld_stream_v4(xc + static_cast<size_t>(t) * frame_stride);
         }
       }
     }
@@ -195,7 +200,8 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
     // 1c: statistics + transposed stores
 #pragma unroll
     for (int n = 0; n < NCB; ++n) {
-      const int c = (warp + 8 * n) * 8 + cc;
+      if (warp + kWarps * n >= C / 8) continue;  // warp-uniform
+      const int c = (warp + kWarps * n) * 8 + cc;
       const int g = c / CPG;
       float pivot[8];
       Elem<__nv_bfloat16>::unpack(pv[n], pivot);
@@ -259,19 +265,22 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   }
   __syncthreads();
 
-  // ---- phases 2-4: one warp per pixel ---------------------------------------------------------------
-  const int p = warp;
+  // ---- phases 2-4: two warps per pixel ------------------------------------------------------------
+  // scores: each warp of the pair takes half of the frames (4 n-tiles); softmax statistics are exchanged
+  // through shared memory; values: each warp takes half of the channels (and one positional n-tile).
+  const int p = warp >> 1, half = warp & 1;
   const int j = lane & 3, r8 = lane >> 2;  // fragment coordinates: row r8 (and r8 + 8), column pair 2j
   const uint32_t x2p = smem_u32(X2 + static_cast<size_t>(p) * C * kRow);
-  float sacc[8][4];  // S^T[h, t]: n-tile nt covers t = 8 nt .. 8 nt + 7
+  const uint32_t pair_bar = 1 + p;         // named barrier of this pixel's two warps
+  float sacc[4][4];  // S^T[h, t]: n-tile nt covers t = 8 (4 half + nt) .. + 7
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) sacc[nt][i] = 0.f;
   float mh0 = 0.f, mh1 = 0.f;  // sum_c U'[h, c] mu[g(c)] for rows r8 and r8 + 8
   {
     const int mat = lane >> 3, mr = lane & 7;
-#pragma unroll 1
+#pragma unroll 2
     for (int ks = 0; ks < KS; ++ks) {
       const float4* up = reinterpret_cast<const float4*>(s_uf + (ks * 32 + lane) * 8);
       const float4 u0 = up[0], u1 = up[1];
@@ -287,10 +296,10 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
       mh0 += (u0.x + u0.y) * m0 + (u1.x + u1.y) * m1;
       mh1 += (u0.z + u0.w) * m0 + (u1.z + u1.w) * m1;
 #pragma unroll
-      for (int ntp = 0; ntp < 4; ++ntp) {
+      for (int ntp = 0; ntp < 2; ++ntp) {
         uint32_t bfr[4];
         const int c = (2 * ks + (mat & 1)) * 8 + mr;
-        const int t0 = (2 * ntp + (mat >> 1)) * 8;
+        const int t0 = (4 * half + 2 * ntp + (mat >> 1)) * 8;
         ldmatrix_x4_trans(bfr, x2p + static_cast<uint32_t>(c * kRow + t0) * 2u);
         mma_bf16(sacc[2 * ntp], ahi, bfr[0], bfr[1]);
         mma_bf16(sacc[2 * ntp], alo, bfr[0], bfr[1]);
@@ -305,14 +314,17 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   mh1 += __shfl_xor_sync(0xffffffffu, mh1, 2);
 
   // softmax over t for rows h = r8 and r8 + 8                                        tae.py:831-836
-  float sa0, sa1;
+  const bool store_attn = a.attn != nullptr && !a.skip_attn_store;
+  float* as = s_as + p * kAsP;                              // probabilities [h][66] of this pixel
+  float* red = s_red + (p * 2 + half) * 2 * kH;              // [max | sum][h] of this warp
+  const float* red_other = s_red + (p * 2 + (half ^ 1)) * 2 * kH;
   {
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int t = nt * 8 + 2 * j + e;
+        const int t = (4 * half + nt) * 8 + 2 * j + e;
         float v0 = sacc[nt][e] + s_cpos[r8 * 66 + t] - mh0;
         float v1 = sacc[nt][2 + e] + s_cpos[(r8 + 8) * 66 + t] - mh1;
         if ((pad_mask >> t) & 1ull) v0 = -1e6f, v1 = -1e6f;
@@ -325,9 +337,13 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    if (j == 0) red[r8] = mx0, red[r8 + 8] = mx1;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    mx0 = fmaxf(mx0, red_other[r8]);       // the other half of the frames (T >= 1: at least one side is finite)
+    mx1 = fmaxf(mx1, red_other[r8 + 8]);
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         sacc[nt][e] = expf(sacc[nt][e] - mx0);
@@ -339,79 +355,73 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
     d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-    sa0 = 0.f, sa1 = 0.f;
-    const float inv0 = 1.f / d0, inv1 = 1.f / d1;
+    if (j == 0) red[kH + r8] = d0, red[kH + r8 + 8] = d1;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    // the sum is formed in the same order by both warps so that they normalise identically
+    const float lo0 = half ? red_other[kH + r8] : d0, hi0 = half ? d0 : red_other[kH + r8];
+    const float lo1 = half ? red_other[kH + r8 + 8] : d1, hi1 = half ? d1 : red_other[kH + r8 + 8];
+    const float inv0 = 1.f / (lo0 + hi0), inv1 = 1.f / (lo1 + hi1);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        sacc[nt][e] = sacc[nt][e] * inv0;
-        sacc[nt][2 + e] = sacc[nt][2 + e] * inv1;
-        sa0 += sacc[nt][e], sa1 += sacc[nt][2 + e];
-      }
+    for (int nt = 0; nt < 4; ++nt) {
+      const int t = (4 * half + nt) * 8 + 2 * j;
+      *reinterpret_cast<float2*>(as + r8 * 66 + t) = make_float2(sacc[nt][0] * inv0, sacc[nt][1] * inv0);
+      *reinterpret_cast<float2*>(as + (r8 + 8) * 66 + t) = make_float2(sacc[nt][2] * inv1, sacc[nt][3] * inv1);
     }
-    sa0 += __shfl_xor_sync(0xffffffffu, sa0, 1);
-    sa0 += __shfl_xor_sync(0xffffffffu, sa0, 2);
-    sa1 += __shfl_xor_sync(0xffffffffu, sa1, 1);
-    sa1 += __shfl_xor_sync(0xffffffffu, sa1, 2);
-    if (j == 0) s_sa[r8 * kPix + p] = sa0, s_sa[(r8 + 8) * kPix + p] = sa1;
-  }
-  const bool store_attn = a.attn != nullptr && !a.skip_attn_store;
-  if (store_attn) {
-    float* as = s_as + p * kAsP;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int t = nt * 8 + 2 * j;
-      *reinterpret_cast<float2*>(as + r8 * 66 + t) = make_float2(sacc[nt][0], sacc[nt][1]);
-      *reinterpret_cast<float2*>(as + (r8 + 8) * 66 + t) = make_float2(sacc[nt][2], sacc[nt][3]);
-    }
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
   }
 
   // values: zr[h, c] = sum_t a[h, t] x[t, c]  (+ 16 positional columns)                 tae.py:839
-  float zacc[C / 8][4];
-  float pacc[2][4];
+  constexpr int ZT = C / 16;  // channel n-tiles per warp
+  float zacc[ZT][4];
+  float pacc[4];
+  float sa0 = 0.f, sa1 = 0.f;
   if (!a.attn_only) {
 #pragma unroll
-    for (int nt = 0; nt < C / 8; ++nt)
+    for (int nt = 0; nt < ZT; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) zacc[nt][i] = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) pacc[nt][i] = 0.f;
+    for (int i = 0; i < 4; ++i) pacc[i] = 0.f;
     const int mat = lane >> 3, mr = lane & 7;
-    const uint32_t pe_hi = smem_u32(s_pe_hi), pe_lo = smem_u32(s_pe_lo);
+    const uint32_t pe_base = smem_u32((mat >> 1) ? s_pe_lo : s_pe_hi);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
+      // A fragment of the probabilities of ALL frames of this k-step (written by both warps of the pair)
+      const float2 p0 = *reinterpret_cast<const float2*>(as + r8 * 66 + ks * 16 + 2 * j);
+      const float2 p1 = *reinterpret_cast<const float2*>(as + (r8 + 8) * 66 + ks * 16 + 2 * j);
+      const float2 p2 = *reinterpret_cast<const float2*>(as + r8 * 66 + ks * 16 + 8 + 2 * j);
+      const float2 p3 = *reinterpret_cast<const float2*>(as + (r8 + 8) * 66 + ks * 16 + 8 + 2 * j);
+      sa0 += (p0.x + p0.y) + (p2.x + p2.y);
+      sa1 += (p1.x + p1.y) + (p3.x + p3.y);
       uint32_t ahi[4], alo[4];
-      split2(sacc[2 * ks][0], sacc[2 * ks][1], ahi[0], alo[0]);
-      split2(sacc[2 * ks][2], sacc[2 * ks][3], ahi[1], alo[1]);
-      split2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1], ahi[2], alo[2]);
-      split2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3], ahi[3], alo[3]);
+      split2(p0.x, p0.y, ahi[0], alo[0]);
+      split2(p1.x, p1.y, ahi[1], alo[1]);
+      split2(p2.x, p2.y, ahi[2], alo[2]);
+      split2(p3.x, p3.y, ahi[3], alo[3]);
       const int t0 = (2 * ks + (mat & 1)) * 8;
 #pragma unroll
-      for (int ntp = 0; ntp < C / 16; ++ntp) {
+      for (int ntp = 0; ntp < ZT / 2; ++ntp) {
         uint32_t bfr[4];
-        const int c = (2 * ntp + (mat >> 1)) * 8 + mr;
+        const int c = (half * ZT + 2 * ntp + (mat >> 1)) * 8 + mr;
         ldmatrix_x4(bfr, x2p + static_cast<uint32_t>(c * kRow + t0) * 2u);
         mma_bf16(zacc[2 * ntp], ahi, bfr[0], bfr[1]);
         mma_bf16(zacc[2 * ntp], alo, bfr[0], bfr[1]);
         mma_bf16(zacc[2 * ntp + 1], ahi, bfr[2], bfr[3]);
         mma_bf16(zacc[2 * ntp + 1], alo, bfr[2], bfr[3]);
       }
-      if (a.pe != nullptr) {
-        uint32_t bh[4], bl[4];
-        const uint32_t off = static_cast<uint32_t>(((mat >> 1) * 8 + mr) * kRow + t0) * 2u;
-        ldmatrix_x4(bh, pe_hi + off);
-        ldmatrix_x4(bl, pe_lo + off);
-        mma_bf16(pacc[0], ahi, bh[0], bh[1]);
-        mma_bf16(pacc[0], alo, bh[0], bh[1]);
-        mma_bf16(pacc[0], ahi, bl[0], bl[1]);
-        mma_bf16(pacc[1], ahi, bh[2], bh[3]);
-        mma_bf16(pacc[1], alo, bh[2], bh[3]);
-        mma_bf16(pacc[1], ahi, bl[2], bl[3]);
+      if (a.pe != nullptr) {  // positional n-tile `half`: matrices (hi, 2ks), (hi, 2ks+1), (lo, 2ks), (lo, 2ks+1)
+        uint32_t bp[4];
+        ldmatrix_x4(bp, pe_base + static_cast<uint32_t>((half * 8 + mr) * kRow + t0) * 2u);
+        mma_bf16(pacc, ahi, bp[0], bp[1]);
+        mma_bf16(pacc, alo, bp[0], bp[1]);
+        mma_bf16(pacc, ahi, bp[2], bp[3]);
       }
     }
+    sa0 += __shfl_xor_sync(0xffffffffu, sa0, 1);
+    sa0 += __shfl_xor_sync(0xffffffffu, sa0, 2);
+    sa1 += __shfl_xor_sync(0xffffffffu, sa1, 1);
+    sa1 += __shfl_xor_sync(0xffffffffu, sa1, 2);
+    if (j == 0 && half == 0) s_sa[r8 * kPix + p] = sa0, s_sa[(r8 + 8) * kPix + p] = sa1;
   }
   __syncthreads();  // every warp is done with X2 (z tiles alias it) and the attention staging is complete
 
@@ -430,8 +440,8 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   __nv_bfloat16* z_lo = z_hi + kH * S::kZH;
   {
 #pragma unroll
-    for (int nt = 0; nt < C / 8; ++nt) {
-      const int c = nt * 8 + 2 * j;
+    for (int nt = 0; nt < ZT; ++nt) {
+      const int c = (half * ZT + nt) * 8 + 2 * j;
       const int g = c / CPG;
       const float r = s_rstd[g * kPix + p], m = s_mu[g * kPix + p];
       const float2 gm = __ldg(reinterpret_cast<const float2*>(a.gamma + c));
@@ -451,14 +461,11 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
       *reinterpret_cast<uint32_t*>(z_hi + o1) = hi;
       *reinterpret_cast<uint32_t*>(z_lo + o1) = lo;
     }
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      const int i0 = nt * 8 + 2 * j;
-      s_pa[(r8 * 16 + i0) * kPix + p] = pacc[nt][0];
-      s_pa[(r8 * 16 + i0 + 1) * kPix + p] = pacc[nt][1];
-      s_pa[((r8 + 8) * 16 + i0) * kPix + p] = pacc[nt][2];
-      s_pa[((r8 + 8) * 16 + i0 + 1) * kPix + p] = pacc[nt][3];
-    }
+    const int i0 = half * 8 + 2 * j;
+    s_pa[(r8 * 16 + i0) * kPix + p] = pacc[0];
+    s_pa[(r8 * 16 + i0 + 1) * kPix + p] = pacc[1];
+    s_pa[((r8 + 8) * 16 + i0) * kPix + p] = pacc[2];
+    s_pa[((r8 + 8) * 16 + i0 + 1) * kPix + p] = pacc[3];
   }
   __syncthreads();
 
