@@ -29,7 +29,8 @@ constexpr int kTP = 64;        // padded frame count
 constexpr int kRow = kTP + 8;  // X2 row pitch in elements (144 B: ldmatrix rows hit distinct banks)
 constexpr int kH = 16;         // heads
 constexpr int kD = 256;        // d_model
-constexpr int kAsP = kH * 66 + 4;  // attention staging: floats per pixel ([h][66] + pad)
+constexpr int kAP = 72;            // pitch of the [h][t] fp32 tiles: 64-bit accesses of a half-warp hit 32 distinct banks
+constexpr int kAsP = kH * kAP + 4;  // attention staging: floats per pixel ([h][kAP] + pad)
 constexpr int kOsRow = kD + 8;     // o_s row pitch (elements)
 
 struct MmaArgs {
@@ -64,8 +65,8 @@ struct Smem {
   static_assert(kZ <= kX2, "z tiles must fit in the X2 region");
   static constexpr int oX2 = 0;
   static constexpr int oAs = oX2 + kX2;                         // float [8][kAsP]
-  static constexpr int oCpos = oAs + kPix * kAsP * 4;           // float [16][66]
-  static constexpr int oPeHi = oCpos + kH * 66 * 4;             // bf16 [16][kRow]
+  static constexpr int oCpos = oAs + kPix * kAsP * 4;           // float [16][kAP]
+  static constexpr int oPeHi = oCpos + kH * kAP * 4;             // bf16 [16][kRow]
   static constexpr int oPeLo = oPeHi + 16 * kRow * 2;
   static constexpr int oRstd = oPeLo + 16 * kRow * 2;           // float [16][8]
   static constexpr int oMu = oRstd + kH * kPix * 4;             // float [16][8]  mean * rstd
@@ -156,7 +157,19 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   {
     constexpr int NCB = (C / 8 + kWarps - 1) / kWarps;  // 8-channel blocks per warp
     const int cc = lane & 7, tp = lane >> 3;
-    // 1a: every global load of this warp's share is issued before anything is consumed (one latency per CTA)
+    // 1a: every global load of this warp's share is issued before anything is consumed (one latency per CTA);
+    // the few loads of the per-sample constants go first so that they are not queued behind the features
+    static_assert(kH * kTP == 2 * kThreads && 16 * kTP == 2 * kThreads && (C / 16) * 64 <= kThreads, "fill mapping");
+    float cpos_r[2], pe_r[2];
+    float4 uf_r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = tid + q * kThreads, t = i / kH, h = i - t * kH;
+      cpos_r[q] = t < a.T ? __ldg(a.cpos + (static_cast<size_t>(b) * a.T + t) * kMaxHeads + h) : 0.f;
+      const int t2 = i / 16, d = i - t2 * 16;
+      pe_r[q] = (!a.attn_only && a.pe != nullptr && t2 < a.T) ? __ldg(a.pe + (static_cast<size_t>(b) * a.T + t2) * kD + d) : 0.f;
+    }
+    if (tid < KS * 64) uf_r = __ldg(reinterpret_cast<const float4*>(a.ufrag) + tid);
     uint4 v[NCB][8][2];
     uint4 pv[NCB];
 #pragma unroll
@@ -181,20 +194,23 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
         }
       }
     }
-    // 1b: per-sample constants go to shared memory while the feature loads are in flight
-    for (int i = tid; i < kH * kTP; i += kThreads) {
-      const int t = i / kH, h = i - t * kH;
-      s_cpos[h * 66 + t] = t < a.T ? __ldg(a.cpos + (static_cast<size_t>(b) * a.T + t) * kMaxHeads + h) : 0.f;
+    // 1b: per-sample constants (their loads were issued ahead of the feature loads) go to shared memory
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = tid + q * kThreads, t = i / kH, h = i - t * kH;
+      s_cpos[h * kAP + t] = cpos_r[q];
     }
-    for (int i = tid; i < KS * 32 * 2; i += kThreads)
-      reinterpret_cast<float4*>(s_uf)[i] = __ldg(reinterpret_cast<const float4*>(a.ufrag) + i);
+    if (tid < KS * 64) {
+      const int ks = tid >> 6, lane_e = tid & 63;  // source order [ks][lane][2] -> [ks][2][lane]
+      reinterpret_cast<float4*>(s_uf)[ks * 64 + (lane_e & 1) * 32 + (lane_e >> 1)] = uf_r;
+    }
     if (!a.attn_only) {
-      for (int i = tid; i < 16 * kTP; i += kThreads) {
-        const int t = i / 16, d = i - t * 16;
-        const float pe = (a.pe != nullptr && t < a.T) ? __ldg(a.pe + (static_cast<size_t>(b) * a.T + t) * kD + d) : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(pe);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = tid + q * kThreads, t = i / 16, d = i - t * 16;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(pe_r[q]);
         s_pe_hi[d * kRow + t] = hi;
-        s_pe_lo[d * kRow + t] = __float2bfloat16_rn(pe - __bfloat162float(hi));
+        s_pe_lo[d * kRow + t] = __float2bfloat16_rn(pe_r[q] - __bfloat162float(hi));
       }
     }
     // 1c: statistics + transposed stores
@@ -282,8 +298,8 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
     const int mat = lane >> 3, mr = lane & 7;
 #pragma unroll 2
     for (int ks = 0; ks < KS; ++ks) {
-      const float4* up = reinterpret_cast<const float4*>(s_uf + (ks * 32 + lane) * 8);
-      const float4 u0 = up[0], u1 = up[1];
+      const float4* up = reinterpret_cast<const float4*>(s_uf) + ks * 64 + lane;  // [ks][2][32 lanes]: 16 B lane stride
+      const float4 u0 = up[0], u1 = up[32];
       const int c_lo = ks * 16 + 2 * j;
       const int g0 = c_lo / CPG, g1 = (c_lo + 8) / CPG;
       const float r0 = s_rstd[g0 * kPix + p], r1 = s_rstd[g1 * kPix + p];
@@ -325,8 +341,8 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int t = (4 * half + nt) * 8 + 2 * j + e;
-        float v0 = sacc[nt][e] + s_cpos[r8 * 66 + t] - mh0;
-        float v1 = sacc[nt][2 + e] + s_cpos[(r8 + 8) * 66 + t] - mh1;
+        float v0 = sacc[nt][e] + s_cpos[r8 * kAP + t] - mh0;
+        float v1 = sacc[nt][2 + e] + s_cpos[(r8 + 8) * kAP + t] - mh1;
         if ((pad_mask >> t) & 1ull) v0 = -1e6f, v1 = -1e6f;
         if (t >= a.T) v0 = -INFINITY, v1 = -INFINITY;
         sacc[nt][e] = v0, sacc[nt][2 + e] = v1;
@@ -364,8 +380,8 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int t = (4 * half + nt) * 8 + 2 * j;
-      *reinterpret_cast<float2*>(as + r8 * 66 + t) = make_float2(sacc[nt][0] * inv0, sacc[nt][1] * inv0);
-      *reinterpret_cast<float2*>(as + (r8 + 8) * 66 + t) = make_float2(sacc[nt][2] * inv1, sacc[nt][3] * inv1);
+      *reinterpret_cast<float2*>(as + r8 * kAP + t) = make_float2(sacc[nt][0] * inv0, sacc[nt][1] * inv0);
+      *reinterpret_cast<float2*>(as + (r8 + 8) * kAP + t) = make_float2(sacc[nt][2] * inv1, sacc[nt][3] * inv1);
     }
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
   }
@@ -387,10 +403,10 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       // A fragment of the probabilities of ALL frames of this k-step (written by both warps of the pair)
-      const float2 p0 = *reinterpret_cast<const float2*>(as + r8 * 66 + ks * 16 + 2 * j);
-      const float2 p1 = *reinterpret_cast<const float2*>(as + (r8 + 8) * 66 + ks * 16 + 2 * j);
-      const float2 p2 = *reinterpret_cast<const float2*>(as + r8 * 66 + ks * 16 + 8 + 2 * j);
-      const float2 p3 = *reinterpret_cast<const float2*>(as + (r8 + 8) * 66 + ks * 16 + 8 + 2 * j);
+      const float2 p0 = *reinterpret_cast<const float2*>(as + r8 * kAP + ks * 16 + 2 * j);
+      const float2 p1 = *reinterpret_cast<const float2*>(as + (r8 + 8) * kAP + ks * 16 + 2 * j);
+      const float2 p2 = *reinterpret_cast<const float2*>(as + r8 * kAP + ks * 16 + 8 + 2 * j);
+      const float2 p3 = *reinterpret_cast<const float2*>(as + (r8 + 8) * kAP + ks * 16 + 8 + 2 * j);
       sa0 += (p0.x + p0.y) + (p2.x + p2.y);
       sa1 += (p1.x + p1.y) + (p3.x + p3.y);
       uint32_t ahi[4], alo[4];
@@ -428,9 +444,11 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   if (store_attn) {  // attn[h, b, t, pix0 .. pix0 + 7]: 32-byte segments                    tae.py:490-493
     const int pp = lane & 7, tq = lane >> 3;
     for (int h = warp; h < kH; h += kThreads / 32) {
-      float* dst = a.attn + (static_cast<size_t>(h) * a.B + b) * a.T * a.hw + pix0 + pp;
-      const float* src = s_as + pp * kAsP + h * 66;
-      for (int t = tq; t < a.T; t += 4) dst[static_cast<size_t>(t) * a.hw] = src[t];
+      float* dst = a.attn + ((static_cast<size_t>(h) * a.B + b) * a.T + tq) * a.hw + pix0 + pp;
+      const float* src = s_as + pp * kAsP + h * kAP + tq;
+      const size_t step = static_cast<size_t>(4) * a.hw;
+#pragma unroll 4
+      for (int t = tq; t < a.T; t += 4, src += 4, dst += step) *dst = *src;
     }
   }
   if (a.attn_only) return;
