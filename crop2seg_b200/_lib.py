@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 1
+C2S_ABI_VERSION = 2
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -21,7 +21,8 @@ LTAE_ATTN_ONLY, LTAE_SKIP_ATTN_STORE, LTAE_ZERO_PADDED, LTAE_BN_BATCH_STATS = 1,
 
 EXPORTS = (
     "c2s_abi_version", "c2s_last_error", "c2s_launch_count", "c2s_reset_launch_count", "c2s_last_kernel",
-    "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_ltae_workspace_bytes", "c2s_ltae_forward",
+    "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_agg_backward_workspace_bytes", "c2s_agg_backward",
+    "c2s_ltae_workspace_bytes", "c2s_ltae_forward",
 )
 
 
@@ -32,7 +33,8 @@ class AggDesc(ctypes.Structure):
 class LtaeDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "B", "T", "C", "H", "W", "n_head", "d_k", "d_model", "c_out", "has_inconv", "pe_mode", "pe_abs",
-        "pos_dtype", "dtype", "flags")] + [("gn_eps", ctypes.c_float), ("bn_eps", ctypes.c_float)]
+        "pos_dtype", "dtype", "flags")] + [(n, ctypes.c_float) for n in (
+        "gn_eps", "bn_eps", "attn_keep_scale", "mlp_keep_scale")]
 
 
 LTAE_PARAM_FIELDS = (
@@ -41,10 +43,11 @@ LTAE_PARAM_FIELDS = (
     "out_norm_weight", "out_norm_bias", "pe_denom", "pe_fc_weight", "pe_fc_bias", "pe_abs_fc_weight",
     "pe_abs_fc_bias",
 )
+LTAE_MASK_FIELDS = ("attn_keep", "mlp_keep")  # uint8 dropout keep masks (training only)
 
 
 class LtaeParams(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_PARAM_FIELDS]
+    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_PARAM_FIELDS + LTAE_MASK_FIELDS]
 
 
 class C2SError(RuntimeError):
@@ -78,6 +81,10 @@ def load() -> ctypes.CDLL:
         lib.c2s_agg_workspace_bytes.argtypes = [ctypes.POINTER(AggDesc)]
         lib.c2s_agg_forward.restype = i32
         lib.c2s_agg_forward.argtypes = [ctypes.POINTER(AggDesc), vp, vp, vp, vp, vp, sz, vp]
+        lib.c2s_agg_backward_workspace_bytes.restype = sz
+        lib.c2s_agg_backward_workspace_bytes.argtypes = [ctypes.POINTER(AggDesc)]
+        lib.c2s_agg_backward.restype = i32
+        lib.c2s_agg_backward.argtypes = [ctypes.POINTER(AggDesc), vp, vp, vp, vp, vp, vp, vp, sz, vp]
         lib.c2s_ltae_workspace_bytes.restype = sz
         lib.c2s_ltae_workspace_bytes.argtypes = [ctypes.POINTER(LtaeDesc)]
         lib.c2s_ltae_forward.restype = i32

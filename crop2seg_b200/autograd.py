@@ -1,0 +1,178 @@
+"""``torch.autograd.Function``s of the hot path.
+
+* ``AggregateFunction``: forward AND backward are CUDA kernels (``c2s_agg_forward`` / ``c2s_agg_backward``) --
+  the aggregations move 97.7 % of the hot path's bytes.
+* ``LtaeFunction``: the forward is the fused CUDA kernel (train-mode BatchNorm statistics and injected dropout masks
+  included).  INTERIM: its backward re-evaluates the encoder with differentiable torch operations on the device
+  (as-written algorithm, tae.py:451-504, same masks and batch statistics) and lets autograd produce the gradients.
+  It materialises the [N,T,D] activations the forward kernel avoids, which is fine at the U-TAE / W-TAE placement
+  (N = B*256 rows) and is the item to replace by backward kernels next.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+
+class AggregateFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, attn, pad_mask, mode):
+        ctx.mode = mode
+        ctx.save_for_backward(x, attn if attn is not None else torch.empty(0, device=x.device),
+                              pad_mask if pad_mask is not None else torch.empty(0, device=x.device))
+        ctx.has_attn, ctx.has_pad = attn is not None, pad_mask is not None
+        return ops.temporal_aggregate_forward(x, pad_mask, attn, mode)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, attn, pad = ctx.saved_tensors
+        attn = attn if ctx.has_attn else None
+        pad = pad if ctx.has_pad else None
+        need_x = ctx.needs_input_grad[0]
+        need_attn = ctx.has_attn and ctx.needs_input_grad[1]
+        gx, gattn = ops.temporal_aggregate_backward(x, pad, attn, grad_out, ctx.mode, need_x=need_x, need_attn=need_attn)
+        return gx, gattn, None, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# differentiable restatement of the encoder used ONLY by LtaeFunction.backward (interim, see module docstring)
+# ------------------------------------------------------------------------------------------------------------
+def _positional(cfg: Dict, P: Dict[str, torch.Tensor], positions: torch.Tensor, n_rows_per_sample: int):
+    """[B,T,D] positional table (identical for every pixel of a sample; positional_encoding.py:25-73)."""
+    h, d = cfg["n_head"], cfg["d_model"] // cfg["n_head"]
+
+    def doy(pos, w, b):
+        idx = pos.to(torch.int64).clamp(0, 364)
+        return (w.t()[idx] + b).repeat(1, 1, h)
+
+    def primary(pos):
+        if cfg["pe_mode"] == _lib.PE_DOY_TABLE:
+            return doy(pos, P["pe_fc_weight"], P["pe_fc_bias"])
+        table = pos.to(torch.float32)[:, :, None] / P["pe_denom"][None, None, :]
+        enc = torch.where((torch.arange(d, device=table.device) % 2 == 0)[None, None, :], torch.sin(table), torch.cos(table))
+        enc = enc.repeat(1, 1, h)
+        if cfg["pe_mode"] == _lib.PE_SINUSOID_LINEAR:
+            enc = F.linear(enc, P["pe_fc_weight"], P["pe_fc_bias"])
+        return enc
+
+    if cfg["pe_abs"]:
+        return primary(positions[..., 0]) + doy(positions[..., 1], P["pe_abs_fc_weight"], P["pe_abs_fc_bias"])
+    return primary(positions)
+
+
+def ltae_torch(x, positions, pad_mask, P: Dict[str, Optional[torch.Tensor]], cfg: Dict, attn_keep=None, mlp_keep=None):
+    """Differentiable evaluation of LTAE / LTAE4WTAE with device tensors (fp32 math).  Returns (out | None, attn)."""
+    b, t, c, hh, ww = x.shape
+    h, dk, D = cfg["n_head"], cfg["d_k"], cfg["d_model"]
+    n = b * hh * ww
+    rows = x.float().permute(0, 3, 4, 1, 2).reshape(n, t, c)
+    e = F.group_norm(rows.permute(0, 2, 1), h, P["in_norm_weight"], P["in_norm_bias"], cfg["gn_eps"]).permute(0, 2, 1)
+    if cfg["has_inconv"]:  # 1x1 Conv1d == per-row Linear; F.linear stays in fp32 (cuDNN convolutions may use TF32)
+        e = F.linear(e, P["inconv_weight"].reshape(D, c), P["inconv_bias"])  # [N,T,D]
+    if cfg["pe_mode"] != _lib.PE_NONE:
+        pe = _positional(cfg, P, positions, hh * ww)  # [B,T,D]
+        e = (e.view(b, hh * ww, t, D) + pe[:, None]).view(n, t, D)
+    k = F.linear(e, P["key_weight"], P["key_bias"]).view(n, t, h, dk)
+    s = torch.einsum("hk,nthk->hnt", P["query"].reshape(h, dk), k) / (dk ** 0.5)
+    if pad_mask is not None:
+        pr = pad_mask.bool()[:, None, :].expand(b, hh * ww, t).reshape(n, t)
+        s = s.masked_fill(pr[None], -1e6)
+    a = torch.softmax(s, dim=2)  # [h,N,T]
+    if attn_keep is not None:
+        keep = attn_keep.view(h, b, t, hh * ww).permute(0, 1, 3, 2).reshape(h, n, t)
+        a = a * keep.to(a.dtype) * cfg["attn_keep_scale"]
+    attn = a.view(h, b, hh, ww, t).permute(0, 1, 4, 2, 3)
+    if cfg["attn_only"]:
+        return None, attn
+    v = e.view(n, t, h, D // h)
+    o = torch.einsum("hnt,nthd->nhd", a, v).reshape(n, D)
+    y = F.linear(o, P["mlp_weight"], P["mlp_bias"])
+    if cfg["bn_batch_stats"]:
+        y = F.batch_norm(y, None, None, P["bn_weight"], P["bn_bias"], True, 0.0, cfg["bn_eps"])
+    else:
+        y = F.batch_norm(y, P["bn_running_mean"], P["bn_running_var"], P["bn_weight"], P["bn_bias"], False, 0.0,
+                         cfg["bn_eps"])
+    y = F.relu(y)
+    if mlp_keep is not None:
+        mk = mlp_keep.view(b, -1, hh * ww).permute(0, 2, 1).reshape(n, -1)
+        y = y * mk.to(y.dtype) * cfg["mlp_keep_scale"]
+    y = F.group_norm(y[:, :, None], h, P["out_norm_weight"], P["out_norm_bias"], cfg["gn_eps"])[:, :, 0]
+    out = y.view(b, hh, ww, -1).permute(0, 3, 1, 2)
+    return out, attn
+
+
+_GRAD_PARAM_ORDER = tuple(_lib.LTAE_PARAM_FIELDS)
+
+
+class LtaeFunction(torch.autograd.Function):
+    """apply(x, positions, pad_mask, attn_keep, mlp_keep, cfg, *params in LTAE_PARAM_FIELDS order)
+    -> (out | None, attn, bn_batch_mean | None, bn_batch_var | None)"""
+
+    @staticmethod
+    def forward(ctx, x, positions, pad_mask, attn_keep, mlp_keep, cfg, *params):
+        P = dict(zip(_GRAD_PARAM_ORDER, params))
+        out, attn, stats = ops.ltae_forward(
+            x, positions, pad_mask, P, n_head=cfg["n_head"], d_k=cfg["d_k"], d_model=cfg["d_model"],
+            has_inconv=cfg["has_inconv"], c_out=cfg["c_out"], pe_mode=cfg["pe_mode"], pe_abs=cfg["pe_abs"],
+            attn_only=cfg["attn_only"], need_attn=True, zero_padded=cfg["zero_padded"],
+            bn_batch_stats=cfg["bn_batch_stats"], gn_eps=cfg["gn_eps"], bn_eps=cfg["bn_eps"],
+            attn_keep=attn_keep, attn_drop_p=1.0 - 1.0 / cfg["attn_keep_scale"],
+            mlp_keep=mlp_keep, mlp_drop_p=1.0 - 1.0 / cfg["mlp_keep_scale"])
+        ctx.cfg = cfg
+        # the running statistics are updated in place right after a training-mode forward and are not needed by
+        # its backward (batch statistics are recomputed), so they are not saved in that case
+        skip = ("bn_running_mean", "bn_running_var") if cfg["bn_batch_stats"] else ()
+        params = [None if name in skip else p for name, p in zip(_GRAD_PARAM_ORDER, params)]
+        ctx.present = [p is not None for p in params]
+        ctx.opt = (positions, pad_mask, attn_keep, mlp_keep)
+        ctx.save_for_backward(x, *[p for p in params if p is not None])
+        mean, var = stats if stats is not None else (None, None)
+        if stats is not None:
+            ctx.mark_non_differentiable(mean, var)
+        return out, attn, mean, var
+
+    @staticmethod
+    def backward(ctx, *grads):
+        cfg = ctx.cfg
+        saved = ctx.saved_tensors
+        x, rest = saved[0], list(saved[1:])
+        positions, pad_mask, attn_keep, mlp_keep = ctx.opt
+        params = [rest.pop(0) if present else None for present in ctx.present]
+        g_out, g_attn = grads[0], grads[1]
+        with torch.enable_grad():
+            xr = x.detach().requires_grad_(ctx.needs_input_grad[0])
+            leaves, P = [], {}
+            for name, p, need in zip(_GRAD_PARAM_ORDER, params, ctx.needs_input_grad[6:]):
+                if p is None:
+                    P[name] = None
+                    continue
+                q = p.detach().float()
+                if need and q.is_floating_point():
+                    q.requires_grad_(True)
+                P[name] = q
+                leaves.append((name, q, need))
+            out, attn = ltae_torch(xr, positions, pad_mask, P, cfg, attn_keep, mlp_keep)
+            outs, gouts = [], []
+            if g_out is not None and out is not None:
+                outs.append(out)
+                gouts.append(g_out.to(out.dtype))
+            if g_attn is not None:
+                outs.append(attn)
+                gouts.append(g_attn.to(attn.dtype))
+            wanted = ([xr] if ctx.needs_input_grad[0] else []) + [q for _, q, need in leaves if need and q.requires_grad]
+            got = torch.autograd.grad(outs, wanted, gouts, allow_unused=True) if outs and wanted else ()
+        got = list(got)
+        gx = got.pop(0).to(x.dtype) if ctx.needs_input_grad[0] and got else None
+        gparams = []
+        lookup = {}
+        for name, q, need in leaves:
+            if need and q.requires_grad:
+                lookup[name] = got.pop(0) if got else None
+        for name, p in zip(_GRAD_PARAM_ORDER, params):
+            g = lookup.get(name)
+            gparams.append(None if g is None or p is None else g.to(p.dtype).reshape(p.shape))
+        return (gx, None, None, None, None, None, *gparams)

@@ -1,4 +1,5 @@
 // Library services of the crop2seg_b200 C ABI: error text, launch accounting, ABI version.
+#include <atomic>
 #include <cstring>
 
 #include "c2s_common.cuh"
@@ -7,8 +8,9 @@ namespace c2s {
 
 namespace {
 thread_local char g_error[512] = "";
-thread_local char g_kernel[128] = "";
-thread_local int64_t g_launches = 0;
+// process-wide (autograd runs backward kernels on its own thread); diagnostics only
+char g_kernel[128] = "";
+std::atomic<int64_t> g_launches{0};
 }  // namespace
 
 void set_error(const char* fmt, ...) {
@@ -58,9 +60,9 @@ int c2s_abi_version(void) { return C2S_ABI_VERSION; }
 
 const char* c2s_last_error(void) { return c2s::g_error; }
 
-int64_t c2s_launch_count(void) { return c2s::g_launches; }
+int64_t c2s_launch_count(void) { return c2s::g_launches.load(); }
 
-void c2s_reset_launch_count(void) { c2s::g_launches = 0; }
+void c2s_reset_launch_count(void) { c2s::g_launches.store(0); }
 
 const char* c2s_last_kernel(void) { return c2s::g_kernel; }
 

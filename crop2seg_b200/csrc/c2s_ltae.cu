@@ -42,6 +42,9 @@ struct LtaeArgs {
   const float* on_w;  // out_norm.weight
   const float* on_b;
   float* ypre;        // [N, c_out] pre-BatchNorm rows (training mode)
+  const uint8_t* attn_keep;  // [h, B, T, hw] dropout keep mask or nullptr
+  const uint8_t* mlp_keep;   // [B, c_out, hw] or nullptr
+  float attn_keep_scale, mlp_keep_scale;
   int B, T, C, hw;
   int n_head, cpg, D, dh, c_out, cog;
   int has_inconv, attn_only, skip_attn_store, zero_padded;
@@ -215,7 +218,9 @@ __global__ void __launch_bounds__(kLtaeThreads) ltae_forward_kernel(const LtaeAr
         den += e;
       }
       for (int t = 0; t < a.T; ++t) {
-        const float v = col[t * stride] / den;
+        float v = col[t * stride] / den;
+        if (a.attn_keep != nullptr && p < n_pix)  // dropout acts on the attention that is returned (tae.py:837)
+          v *= a.attn_keep[((static_cast<size_t>(hh) * a.B + b) * a.T + t) * a.hw + pix0 + p] ? a.attn_keep_scale : 0.f;
         col[t * stride] = v;
         sum_a += v;
       }
@@ -330,7 +335,12 @@ __global__ void __launch_bounds__(kLtaeThreads) ltae_forward_kernel(const LtaeAr
     if (a.bnf != nullptr) {
       const float sc = __ldg(a.bnf + j), sh = __ldg(a.bnf + a.c_out + j);
 #pragma unroll
-      for (int p = 0; p < kPT; ++p) s_ys[j * kPT + p] = fmaxf(fmaf(acc[p], sc, sh), 0.f);
+      for (int p = 0; p < kPT; ++p) {
+        float v = fmaxf(fmaf(acc[p], sc, sh), 0.f);
+        if (a.mlp_keep != nullptr && p < n_pix)
+          v *= a.mlp_keep[(static_cast<size_t>(b) * a.c_out + j) * a.hw + pix0 + p] ? a.mlp_keep_scale : 0.f;
+        s_ys[j * kPT + p] = v;
+      }
     } else {
 #pragma unroll
       for (int p = 0; p < kPT; ++p) s_ys[j * kPT + p] = acc[p];
@@ -417,7 +427,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ ypre, const float* __r
                                 const float* __restrict__ var, const float* __restrict__ bn_w,
                                 const float* __restrict__ bn_b, const float* __restrict__ on_w,
                                 const float* __restrict__ on_b, T* __restrict__ out, int B, int hw, int c_out,
-                                int n_head, float bn_eps, float gn_eps) {
+                                int n_head, float bn_eps, float gn_eps, const uint8_t* __restrict__ keep,
+                                float keep_scale) {
   // one thread per (row, group); rows = b*hw + pix
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t n_rows = static_cast<size_t>(B) * hw;
@@ -426,23 +437,23 @@ __global__ void bn_apply_kernel(const float* __restrict__ ypre, const float* __r
   const size_t row = i - static_cast<size_t>(g) * n_rows;
   const int cog = c_out / n_head;
   const int b = static_cast<int>(row / hw), pix = static_cast<int>(row - static_cast<size_t>(b) * hw);
+  auto act = [&](int j) {  // BatchNorm (batch statistics) -> ReLU -> dropout       tae.py:445-448
+    float y = fmaxf((ypre[row * c_out + j] - mean[j]) / sqrtf(var[j] + bn_eps) * bn_w[j] + bn_b[j], 0.f);
+    if (keep != nullptr) y *= keep[(static_cast<size_t>(b) * c_out + j) * hw + pix] ? keep_scale : 0.f;
+    return y;
+  };
   float m = 0.f;
-  for (int k = 0; k < cog; ++k) {
-    const int j = g * cog + k;
-    const float y = (ypre[row * c_out + j] - mean[j]) / sqrtf(var[j] + bn_eps) * bn_w[j] + bn_b[j];
-    m += fmaxf(y, 0.f);
-  }
+  for (int k = 0; k < cog; ++k) m += act(g * cog + k);
   m /= static_cast<float>(cog);
   float v = 0.f;
   for (int k = 0; k < cog; ++k) {
-    const int j = g * cog + k;
-    const float y = fmaxf((ypre[row * c_out + j] - mean[j]) / sqrtf(var[j] + bn_eps) * bn_w[j] + bn_b[j], 0.f);
+    const float y = act(g * cog + k);
     v = fmaf(y - m, y - m, v);
   }
   const float rstd = 1.f / sqrtf(v / static_cast<float>(cog) + gn_eps);
   for (int k = 0; k < cog; ++k) {
     const int j = g * cog + k;
-    const float y = fmaxf((ypre[row * c_out + j] - mean[j]) / sqrtf(var[j] + bn_eps) * bn_w[j] + bn_b[j], 0.f);
+    const float y = act(j);
     Elem<T>::store(out + (static_cast<size_t>(b) * c_out + j) * hw + pix, fmaf((y - m) * rstd, on_w[j], on_b[j]));
   }
 }
@@ -464,6 +475,8 @@ int launch_general(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void*
   a.bnf = (attn_only || train) ? nullptr : ws + lay.bnf;
   a.on_w = p.out_norm_weight, a.on_b = p.out_norm_bias;
   a.ypre = train ? ws + lay.ypre : nullptr;
+  a.attn_keep = p.attn_keep, a.mlp_keep = p.mlp_keep;
+  a.attn_keep_scale = d.attn_keep_scale, a.mlp_keep_scale = d.mlp_keep_scale;
   a.B = d.B, a.T = d.T, a.C = d.C, a.hw = hw;
   a.n_head = d.n_head, a.cpg = d.C / d.n_head, a.D = d.d_model, a.dh = d.d_model / d.n_head;
   a.c_out = attn_only ? 0 : d.c_out, a.cog = attn_only ? 0 : d.c_out / d.n_head;
@@ -591,11 +604,12 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
     if (d.dtype == C2S_BF16) {
       bn_apply_kernel<__nv_bfloat16><<<ceil_div(n_items, 256), 256, 0, stream>>>(
           ypre, bn_batch_mean, bn_batch_var, p.bn_weight, p.bn_bias, p.out_norm_weight, p.out_norm_bias,
-          static_cast<__nv_bfloat16*>(out), d.B, hw, d.c_out, d.n_head, d.bn_eps, d.gn_eps);
+          static_cast<__nv_bfloat16*>(out), d.B, hw, d.c_out, d.n_head, d.bn_eps, d.gn_eps, p.mlp_keep,
+          d.mlp_keep_scale);
     } else {
       bn_apply_kernel<float><<<ceil_div(n_items, 256), 256, 0, stream>>>(
           ypre, bn_batch_mean, bn_batch_var, p.bn_weight, p.bn_bias, p.out_norm_weight, p.out_norm_bias,
-          static_cast<float*>(out), d.B, hw, d.c_out, d.n_head, d.bn_eps, d.gn_eps);
+          static_cast<float*>(out), d.B, hw, d.c_out, d.n_head, d.bn_eps, d.gn_eps, p.mlp_keep, d.mlp_keep_scale);
     }
     C2S_LAUNCH_CHECK("ltae_bn_apply");
   }

@@ -51,6 +51,9 @@ struct MmaArgs {
   const float* on_w;
   const float* on_b;
   float* ypre;
+  const uint8_t* attn_keep;  // [16, B, T, hw] dropout keep mask or nullptr
+  const uint8_t* mlp_keep;   // [B, c_out, hw] or nullptr
+  float attn_keep_scale, mlp_keep_scale;
   int B, T, hw, c_out;
   int attn_only, skip_attn_store, zero_padded;
   float gn_eps;
@@ -380,8 +383,19 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int t = (4 * half + nt) * 8 + 2 * j;
-      *reinterpret_cast<float2*>(as + r8 * kAP + t) = make_float2(sacc[nt][0] * inv0, sacc[nt][1] * inv0);
-      *reinterpret_cast<float2*>(as + (r8 + 8) * kAP + t) = make_float2(sacc[nt][2] * inv1, sacc[nt][3] * inv1);
+      float2 q0 = make_float2(sacc[nt][0] * inv0, sacc[nt][1] * inv0);
+      float2 q1 = make_float2(sacc[nt][2] * inv1, sacc[nt][3] * inv1);
+      if (a.attn_keep != nullptr) {  // training: dropout acts on the attention that is returned (tae.py:837)
+        const uint8_t* k0 = a.attn_keep + ((static_cast<size_t>(r8) * a.B + b) * a.T + t) * a.hw + pix0 + p;
+        const uint8_t* k1 = a.attn_keep + ((static_cast<size_t>(r8 + 8) * a.B + b) * a.T + t) * a.hw + pix0 + p;
+        const float sc = a.attn_keep_scale;
+        q0.x = (t < a.T && k0[0]) ? q0.x * sc : 0.f;
+        q0.y = (t + 1 < a.T && k0[a.hw]) ? q0.y * sc : 0.f;
+        q1.x = (t < a.T && k1[0]) ? q1.x * sc : 0.f;
+        q1.y = (t + 1 < a.T && k1[a.hw]) ? q1.y * sc : 0.f;
+      }
+      *reinterpret_cast<float2*>(as + r8 * kAP + t) = q0;
+      *reinterpret_cast<float2*>(as + (r8 + 8) * kAP + t) = q1;
     }
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
   }
@@ -542,7 +556,11 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
     for (int e = 0; e < 4; ++e) {
       const int jj = mt * 16 + r8 + (e >> 1) * 8, pp = 2 * j + (e & 1);
       float v = acc[e] + __ldg(a.bm + jj);
-      if (a.bnf != nullptr) v = fmaxf(fmaf(v, __ldg(a.bnf + jj), __ldg(a.bnf + a.c_out + jj)), 0.f);
+      if (a.bnf != nullptr) {
+        v = fmaxf(fmaf(v, __ldg(a.bnf + jj), __ldg(a.bnf + a.c_out + jj)), 0.f);
+        if (a.mlp_keep != nullptr)
+          v *= a.mlp_keep[(static_cast<size_t>(b) * a.c_out + jj) * a.hw + pix0 + pp] ? a.mlp_keep_scale : 0.f;
+      }
       s_ys[jj * kPix + pp] = v;
     }
   }
@@ -668,6 +686,8 @@ int ltae_mma_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const voi
   a.bnf = (attn_only || train) ? nullptr : ws + lay.bnf;
   a.on_w = p.out_norm_weight, a.on_b = p.out_norm_bias;
   a.ypre = train ? ws + lay.ypre : nullptr;
+  a.attn_keep = p.attn_keep, a.mlp_keep = p.mlp_keep;
+  a.attn_keep_scale = d.attn_keep_scale, a.mlp_keep_scale = d.mlp_keep_scale;
   a.B = d.B, a.T = d.T, a.hw = d.H * d.W, a.c_out = attn_only ? 0 : d.c_out;
   a.attn_only = attn_only;
   a.skip_attn_store = (d.flags & C2S_LTAE_SKIP_ATTN_STORE) != 0;

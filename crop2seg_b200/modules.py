@@ -139,6 +139,13 @@ class _LTAEBase(nn.Module):
                 p["pe_abs_fc_bias"] = self.positional_encoder_abs.fc.bias
         return p
 
+    def _cfg(self, c_out, attn_only, bn_batch_stats, attn_p, mlp_p, bn_eps=1e-5):
+        return {"n_head": self.n_head, "d_k": self.d_k, "d_model": self.d_model, "has_inconv": self.inconv is not None,
+                "c_out": c_out, "pe_mode": self._pe_mode(), "pe_abs": bool(self.use_abs_rel_enc), "attn_only": attn_only,
+                "zero_padded": bool(self.assume_zero_padded), "bn_batch_stats": bool(bn_batch_stats),
+                "gn_eps": self.in_norm.eps, "bn_eps": bn_eps, "attn_keep_scale": 1.0 / (1.0 - attn_p),
+                "mlp_keep_scale": 1.0 / (1.0 - mlp_p)}
+
     def _check_inputs(self, x, batch_positions):
         if self.num_queries != 1:
             # the reference accepts num_queries > 1 here but every shipped model then crashes in the
@@ -186,12 +193,13 @@ class LTAE(_LTAEBase):
         """x[B,T,C,H,W] -> (out[B,C',H,W], attn[n_head,B,T,H,W]); ``return_comp`` is ignored as in tae.py:451.
 
         ``return_att=False`` (extension) skips the attention store and returns ``(out, None)``.
+        Training mode follows the reference: BatchNorm1d batch statistics (+ running-stat update), dropout on the
+        attention before it is returned (tae.py:837) and after the MLP's ReLU (tae.py:448); the masks are drawn with
+        torch's generator here and injected into the kernel.
         """
         self._check_inputs(x, batch_positions)
         bn = self.mlp[2]
         train_bn = self.training or not bn.track_running_stats
-        if self.training:
-            self._check_training_supported(x)
         params = self._front_params(x.device)
         params.update({
             "mlp_weight": self.mlp[0].weight, "mlp_bias": self.mlp[0].bias,
@@ -199,26 +207,30 @@ class LTAE(_LTAEBase):
             "bn_running_mean": bn.running_mean, "bn_running_var": bn.running_var,
             "out_norm_weight": self.out_norm.weight, "out_norm_bias": self.out_norm.bias,
         })
-        out, attn, stats = ops.ltae_forward(
-            x, batch_positions, pad_mask, params, n_head=self.n_head, d_k=self.d_k, d_model=self.d_model,
-            has_inconv=self.inconv is not None, c_out=self._widths[-1], pe_mode=self._pe_mode(),
-            pe_abs=self.use_abs_rel_enc, need_attn=return_att, zero_padded=self.assume_zero_padded,
-            bn_batch_stats=train_bn, gn_eps=self.in_norm.eps, bn_eps=bn.eps)
-        if stats is not None and self.training and bn.track_running_stats:
-            self._update_running_stats(bn, stats, x.shape[0] * x.shape[3] * x.shape[4])
-        return out, attn
-
-    def _check_training_supported(self, x):
+        b, t, _, h, w = x.shape
+        c_out = self._widths[-1]
+        attn_p = ATTENTION_DROPOUT if self.training else 0.0
+        mlp_p = float(self.mlp[5].p) if self.training else 0.0
+        attn_keep = (torch.rand((self.n_head, b, t, h, w), device=x.device) >= attn_p).to(torch.uint8) if attn_p > 0 else None
+        mlp_keep = (torch.rand((b, c_out, h, w), device=x.device) >= mlp_p).to(torch.uint8) if mlp_p > 0 else None
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
-            raise NotImplementedError(
-                "crop2seg_b200: the backward pass of the fused L-TAE is not implemented yet; "
-                "use torch.no_grad() / model.eval() for inference")
-        if self.mlp[5].p > 0 or ATTENTION_DROPOUT > 0:
-            raise NotImplementedError(
-                "crop2seg_b200: train-mode dropout (tae.py:448, :819) is not implemented yet; call .eval(), or "
-                "set mlp[5].p = 0 and crop2seg_b200.modules.ATTENTION_DROPOUT = 0 for train-mode BatchNorm statistics")
+            from .autograd import LtaeFunction
+            cfg = self._cfg(c_out, attn_only=False, bn_batch_stats=train_bn, attn_p=attn_p, mlp_p=mlp_p, bn_eps=bn.eps)
+            out, attn, mean, var = LtaeFunction.apply(x, batch_positions, pad_mask, attn_keep, mlp_keep, cfg,
+                                                      *[params.get(k) for k in _lib.LTAE_PARAM_FIELDS])
+            stats = (mean, var) if mean is not None else None
+        else:
+            out, attn, stats = ops.ltae_forward(
+                x, batch_positions, pad_mask, params, n_head=self.n_head, d_k=self.d_k, d_model=self.d_model,
+                has_inconv=self.inconv is not None, c_out=c_out, pe_mode=self._pe_mode(),
+                pe_abs=self.use_abs_rel_enc, need_attn=return_att, zero_padded=self.assume_zero_padded,
+                bn_batch_stats=train_bn, gn_eps=self.in_norm.eps, bn_eps=bn.eps, attn_keep=attn_keep,
+                attn_drop_p=attn_p, mlp_keep=mlp_keep, mlp_drop_p=mlp_p)
+        if stats is not None and self.training and bn.track_running_stats:
+            self._update_running_stats(bn, stats, b * h * w)
+        return out, (attn if return_att else None)
 
     @staticmethod
     @torch.no_grad()
@@ -242,13 +254,25 @@ class LTAE4WTAE(_LTAEBase):
                           use_doy, add_linear)
 
     def forward(self, x, batch_positions=None, pad_mask=None, return_comp=False):
-        """x[B,T,C,H,W] -> attn[n_head,B,T,H,W] (tae.py:589-635)."""
+        """x[B,T,C,H,W] -> attn[n_head,B,T,H,W] (tae.py:589-635); dropout on the attention in training mode."""
         self._check_inputs(x, batch_positions)
+        b, t, _, h, w = x.shape
+        attn_p = ATTENTION_DROPOUT if self.training else 0.0
+        attn_keep = (torch.rand((self.n_head, b, t, h, w), device=x.device) >= attn_p).to(torch.uint8) if attn_p > 0 else None
+        params = self._front_params(x.device)
+        needs_grad = torch.is_grad_enabled() and (
+            x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            from .autograd import LtaeFunction
+            cfg = self._cfg(0, attn_only=True, bn_batch_stats=False, attn_p=attn_p, mlp_p=0.0)
+            _, attn, _, _ = LtaeFunction.apply(x, batch_positions, pad_mask, attn_keep, None, cfg,
+                                               *[params.get(k) for k in _lib.LTAE_PARAM_FIELDS])
+            return attn
         _, attn, _ = ops.ltae_forward(
-            x, batch_positions, pad_mask, self._front_params(x.device), n_head=self.n_head, d_k=self.d_k,
+            x, batch_positions, pad_mask, params, n_head=self.n_head, d_k=self.d_k,
             d_model=self.d_model, has_inconv=self.inconv is not None, c_out=0, pe_mode=self._pe_mode(),
             pe_abs=self.use_abs_rel_enc, attn_only=True, zero_padded=self.assume_zero_padded,
-            gn_eps=self.in_norm.eps)
+            gn_eps=self.in_norm.eps, attn_keep=attn_keep, attn_drop_p=attn_p)
         return attn
 
 

@@ -50,6 +50,24 @@ def _mask_u8(pad_mask: Optional[torch.Tensor], b: int, t: int, device) -> Option
 
 def temporal_aggregate(x: torch.Tensor, pad_mask: Optional[torch.Tensor] = None,
                        attn_mask: Optional[torch.Tensor] = None, mode: str = "mean") -> torch.Tensor:
+    """``TemporalAggregator(mode).forward(x, pad_mask, attn_mask)`` (temporal_aggregator.py:14-77), differentiable
+    w.r.t. x and attn_mask (both directions are CUDA kernels)."""
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or (attn_mask is not None and attn_mask.requires_grad))
+    if not needs_grad:
+        return temporal_aggregate_forward(x, pad_mask, attn_mask, mode)
+    from .autograd import AggregateFunction
+    if mode not in _AGG_MODES:
+        raise ValueError(f"unknown aggregation mode {mode!r}")
+    attn = None
+    if mode != "mean":
+        if attn_mask is None:
+            raise RuntimeError(f"crop2seg_b200: mode {mode!r} needs attn_mask")
+        attn = attn_mask if attn_mask.dtype == torch.float32 else attn_mask.float()
+    return AggregateFunction.apply(x, attn, pad_mask, mode)
+
+
+def temporal_aggregate_forward(x: torch.Tensor, pad_mask: Optional[torch.Tensor] = None,
+                               attn_mask: Optional[torch.Tensor] = None, mode: str = "mean") -> torch.Tensor:
     """``TemporalAggregator(mode).forward(x, pad_mask, attn_mask)`` (temporal_aggregator.py:14-77).
 
     x[B,T,C,H,W] float32/bfloat16, attn_mask[h,B,T,ha,wa] (float32 used as is), pad_mask[B,T] bool.
@@ -85,6 +103,38 @@ def temporal_aggregate(x: torch.Tensor, pad_mask: Optional[torch.Tensor] = None,
     return out
 
 
+def temporal_aggregate_backward(x: torch.Tensor, pad_mask: Optional[torch.Tensor], attn_mask: Optional[torch.Tensor],
+                                grad_out: torch.Tensor, mode: str, need_x: bool = True, need_attn: bool = True
+                                ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Backward of :func:`temporal_aggregate`: ``(grad_x | None, grad_attn | None)`` (``c2s_agg_backward``).
+
+    grad_attn is accumulated with float atomics (low bits depend on the execution order, like the reference's own
+    backward, train.py:623-626)."""
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    b, t, c, h, w = x.shape
+    desc = _lib.AggDesc(B=b, T=t, C=c, H=h, W=w, n_heads=1, ha=1, wa=1, mode=_AGG_MODES[mode],
+                        dtype=_dtype_code(x, "x"))
+    attn = None
+    if mode != "mean":
+        attn = attn_mask.to(device=x.device, dtype=torch.float32).contiguous()
+        desc.n_heads, desc.ha, desc.wa = attn.shape[0], attn.shape[3], attn.shape[4]
+    else:
+        need_attn = False
+    gout = grad_out.to(dtype=x.dtype).contiguous()
+    pad = _mask_u8(pad_mask, b, t, x.device)
+    gx = torch.empty_like(x) if need_x else None
+    gattn = torch.zeros_like(attn) if need_attn else None
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.c2s_agg_backward_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+        status = lib.c2s_agg_backward(ctypes.byref(desc), x.data_ptr(), _ptr(attn), _ptr(pad), gout.data_ptr(),
+                                      _ptr(gx), _ptr(gattn), _ptr(ws), ws_bytes, _stream(x.device))
+    _lib.check(status, "c2s_agg_backward")
+    return gx, gattn
+
+
 def _f32(t: Optional[torch.Tensor], device, keep) -> Optional[int]:
     """Device pointer of a float32, contiguous view of a parameter (kept alive in ``keep``)."""
     if t is None:
@@ -100,7 +150,8 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
                  params: Dict[str, Optional[torch.Tensor]], *, n_head: int, d_k: int, d_model: int,
                  has_inconv: bool, c_out: int, pe_mode: int, pe_abs: bool = False, attn_only: bool = False,
                  need_attn: bool = True, zero_padded: bool = False, bn_batch_stats: bool = False,
-                 gn_eps: float = 1e-5, bn_eps: float = 1e-5
+                 gn_eps: float = 1e-5, bn_eps: float = 1e-5, attn_keep: Optional[torch.Tensor] = None,
+                 attn_drop_p: float = 0.0, mlp_keep: Optional[torch.Tensor] = None, mlp_drop_p: float = 0.0
                  ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[Tuple[torch.Tensor, torch.Tensor]]]:
     """Fused ``LTAE.forward`` / ``LTAE4WTAE.forward`` (tae.py:451-504, 589-635).
 
@@ -140,9 +191,22 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
     desc = _lib.LtaeDesc(B=b, T=t, C=c, H=h, W=w, n_head=n_head, d_k=d_k, d_model=d_model,
                          c_out=0 if attn_only else c_out, has_inconv=int(has_inconv), pe_mode=pe_mode,
                          pe_abs=int(pe_abs), pos_dtype=pos_dtype, dtype=_dtype_code(x, "x"), flags=flags,
-                         gn_eps=gn_eps, bn_eps=bn_eps)
+                         gn_eps=gn_eps, bn_eps=bn_eps, attn_keep_scale=1.0 / (1.0 - attn_drop_p),
+                         mlp_keep_scale=1.0 / (1.0 - mlp_drop_p))
     keep = []
     cparams = _lib.LtaeParams(**{k: _f32(params.get(k), dev, keep) for k in _lib.LTAE_PARAM_FIELDS})
+    if attn_keep is not None:  # uint8 [h,B,T,H,W]: dropout mask of the attention (tae.py:837)
+        if tuple(attn_keep.shape) != (n_head, b, t, h, w):
+            raise RuntimeError(f"crop2seg_b200: attn_keep has shape {tuple(attn_keep.shape)}")
+        m = attn_keep.to(device=dev, dtype=torch.uint8).contiguous()
+        keep.append(m)
+        cparams.attn_keep = m.data_ptr()
+    if mlp_keep is not None and not attn_only:  # uint8 [B,c_out,H,W]: dropout mask after the ReLU (tae.py:448)
+        if tuple(mlp_keep.shape) != (b, c_out, h, w):
+            raise RuntimeError(f"crop2seg_b200: mlp_keep has shape {tuple(mlp_keep.shape)}")
+        m = mlp_keep.to(device=dev, dtype=torch.uint8).contiguous()
+        keep.append(m)
+        cparams.mlp_keep = m.data_ptr()
     pad = _mask_u8(pad_mask, b, t, dev)
     out = None if attn_only else torch.empty((b, c_out, h, w), dtype=x.dtype, device=dev)
     attn = torch.empty((n_head, b, t, h, w), dtype=torch.float32, device=dev) if need_attn else None

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 1
+#define C2S_ABI_VERSION 2
 
 enum c2s_status {
   C2S_OK = 0,
@@ -78,6 +78,18 @@ int c2s_agg_forward(const c2s_agg_desc* desc, const void* x, const float* attn,
                     const uint8_t* pad_mask, void* out, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Backward of TemporalAggregator.forward (what autograd derives from temporal_aggregator.py:14-77):
+ *   grad_x[b,t,c]        = resize(attn)[c // (C/n_heads), b, t] * (pad ? 0 : 1) * grad_out[b,c]      (x's dtype)
+ *   grad_attn[h,b,t,:,:] = resize^T( sum_{c in head h} x[b,t,c] * grad_out[b,c] )                  (float32)
+ * grad_x / grad_attn may be NULL when not needed; grad_attn must be ZERO-FILLED by the caller (it is
+ * accumulated with float atomics, so its low bits depend on the execution order -- the reference's own
+ * backward is non-deterministic too, train.py:623-626).  x is only read when grad_attn is requested.
+ * The AvgPool2d branch (attention finer than x, never taken by the shipped models) returns C2S_ERR_UNSUPPORTED. */
+size_t c2s_agg_backward_workspace_bytes(const c2s_agg_desc* desc);
+int c2s_agg_backward(const c2s_agg_desc* desc, const void* x, const float* attn, const uint8_t* pad_mask,
+                     const void* grad_out, void* grad_x, float* grad_attn, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * LTAE / LTAE4WTAE                                             tae.py:349-635
  * ---------------------------------------------------------------------------------------- */
@@ -95,6 +107,8 @@ typedef struct c2s_ltae_desc {
   int32_t flags;         /* enum c2s_ltae_flags                                               */
   float gn_eps;          /* 1e-5 (nn.GroupNorm default)                                       */
   float bn_eps;          /* 1e-5 (nn.BatchNorm1d default)                                     */
+  float attn_keep_scale; /* 1/(1-p) of ScaledDotProductAttention.dropout (tae.py:819), used with attn_keep */
+  float mlp_keep_scale;  /* 1/(1-p) of the MLP dropout (tae.py:448), used with mlp_keep        */
 } c2s_ltae_desc;
 
 /* state_dict tensors, float32, reference shapes. NULL where absent. */
@@ -120,6 +134,10 @@ typedef struct c2s_ltae_params {
   const float* pe_fc_bias;
   const float* pe_abs_fc_weight; /* positional_encoder_abs.fc.weight [d_model/n_head, 365]     */
   const float* pe_abs_fc_bias;
+  /* training-mode dropout, drawn by the caller (torch's Philox stream cannot be reproduced in a kernel):
+   * uint8 keep masks, NULL = no dropout.  The attention is masked BEFORE it is returned (tae.py:836-837). */
+  const uint8_t* attn_keep;      /* [n_head, B, T, H, W]                                        */
+  const uint8_t* mlp_keep;       /* [B, c_out, H, W], applied after the ReLU (tae.py:447-448)   */
 } c2s_ltae_params;
 
 /* Scratch bytes for c2s_ltae_forward (folded weights + per-sample positional tables). */
@@ -146,11 +164,11 @@ int c2s_ltae_forward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, c
  * ---------------------------------------------------------------------------------------- */
 int c2s_abi_version(void);
 const char* c2s_last_error(void);
-/* Number of kernels this library launched on the calling thread since the last reset
+/* Number of kernels this library launched (all threads of the process) since the last reset
  * (bench.py reports it as gpu_launches). */
 int64_t c2s_launch_count(void);
 void c2s_reset_launch_count(void);
-/* Name of the kernel variant the last forward call on this thread selected (diagnostics). */
+/* Name of the kernel the library launched last (diagnostics). */
 const char* c2s_last_kernel(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,174 @@
+"""Backward / training-mode parity on the GPU.
+
+* TemporalAggregator: forward and backward are CUDA kernels; gradients are compared with autograd through the
+  torch-CPU oracle (oracle/torch_port.py) on the same inputs.
+* L-TAE: the training-mode forward kernel (BatchNorm batch statistics + injected dropout masks) is compared with the
+  numpy oracle; its (interim, torch-recompute) backward is compared with autograd through the torch-CPU oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+import crop2seg_b200 as c2s
+from crop2seg_b200 import _lib, ops
+from oracle import ltae_forward
+from oracle.torch_port import ltae_forward_torch, temporal_aggregator_torch
+from golden_util import rel_err
+from c2s_testlib import (bf16_round, oracle_config, oracle_params, random_attention, randomise, synth_inputs,
+                         to_dev)
+
+pytestmark = pytest.mark.gpu
+
+AGG_BWD_CASES = {
+    # name: (mode, heads, (B,T,C,H,W), (ha,wa), lengths)
+    "x8_128": ("att_group", 16, (2, 5, 64, 128, 128), (16, 16), [5, 3]),
+    "x4_64": ("att_group", 16, (2, 5, 64, 64, 64), (16, 16), [5, 2]),
+    "x2_32": ("att_group", 16, (2, 6, 64, 32, 32), (16, 16), [6, 0]),
+    "x2_small": ("att_group", 4, (2, 5, 8, 8, 8), (4, 4), [5, 3]),
+    "frac": ("att_group", 4, (2, 4, 8, 12, 12), (5, 5), [4, 3]),
+    "rect": ("att_group", 4, (2, 4, 8, 12, 20), (4, 6), [4, 1]),
+    "att_mean": ("att_mean", 4, (2, 5, 8, 16, 16), (4, 4), [5, 3]),
+    "mean": ("mean", 4, (2, 5, 6, 8, 8), (4, 4), [5, 3]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(AGG_BWD_CASES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_aggregator_backward_matches_autograd_of_the_oracle(name, dtype):
+    mode, heads, (b, t, c, h, w), (ha, wa), lengths = AGG_BWD_CASES[name]
+    rng = np.random.RandomState(7000 + len(name))
+    x, _, pad = synth_inputs(rng, b, t, c, h, w, lengths)
+    x = x + 0.25 * rng.standard_normal(x.shape).astype(np.float32) * (~pad)[:, :, None, None, None]
+    attn = random_attention(rng, heads, pad, ha, wa)
+    gout = rng.standard_normal((b, c, h, w)).astype(np.float32)
+    if dtype == torch.bfloat16:
+        x, gout = bf16_round(x), bf16_round(gout)
+    # oracle gradients (CPU autograd through the as-written algorithm)
+    xr = torch.from_numpy(x).requires_grad_(True)
+    ar = torch.from_numpy(attn).requires_grad_(mode != "mean")
+    ref = temporal_aggregator_torch(xr, torch.from_numpy(pad), ar, mode)
+    ref.backward(torch.from_numpy(gout))
+    # CUDA path
+    xd = to_dev(x, dtype=dtype).requires_grad_(True)
+    ad = to_dev(attn).requires_grad_(mode != "mean")
+    out = c2s.TemporalAggregator(mode)(xd, pad_mask=to_dev(pad), attn_mask=ad)
+    out.backward(to_dev(gout, dtype=dtype))
+    assert "agg_backward" in _lib.last_kernel() or "spread" in _lib.last_kernel()
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert rel_err(out.detach().float().cpu().numpy(), ref.detach().numpy()) < tol
+    assert xd.grad.dtype == dtype and xd.grad.shape == xd.shape
+    assert rel_err(xd.grad.float().cpu().numpy(), xr.grad.numpy()) < tol
+    gx = xd.grad.float().cpu().numpy()
+    assert np.all(gx[pad] == 0.0)  # padded frames receive exactly zero gradient
+    if mode != "mean":
+        assert rel_err(ad.grad.cpu().numpy(), ar.grad.numpy()) < tol
+
+
+def _ltae(kw, seed, kind="ltae"):
+    rng = np.random.RandomState(seed)
+    m = (c2s.LTAE if kind == "ltae" else c2s.LTAE4WTAE)(**kw)
+    randomise(m, rng)
+    return m.cuda(), rng
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ltae_train_mode_forward_with_injected_dropout(dtype):
+    """BatchNorm batch statistics + dropout masks on the attention and after the ReLU (tae.py:445-448, :837)."""
+    kw = dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256)
+    m, rng = _ltae(kw, 31)
+    b, t, h, w = 2, 19, 4, 4
+    x, pos, pad = synth_inputs(rng, b, t, 128, h, w, [19, 11])
+    attn_keep = (rng.uniform(size=(16, b, t, h, w)) >= 0.1).astype(np.uint8)
+    mlp_keep = (rng.uniform(size=(b, 128, h, w)) >= 0.2).astype(np.uint8)
+    xr = x if dtype == torch.float32 else bf16_round(x)
+    n = b * h * w
+    ref_out, ref_attn, (rm, rv) = ltae_forward(
+        oracle_config("ltae", kw), oracle_params(m), xr, pos, pad, training=True,
+        attn_keep=np.ascontiguousarray(attn_keep.transpose(0, 1, 3, 4, 2)).reshape(16, n, 1, t),
+        mlp_keep=np.ascontiguousarray(mlp_keep.transpose(0, 2, 3, 1)).reshape(n, 128))
+    params = m._front_params(torch.device("cuda"))
+    bn = m.mlp[2]
+    params.update({"mlp_weight": m.mlp[0].weight, "mlp_bias": m.mlp[0].bias, "bn_weight": bn.weight,
+                   "bn_bias": bn.bias, "bn_running_mean": bn.running_mean, "bn_running_var": bn.running_var,
+                   "out_norm_weight": m.out_norm.weight, "out_norm_bias": m.out_norm.bias})
+    out, attn, stats = ops.ltae_forward(
+        to_dev(x, dtype=dtype), to_dev(pos), to_dev(pad), params, n_head=16, d_k=4, d_model=256, has_inconv=True,
+        c_out=128, pe_mode=_lib.PE_SINUSOID, bn_batch_stats=True, attn_keep=to_dev(attn_keep), attn_drop_p=0.1,
+        mlp_keep=to_dev(mlp_keep), mlp_drop_p=0.2)
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert rel_err(attn.cpu().numpy(), ref_attn) < (1e-4 if dtype == torch.float32 else 1e-3)
+    assert rel_err(out.float().cpu().numpy(), ref_out) < tol
+    a = attn.cpu().numpy()
+    assert np.all(a[attn_keep == 0] == 0.0)
+
+
+def _loss_weights(rng, out_shape, attn_shape):
+    return (rng.standard_normal(out_shape).astype(np.float32), rng.standard_normal(attn_shape).astype(np.float32))
+
+
+@pytest.mark.parametrize("variant", ["sinusoid", "doy", "abs_rel", "add_linear", "no_pe"])
+def test_ltae_backward_matches_autograd_of_the_oracle(variant):
+    extra = {"sinusoid": {}, "doy": dict(use_doy=True), "abs_rel": dict(use_abs_rel_enc=True),
+             "add_linear": dict(add_linear=True), "no_pe": dict(positional_encoding=False)}[variant]
+    kw = dict(in_channels=32, n_head=4, d_k=4, mlp=[64, 32], d_model=64, **extra)
+    m, rng = _ltae(kw, 50 + len(variant))
+    m.eval()
+    b, t, h, w = 2, 7, 3, 3
+    x, pos, pad = synth_inputs(rng, b, t, 32, h, w, [7, 4], doy=variant == "doy", abs_rel=variant == "abs_rel")
+    x = x + 0.3 * rng.standard_normal(x.shape).astype(np.float32) * (~pad)[:, :, None, None, None]
+    pos = None if variant == "no_pe" else pos
+    wo, wa = _loss_weights(rng, (b, 32, h, w), (4, b, t, h, w))
+    # oracle: CPU autograd through the as-written algorithm
+    P = {k: torch.from_numpy(v).clone().requires_grad_(np.issubdtype(v.dtype, np.floating) and "running" not in k
+                                                        and "denom" not in k)
+         for k, v in oracle_params(m).items()}
+    xr = torch.from_numpy(x).requires_grad_(True)
+    ro, ra = ltae_forward_torch(oracle_config("ltae", kw), P, xr, None if pos is None else torch.from_numpy(pos),
+                                torch.from_numpy(pad))
+    ((ro * torch.from_numpy(wo)).sum() + (ra * torch.from_numpy(wa)).sum()).backward()
+    # CUDA forward + backward through the module
+    xd = to_dev(x).requires_grad_(True)
+    out, attn = m(xd, batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+    assert "ltae_forward" in _lib.last_kernel()
+    ((out * to_dev(wo)).sum() + (attn * to_dev(wa)).sum()).backward()
+    assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-3
+    gmax = max(float(P[name].grad.abs().max()) for name, _ in m.named_parameters())
+    for name, p in m.named_parameters():
+        ref = P[name].grad
+        assert ref is not None, name
+        assert p.grad is not None, name
+        # fc1_k.bias shifts every score of a head alike, so its true gradient is zero (both sides return rounding
+        # noise): the floor of the comparison is relative to the largest parameter gradient
+        diff = float(np.abs(p.grad.cpu().numpy() - ref.numpy()).max())
+        assert diff <= 1e-3 * max(float(ref.abs().max()), 1e-3 * gmax), (name, diff)
+
+
+def test_utae_bottleneck_trains_end_to_end():
+    """LTAE -> two aggregations -> loss: gradients reach x, the skip features and every encoder parameter, and one
+    SGD step on the CUDA path lowers the loss (training mode: batch statistics + dropout)."""
+    kw = dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256)
+    m, rng = _ltae(kw, 91)
+    m.train()
+    agg = c2s.TemporalAggregator("att_group")
+    b, t = 2, 9
+    x4, pos, pad = synth_inputs(rng, b, t, 128, 4, 4, [9, 5])
+    x3 = synth_inputs(rng, b, t, 64, 8, 8, [9, 5])[0]
+    x1 = synth_inputs(rng, b, t, 64, 32, 32, [9, 5])[0]
+    x4d, x3d, x1d = (to_dev(v).requires_grad_(True) for v in (x4, x3, x1))
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3)
+    torch.manual_seed(0)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        torch.manual_seed(0)  # same dropout masks every iteration so that the loss is comparable
+        out, att = m(x4d, batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+        s3 = agg(x3d, pad_mask=to_dev(pad), attn_mask=att)
+        s1 = agg(x1d, pad_mask=to_dev(pad), attn_mask=att)
+        loss = out.pow(2).mean() + s3.pow(2).mean() + s1.pow(2).mean()
+        loss.backward()
+        losses.append(float(loss.detach()))
+        opt.step()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    assert x4d.grad is not None and x3d.grad is not None and x1d.grad is not None
+    assert int(m.mlp[2].num_batches_tracked) == 3
+    assert losses[-1] < losses[0]
