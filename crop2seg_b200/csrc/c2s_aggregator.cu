@@ -620,7 +620,9 @@ int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, con
   const int env_stages = getenv("C2S_AGG_STAGES") ? atoi(getenv("C2S_AGG_STAGES")) : 0;
   if (!no_pipe && scale_class > 0 && vec == vec_full && a.cpg % kPipeCPT == 0) {
     const int vecs = a.hw / vec;
-    int n_consumers = vecs < kPipeMaxConsumers ? vecs : kPipeMaxConsumers;
+    const int env_cons = getenv("C2S_AGG_CONSUMERS") ? atoi(getenv("C2S_AGG_CONSUMERS")) : 0;  // tuning hook
+    const int max_cons = (env_cons >= 64 && env_cons <= kPipeMaxConsumers && a.hw <= 4096) ? env_cons : kPipeMaxConsumers;
+    int n_consumers = vecs < max_cons ? vecs : max_cons;
     if (n_consumers >= 64 && n_consumers % 32 == 0 && vecs % n_consumers == 0) {
       int n_stages = env_stages > 0 ? env_stages : 4;  // 4 x 16 KB: three CTAs per SM, 192 KB of loads in flight
       n_stages = n_stages > 16 ? 16 : (n_stages < 2 ? 2 : n_stages);

@@ -17,6 +17,8 @@
 //                (tae.py:463, 486-488) with N = 8 pixels on the tensor cores (weights pre-split hi/lo).
 // The per-pixel operands make steps 2 and 4 batched 16xK GEMMs (A differs per pixel), which is the shape
 // mma.sync m16n8k16 fits exactly; tcgen05's M >= 64 tiles would be 3/4 empty.  See DESIGN.md.
+#include <cstdlib>
+
 #include "c2s_ltae_prep.cuh"
 
 namespace c2s {
@@ -54,6 +56,8 @@ struct MmaArgs {
   const uint8_t* attn_keep;  // [16, B, T, hw] dropout keep mask or nullptr
   const uint8_t* mlp_keep;   // [B, c_out, hw] or nullptr
   float attn_keep_scale, mlp_keep_scale;
+  __nv_bfloat16* o_hi;       // [B*hw][256] rows for the tcgen05 MLP kernel (nullptr: MLP runs in this kernel)
+  __nv_bfloat16* o_lo;
   int B, T, hw, c_out;
   int attn_only, skip_attn_store, zero_padded;
   float gn_eps;
@@ -533,6 +537,18 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
   }
   __syncthreads();
 
+  if (a.o_hi != nullptr) {  // the MLP, BatchNorm, ReLU and output GroupNorm run as a tcgen05 row GEMM (c2s_ltae_mlp_tc.cu)
+    const size_t row0 = static_cast<size_t>(b) * a.hw + pix0;
+    for (int i = tid; i < 2 * kPix * (kD / 8); i += kThreads) {  // 16-byte pieces of the 8 rows, hi then lo
+      const int plane = i / (kPix * (kD / 8)), r = i - plane * (kPix * (kD / 8));
+      const int pp = r / (kD / 8), q = r - pp * (kD / 8);
+      const __nv_bfloat16* src = (plane ? s_os_lo : s_os_hi) + pp * kOsRow + q * 8;
+      __nv_bfloat16* dst = (plane ? a.o_lo : a.o_hi) + (row0 + pp) * kD + q * 8;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+    }
+    return;
+  }
+
   // ---- phase 5b: MLP Linear (+ eval BatchNorm + ReLU)                                        tae.py:442-447
   for (int mt = warp; mt < a.c_out / 16; mt += kThreads / 32) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -656,6 +672,8 @@ size_t ltae_mma_workspace_floats(const c2s_ltae_desc& d) {
 int ltae_mma_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask,
                      void* out, float* attn, float* ws, const LtaeWorkspace& lay, float* frag_ws,
                      cudaStream_t stream) {
+  // test hook: keep the MLP inside the attention kernel (mma.sync) instead of the tcgen05 row GEMM
+  const bool split_mlp = !(d.flags & C2S_LTAE_ATTN_ONLY) && getenv("C2S_LTAE_NO_TCGEN05") == nullptr;
   const bool attn_only = (d.flags & C2S_LTAE_ATTN_ONLY) != 0;
   const bool train = (d.flags & C2S_LTAE_BN_BATCH_STATS) != 0 && !attn_only;
   const int C = d.C, KS = C / 16;
@@ -667,9 +685,11 @@ int ltae_mma_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const voi
   if (!attn_only) {
     build_wfrag_kernel<<<ceil_div((kD / 16) * KS * 128, 256), 256, 0, stream>>>(p.inconv_weight, wcfrag, kD, C);
     C2S_LAUNCH_CHECK("ltae_build_wcfrag");
-    build_wfrag_kernel<<<ceil_div((d.c_out / 16) * (kD / 16) * 128, 256), 256, 0, stream>>>(p.mlp_weight, wmfrag,
-                                                                                         d.c_out, kD);
-    C2S_LAUNCH_CHECK("ltae_build_wmfrag");
+    if (!split_mlp) {
+      build_wfrag_kernel<<<ceil_div((d.c_out / 16) * (kD / 16) * 128, 256), 256, 0, stream>>>(p.mlp_weight, wmfrag,
+                                                                                           d.c_out, kD);
+      C2S_LAUNCH_CHECK("ltae_build_wmfrag");
+    }
   }
   MmaArgs a{};
   a.x = static_cast<const __nv_bfloat16*>(x);
@@ -694,6 +714,10 @@ int ltae_mma_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const voi
   a.zero_padded = (d.flags & C2S_LTAE_ZERO_PADDED) != 0;
   a.gn_eps = d.gn_eps;
   a.tiles_per_b = a.hw / kPix;
+  if (split_mlp) {
+    __nv_bfloat16 *w_hi, *w_lo;
+    ltae_mlp_tc_buffers(d, ws + lay.tc, &a.o_hi, &a.o_lo, &w_hi, &w_lo);
+  }
   const long long n_tiles = static_cast<long long>(d.B) * a.tiles_per_b;
   if (n_tiles > 0x7fffffffll) C2S_UNSUPPORTED("c2s_ltae_forward: too many pixel tiles");
   if (C == 128) {
@@ -705,6 +729,7 @@ int ltae_mma_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const voi
     ltae_mma_kernel<64><<<static_cast<unsigned>(n_tiles), kThreads, Smem<64>::kTotal, stream>>>(a);
     C2S_LAUNCH_CHECK("ltae_forward<mma,C=64>");
   }
+  if (split_mlp) return ltae_mlp_tc_forward(d, p, ws + lay.tc, a.bnf, a.ypre, out, stream);
   return C2S_OK;
 }
 

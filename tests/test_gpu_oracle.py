@@ -106,8 +106,14 @@ def test_tensor_core_path_is_selected():
     kind, kw, (b, t, h, w), lengths, _ = LTAE_CASES["utae"]
     m, rng = _build(kind, kw, 1)
     x, pos, pad = synth_inputs(rng, b, t, 128, h, w, lengths)
-    _, kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
+    (out_tc, attn_tc), kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
+    assert kernel == "ltae_mlp<tcgen05>"  # attention kernel (mma.sync) followed by the tcgen05 row GEMM of the MLP
+    with env("C2S_LTAE_NO_TCGEN05", True):
+        (out_mma, attn_mma), kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
     assert kernel == "ltae_forward<mma,C=128>"
+    assert torch.equal(attn_tc, attn_mma)
+    # same hi/lo bf16 products, different accumulation order: equal up to the bf16 rounding of the output
+    assert rel_err(out_tc.float().cpu().numpy(), out_mma.float().cpu().numpy()) < 1e-2
     _, kernel = _call(m, kind, x, pos, pad, general=True, dtype=torch.bfloat16)
     assert kernel == "ltae_forward<general>"
     _, kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.float32)
