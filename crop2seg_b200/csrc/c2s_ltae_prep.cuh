@@ -34,12 +34,14 @@ struct LtaeWorkspace {
   size_t bnpart; // [2, c_out, parts] partial batch statistics (training mode only)
   size_t frag;   // fragment-ordered weights of the tensor-core path
   size_t tc;     // tcgen05 MLP: o hi/lo rows + mlp weight hi/lo
+  size_t tca;    // tcgen05 attention: score weight tiles
   size_t total;  // floats
 };
 
 inline size_t align64(size_t n) { return (n + 63) & ~static_cast<size_t>(63); }
 size_t ltae_mma_workspace_floats(const c2s_ltae_desc& d);
 size_t ltae_mlp_tc_workspace_floats(const c2s_ltae_desc& d);
+size_t ltae_tc_workspace_floats(const c2s_ltae_desc& d);
 
 inline LtaeWorkspace ltae_workspace(const c2s_ltae_desc& d) {
   LtaeWorkspace w{};
@@ -66,6 +68,7 @@ inline LtaeWorkspace ltae_workspace(const c2s_ltae_desc& d) {
   w.bnpart = take(train ? 2 * co * 1024 : 0);
   w.frag = take(ltae_mma_workspace_floats(d));
   w.tc = take(ltae_mlp_tc_workspace_floats(d));
+  w.tca = take(ltae_tc_workspace_floats(d));
   w.total = off;
   return w;
 }
@@ -82,6 +85,12 @@ void ltae_mlp_tc_buffers(const c2s_ltae_desc& d, float* ws, __nv_bfloat16** o_hi
                          __nv_bfloat16** w_hi, __nv_bfloat16** w_lo);
 int ltae_mlp_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, float* tc_ws, const float* bnf, float* ypre,
                         void* out, cudaStream_t stream);
+
+// tcgen05 attention kernel (c2s_ltae_tc.cu), opt-in with C2S_LTAE_TC while it only covers the attention-only encoder
+bool ltae_tc_enabled();
+bool ltae_tc_eligible(const c2s_ltae_desc& d);
+int ltae_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask, float* attn,
+                    float* ws, const LtaeWorkspace& lay, float* tc_ws, cudaStream_t stream);
 
 int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* positions, float* ws,
                  const LtaeWorkspace& lay, bool need_transposed, cudaStream_t stream);
