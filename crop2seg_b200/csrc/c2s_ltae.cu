@@ -583,7 +583,7 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
   const int hw = d.H * d.W;
   float* ypre = train ? ws + lay.ypre : nullptr;
   if (use_mma && ltae_tc_enabled() && ltae_tc_eligible(d)) {
-    status = ltae_tc_forward(d, p, x, pad_mask, attn, ws, lay, ws + lay.tca, stream);
+    status = ltae_tc_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.tca, stream);
     if (status != C2S_OK) return status;
   } else if (use_mma) {
     status = ltae_mma_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.frag, stream);

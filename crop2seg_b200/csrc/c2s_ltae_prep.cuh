@@ -89,8 +89,8 @@ int ltae_mlp_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, float*
 // tcgen05 attention kernel (c2s_ltae_tc.cu), opt-in with C2S_LTAE_TC while it only covers the attention-only encoder
 bool ltae_tc_enabled();
 bool ltae_tc_eligible(const c2s_ltae_desc& d);
-int ltae_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask, float* attn,
-                    float* ws, const LtaeWorkspace& lay, float* tc_ws, cudaStream_t stream);
+int ltae_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask, void* out,
+                    float* attn, float* ws, const LtaeWorkspace& lay, float* tc_ws, cudaStream_t stream);
 
 int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* positions, float* ws,
                  const LtaeWorkspace& lay, bool need_transposed, cudaStream_t stream);

@@ -1,23 +1,36 @@
+"""Development check of the tcgen05 attention kernel (C2S_LTAE_TC=1) against the oracle and the mma.sync kernel."""
 import os, sys, numpy as np, torch
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import crop2seg_b200 as c2s
 from crop2seg_b200 import _lib
-from oracle import ltae4wtae_forward
+from oracle import ltae4wtae_forward, ltae_forward
 from c2s_testlib import *
 from golden_util import rel_err
-for C,(b,t,h,w),lengths in [(128,(2,61,8,8),[61,27]),(128,(3,17,4,4),[17,0,1]),(64,(2,40,4,8),[40,33])]:
-    kw=dict(in_channels=C,n_head=16,d_k=4,d_model=256)
-    rng=np.random.RandomState(3)
-    m=c2s.LTAE4WTAE(**kw); randomise(m,rng); m=m.cuda().eval()
-    for zp in (False,True):
-        m.assume_zero_padded=zp
-        x,pos,pad=synth_inputs(rng,b,t,C,h,w,lengths)
-        ref=ltae4wtae_forward(oracle_config('ltae4wtae',kw),oracle_params(m),bf16_round(x),pos,pad)
-        os.environ.pop('C2S_LTAE_TC',None)
-        with torch.no_grad(): a0=m(to_dev(x,dtype=torch.bfloat16),batch_positions=to_dev(pos),pad_mask=to_dev(pad))
-        k0=_lib.last_kernel()
-        os.environ['C2S_LTAE_TC']='1'
-        with torch.no_grad(): a1=m(to_dev(x,dtype=torch.bfloat16),batch_positions=to_dev(pos),pad_mask=to_dev(pad))
-        torch.cuda.synchronize()
-        k1=_lib.last_kernel()
-        print(C,(b,t,h,w),zp,k0,rel_err(a0.cpu().numpy(),ref),k1,rel_err(a1.cpu().numpy(),ref), float(a1.sum(2).sub(1).abs().max()))
+cases = [("ltae4wtae", 128, (2, 61, 8, 8), [61, 27], {}), ("ltae", 128, (2, 61, 8, 8), [61, 27], {}),
+         ("ltae", 128, (3, 17, 4, 4), [17, 0, 1], {}), ("ltae", 64, (2, 40, 4, 8), [40, 33], {}),
+         ("ltae", 128, (2, 33, 4, 4), [33, 30], {"positional_encoding": False}),
+         ("ltae", 128, (2, 40, 4, 4), [40, 28], {"use_doy": True})]
+for kind, C, (b, t, h, w), lengths, extra in cases:
+    kw = dict(in_channels=C, n_head=16, d_k=4, d_model=256, **extra)
+    if kind == "ltae": kw["mlp"] = [256, C]
+    rng = np.random.RandomState(3)
+    m = (c2s.LTAE if kind == "ltae" else c2s.LTAE4WTAE)(**kw); randomise(m, rng); m = m.cuda().eval()
+    for zp in (False, True):
+        m.assume_zero_padded = zp
+        x, pos, pad = synth_inputs(rng, b, t, C, h, w, lengths, doy=bool(extra.get("use_doy")))
+        if extra.get("positional_encoding") is False: pos = None
+        if kind == "ltae":
+            ref_o, ref_a = ltae_forward(oracle_config(kind, kw), oracle_params(m), bf16_round(x), pos, pad)
+        else:
+            ref_o, ref_a = None, ltae4wtae_forward(oracle_config(kind, kw), oracle_params(m), bf16_round(x), pos, pad)
+        res = {}
+        for tc in (False, True):
+            os.environ.pop('C2S_LTAE_TC', None)
+            if tc: os.environ['C2S_LTAE_TC'] = '1'
+            with torch.no_grad():
+                r = m(to_dev(x, dtype=torch.bfloat16), batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+            torch.cuda.synchronize()
+            o, a_ = (r if kind == "ltae" else (None, r))
+            res[tc] = (_lib.last_kernel(), rel_err(a_.cpu().numpy(), ref_a), None if o is None else rel_err(o.float().cpu().numpy(), ref_o))
+        print(kind, C, (b, t, h, w), zp, extra, res[False], res[True], flush=True)
