@@ -21,6 +21,7 @@ LTAE_ATTN_ONLY, LTAE_SKIP_ATTN_STORE, LTAE_ZERO_PADDED, LTAE_BN_BATCH_STATS = 1,
 
 EXPORTS = (
     "c2s_abi_version", "c2s_last_error", "c2s_launch_count", "c2s_reset_launch_count", "c2s_last_kernel",
+    "c2s_last_ltae_kernel",
     "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_agg_backward_workspace_bytes", "c2s_agg_backward",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward",
 )
@@ -75,6 +76,7 @@ def load() -> ctypes.CDLL:
         lib.c2s_abi_version.restype = i32
         lib.c2s_last_error.restype = ctypes.c_char_p
         lib.c2s_last_kernel.restype = ctypes.c_char_p
+        lib.c2s_last_ltae_kernel.restype = ctypes.c_char_p
         lib.c2s_launch_count.restype = ctypes.c_int64
         lib.c2s_reset_launch_count.restype = None
         lib.c2s_agg_workspace_bytes.restype = sz
@@ -113,3 +115,8 @@ def reset_launch_count() -> None:
 
 def last_kernel() -> str:
     return load().c2s_last_kernel().decode("utf-8", "replace")
+
+
+def last_ltae_kernel() -> str:
+    """The L-TAE attention kernel that served the last ``c2s_ltae_forward`` call."""
+    return load().c2s_last_ltae_kernel().decode("utf-8", "replace")

@@ -10,6 +10,7 @@ namespace {
 thread_local char g_error[512] = "";
 // process-wide (autograd runs backward kernels on its own thread); diagnostics only
 char g_kernel[128] = "";
+char g_ltae_kernel[128] = "";
 std::atomic<int64_t> g_launches{0};
 }  // namespace
 
@@ -24,6 +25,10 @@ void note_launch(const char* kernel_name) {
   ++g_launches;
   strncpy(g_kernel, kernel_name, sizeof(g_kernel) - 1);
   g_kernel[sizeof(g_kernel) - 1] = '\0';
+  if (strncmp(kernel_name, "ltae_forward", 12) == 0) {
+    strncpy(g_ltae_kernel, kernel_name, sizeof(g_ltae_kernel) - 1);
+    g_ltae_kernel[sizeof(g_ltae_kernel) - 1] = '\0';
+  }
 }
 
 int check_device() {
@@ -65,5 +70,6 @@ int64_t c2s_launch_count(void) { return c2s::g_launches.load(); }
 void c2s_reset_launch_count(void) { c2s::g_launches.store(0); }
 
 const char* c2s_last_kernel(void) { return c2s::g_kernel; }
+const char* c2s_last_ltae_kernel(void) { return c2s::g_ltae_kernel; }
 
 }  // extern "C"

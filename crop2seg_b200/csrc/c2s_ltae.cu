@@ -582,7 +582,10 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
 
   const int hw = d.H * d.W;
   float* ypre = train ? ws + lay.ypre : nullptr;
-  if (use_mma && ltae_tc_enabled() && ltae_tc_eligible(d)) {
+  if (use_mma && !ltae_tc_enabled() && ltae_fa_eligible(d)) {
+    status = ltae_fa_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.fa, stream);
+    if (status != C2S_OK) return status;
+  } else if (use_mma && ltae_tc_enabled() && ltae_tc_eligible(d)) {
     status = ltae_tc_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.tca, stream);
     if (status != C2S_OK) return status;
   } else if (use_mma) {

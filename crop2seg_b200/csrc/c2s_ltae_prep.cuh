@@ -35,6 +35,7 @@ struct LtaeWorkspace {
   size_t frag;   // fragment-ordered weights of the tensor-core path
   size_t tc;     // tcgen05 MLP: o hi/lo rows + mlp weight hi/lo
   size_t tca;    // tcgen05 attention: score weight tiles
+  size_t fa;     // persistent TMA kernel: score / in-projection / MLP weight fragments, scales
   size_t total;  // floats
 };
 
@@ -42,6 +43,7 @@ inline size_t align64(size_t n) { return (n + 63) & ~static_cast<size_t>(63); }
 size_t ltae_mma_workspace_floats(const c2s_ltae_desc& d);
 size_t ltae_mlp_tc_workspace_floats(const c2s_ltae_desc& d);
 size_t ltae_tc_workspace_floats(const c2s_ltae_desc& d);
+size_t ltae_fa_workspace_floats(const c2s_ltae_desc& d);
 
 inline LtaeWorkspace ltae_workspace(const c2s_ltae_desc& d) {
   LtaeWorkspace w{};
@@ -69,6 +71,7 @@ inline LtaeWorkspace ltae_workspace(const c2s_ltae_desc& d) {
   w.frag = take(ltae_mma_workspace_floats(d));
   w.tc = take(ltae_mlp_tc_workspace_floats(d));
   w.tca = take(ltae_tc_workspace_floats(d));
+  w.fa = take(ltae_fa_workspace_floats(d));
   w.total = off;
   return w;
 }
@@ -91,6 +94,11 @@ bool ltae_tc_enabled();
 bool ltae_tc_eligible(const c2s_ltae_desc& d);
 int ltae_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask, void* out,
                     float* attn, float* ws, const LtaeWorkspace& lay, float* tc_ws, cudaStream_t stream);
+
+// persistent TMA-fed kernel (c2s_ltae_fa.cu): the default for the shapes ltae_mma_eligible accepts
+bool ltae_fa_eligible(const c2s_ltae_desc& d);
+int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask, void* out,
+                    float* attn, float* ws, const LtaeWorkspace& lay, float* fa_ws, cudaStream_t stream);
 
 int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* positions, float* ws,
                  const LtaeWorkspace& lay, bool need_transposed, cudaStream_t stream);

@@ -170,6 +170,9 @@ int64_t c2s_launch_count(void);
 void c2s_reset_launch_count(void);
 /* Name of the kernel the library launched last (diagnostics). */
 const char* c2s_last_kernel(void);
+/* Name of the last L-TAE attention kernel ("ltae_forward<...>") the library launched (diagnostics: which of the
+ * kernels behind c2s_ltae_forward served the call). */
+const char* c2s_last_ltae_kernel(void);
 
 #ifdef __cplusplus
 }

@@ -106,18 +106,58 @@ def test_tensor_core_path_is_selected():
     kind, kw, (b, t, h, w), lengths, _ = LTAE_CASES["utae"]
     m, rng = _build(kind, kw, 1)
     x, pos, pad = synth_inputs(rng, b, t, 128, h, w, lengths)
-    (out_tc, attn_tc), kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
-    assert kernel == "ltae_mlp<tcgen05>"  # attention kernel (mma.sync) followed by the tcgen05 row GEMM of the MLP
-    with env("C2S_LTAE_NO_TCGEN05", True):
+    (out_fa, attn_fa), kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
+    # persistent TMA kernel (mma.sync attention) followed by the tcgen05 row GEMM of the MLP
+    assert kernel == "ltae_mlp<tcgen05>" and _lib.last_ltae_kernel() == "ltae_forward<fa,C=128>"
+    with env("C2S_LTAE_MMA", True):  # the older register-staged kernel, kept for comparison
         (out_mma, attn_mma), kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
+    assert kernel == "ltae_mlp<tcgen05>" and _lib.last_ltae_kernel() == "ltae_forward<mma,C=128>"
+    assert rel_err(attn_fa.cpu().numpy(), attn_mma.cpu().numpy()) < 1e-4
+    assert rel_err(out_fa.float().cpu().numpy(), out_mma.float().cpu().numpy()) < 1e-2
+    with env("C2S_LTAE_NO_TCGEN05", True):
+        (out_in, attn_in), kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
     assert kernel == "ltae_forward<mma,C=128>"
-    assert torch.equal(attn_tc, attn_mma)
+    assert torch.equal(attn_in, attn_mma)
     # same hi/lo bf16 products, different accumulation order: equal up to the bf16 rounding of the output
-    assert rel_err(out_tc.float().cpu().numpy(), out_mma.float().cpu().numpy()) < 1e-2
+    assert rel_err(out_in.float().cpu().numpy(), out_mma.float().cpu().numpy()) < 1e-2
     _, kernel = _call(m, kind, x, pos, pad, general=True, dtype=torch.bfloat16)
     assert kernel == "ltae_forward<general>"
     _, kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.float32)
     assert kernel == "ltae_forward<general>"  # fp32 features keep the fp32 CUDA-core kernel
+
+
+MULTI_TILE_CASES = {
+    # more tiles than SMs: every CTA of the persistent kernel walks over several tiles (and, with C = 64, both slabs)
+    "utae_many": ("ltae", dict(in_channels=128, n_head=16, d_k=4, mlp=[256, 128], d_model=256), (70, 61, 8, 8)),
+    "timeunet_many": ("ltae", dict(in_channels=64, n_head=16, d_k=4, mlp=[256, 64], d_model=256), (5, 61, 16, 16)),
+    "wtae_many": ("ltae4wtae", dict(in_channels=128, n_head=16, d_k=4, d_model=256), (40, 33, 8, 8)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MULTI_TILE_CASES))
+@pytest.mark.parametrize("zero_padded", [False, True])
+def test_persistent_ltae_many_tiles(name, zero_padded):
+    kind, kw, (b, t, h, w) = MULTI_TILE_CASES[name]
+    m, rng = _build(kind, kw, 6000 + len(name))
+    m.assume_zero_padded = zero_padded
+    lengths = [t] + [max(1, t - (i * 7) % (t // 2 + 1)) for i in range(1, b)]
+    lengths[b // 2] = 0  # one series without a single valid frame
+    x, pos, pad = synth_inputs(rng, b, t, kw["in_channels"], h, w, lengths)
+    xr = bf16_round(x)
+    cfg, params = oracle_config(kind, kw), oracle_params(m)
+    if kind == "ltae":
+        ref_out, ref_attn = ltae_forward(cfg, params, xr, pos, pad)
+    else:
+        ref_out, ref_attn = None, ltae4wtae_forward(cfg, params, xr, pos, pad)
+    (out, attn), _ = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
+    assert _lib.last_ltae_kernel().startswith("ltae_forward<fa")
+    a = attn.cpu().numpy()
+    assert rel_err(a, ref_attn) < 1e-3
+    assert np.all(np.abs(a.sum(axis=2) - 1.0) < 1e-5)
+    for bi in np.nonzero(~pad.all(axis=1))[0]:
+        assert np.all(a[:, bi, pad[bi]] == 0.0)
+    if kind == "ltae":
+        assert rel_err(out.float().cpu().numpy(), ref_out) < 1e-2
 
 
 def test_tensor_core_ltae_train_mode_batch_statistics():
