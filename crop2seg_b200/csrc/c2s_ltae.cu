@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <mutex>
+
 #include "c2s_ltae_prep.cuh"
 
 namespace c2s {
@@ -506,6 +508,25 @@ int launch_general(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void*
   return C2S_OK;
 }
 
+// Workspaces whose weight-only preparation was built by the persistent path (most recent 16).  Returns whether
+// `ws` was in the set before the call; `mark` adds it, otherwise it is removed.
+bool fa_prepared(const void* ws, bool mark) {
+  static std::mutex mu;
+  static const void* recent[16] = {};
+  static int next = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  int at = -1;
+  for (int i = 0; i < 16; ++i)
+    if (recent[i] == ws) at = i;
+  if (mark && at < 0) {
+    recent[next] = ws;
+    next = (next + 1) % 16;
+  } else if (!mark && at >= 0) {
+    recent[at] = nullptr;
+  }
+  return at >= 0;
+}
+
 }  // namespace
 }  // namespace c2s
 
@@ -521,7 +542,7 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
                      void* workspace, size_t workspace_bytes, void* stream_ptr) {
   using namespace c2s;
   C2S_CHECK_ARG(dp != nullptr && pp != nullptr, "c2s_ltae_forward: desc/params is NULL");
-  const c2s_ltae_desc& d = *dp;
+  c2s_ltae_desc d = *dp;  // local copy: C2S_LTAE_REUSE_FOLDED is dropped when this workspace was not prepared that way
   const c2s_ltae_params& p = *pp;
   const bool attn_only = (d.flags & C2S_LTAE_ATTN_ONLY) != 0;
   const bool train = (d.flags & C2S_LTAE_BN_BATCH_STATS) != 0 && !attn_only;
@@ -577,12 +598,15 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
   float* ws = static_cast<float*>(workspace);
   const bool force_general = getenv("C2S_LTAE_FORCE_GENERAL") != nullptr;  // test hook: compare both kernels
   const bool use_mma = !force_general && ltae_mma_eligible(d, x, out);
+  const bool use_fa = use_mma && !ltae_tc_enabled() && ltae_fa_eligible(d);
+  // the reuse flag is honoured only if the previous call on this very workspace went through the same (persistent) path
+  if (!(use_fa && fa_prepared(workspace, /*mark=*/use_fa))) d.flags &= ~C2S_LTAE_REUSE_FOLDED;
   status = ltae_prepare(d, p, positions, ws, lay, /*need_transposed=*/!use_mma, stream);
   if (status != C2S_OK) return status;
 
   const int hw = d.H * d.W;
   float* ypre = train ? ws + lay.ypre : nullptr;
-  if (use_mma && !ltae_tc_enabled() && ltae_fa_eligible(d)) {
+  if (use_fa) {
     status = ltae_fa_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.fa, stream);
     if (status != C2S_OK) return status;
   } else if (use_mma && ltae_tc_enabled() && ltae_tc_eligible(d)) {

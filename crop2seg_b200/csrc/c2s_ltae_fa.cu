@@ -903,11 +903,14 @@ int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void
   float* wscale = reinterpret_cast<float*>(wc16 + align64(static_cast<size_t>(kD) * C));
   unsigned long long* masks = reinterpret_cast<unsigned long long*>(wscale + align64(2));
 
-  fa_build_ufrag_kernel<<<ceil_div((C / 16) * 256, 256), 256, 0, stream>>>(ws + lay.u, ufrag, C);
-  C2S_LAUNCH_CHECK("ltae_fa_build_ufrag");
+  const bool reuse = (d.flags & C2S_LTAE_REUSE_FOLDED) != 0;
+  if (!reuse) {
+    fa_build_ufrag_kernel<<<ceil_div((C / 16) * 256, 256), 256, 0, stream>>>(ws + lay.u, ufrag, C);
+    C2S_LAUNCH_CHECK("ltae_fa_build_ufrag");
+  }
   fa_masks_kernel<<<ceil_div(d.B, 128), 128, 0, stream>>>(pad_mask, masks, d.B, d.T, (d.flags & C2S_LTAE_ZERO_PADDED) != 0);
   C2S_LAUNCH_CHECK("ltae_fa_masks");
-  if (!attn_only) {
+  if (!attn_only && !reuse) {
     fa_weight_scale_kernel<<<1, 1024, 0, stream>>>(p.inconv_weight, kD * C, wscale);
     C2S_LAUNCH_CHECK("ltae_fa_weight_scale");
     fa_build_w16_kernel<<<ceil_div((kD / 16) * (C / 16) * 128, 256), 256, 0, stream>>>(p.inconv_weight, wscale, wc16, kD, C);

@@ -296,8 +296,10 @@ int ltae_mlp_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, float*
   ltae_mlp_tc_buffers(d, tc_ws, &o_hi, &o_lo, &w_hi, &w_lo);
   const size_t rows = static_cast<size_t>(d.B) * d.H * d.W;
   const size_t nw = static_cast<size_t>(d.c_out) * kK;
-  split_rows_kernel<<<ceil_div(nw, 256), 256, 0, stream>>>(p.mlp_weight, w_hi, w_lo, nw);
-  C2S_LAUNCH_CHECK("ltae_split_mlp_weight");
+  if (!(d.flags & C2S_LTAE_REUSE_FOLDED)) {
+    split_rows_kernel<<<ceil_div(nw, 256), 256, 0, stream>>>(p.mlp_weight, w_hi, w_lo, nw);
+    C2S_LAUNCH_CHECK("ltae_split_mlp_weight");
+  }
   CUtensorMap m_ohi, m_olo, m_whi, m_wlo;
   int status = make_map(&m_ohi, o_hi, rows, kRows);
   if (status == C2S_OK) status = make_map(&m_olo, o_lo, rows, kRows);

@@ -184,6 +184,8 @@ int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* p
   float* qk = ws + lay.qk;
   if (has_pe && (h > kMaxHeads || kPrepThreads < 16 * h)) C2S_UNSUPPORTED("ltae_prepare: n_head=%d too large", h);
 
+  const bool reuse = (d.flags & C2S_LTAE_REUSE_FOLDED) != 0;  // the weight-only blocks of ws are still valid
+  if (!reuse) {
   fold_qk_kernel<<<ceil_div(h * D, kPrepThreads), kPrepThreads, 0, stream>>>(p.query, p.key_weight, qk, h, dk, D);
   C2S_LAUNCH_CHECK("ltae_fold_qk");
   fold_u_kernel<<<dim3(ceil_div(C, 32), kMaxHeads), 256, 0, stream>>>(qk, p.inconv_weight, p.in_norm_weight, ws + lay.u,
@@ -210,6 +212,7 @@ int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* p
       C2S_LAUNCH_CHECK("ltae_fold_bn");
     }
   }
+  }  // !reuse
   const size_t n_bt = static_cast<size_t>(d.B) * d.T;
   if (has_pe) {
     const int stride = d.pe_abs ? 2 : 1;

@@ -105,6 +105,32 @@ class _LTAEBase(nn.Module):
         #: set by the caller (``crop2seg_b200.install`` does) when padded frames of x are exactly zero, as
         #: ``smart_forward`` guarantees with pad_value=0 (temp_shared_block.py:30-40); padded frames are then not read
         self.assume_zero_padded = False
+        #: eval mode keeps the folded weights between calls while no parameter changes (``Tensor._version`` and
+        #: ``data_ptr`` of every parameter / buffer); writes through ``.data`` bypass the version counters -- call
+        #: ``invalidate_folded_weights()`` after those, or set this to False
+        self.cache_folded_weights = True
+        self._folded_cache = {}
+
+    def invalidate_folded_weights(self):
+        """Forget the cached weight preparation (needed only after parameter writes that bypass autograd's version
+        counters, e.g. ``p.data.copy_(...)`` between two eval-mode calls)."""
+        self._folded_cache.clear()
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .half(): new storages
+        self._folded_cache.clear()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._folded_cache.clear()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _folded_args(self):
+        """kwargs for ops.ltae_forward: reuse of the weight-only preparation in eval mode."""
+        if self.training or not self.cache_folded_weights:
+            return {}
+        tensors = list(self.parameters()) + list(self.buffers())
+        key = tuple((t._version, t.data_ptr()) for t in tensors)
+        return {"folded_cache": self._folded_cache, "folded_key": key}
 
     # -- helpers ---------------------------------------------------------------------------------
     def _pe_mode(self) -> int:
@@ -227,7 +253,7 @@ class LTAE(_LTAEBase):
                 has_inconv=self.inconv is not None, c_out=c_out, pe_mode=self._pe_mode(),
                 pe_abs=self.use_abs_rel_enc, need_attn=return_att, zero_padded=self.assume_zero_padded,
                 bn_batch_stats=train_bn, gn_eps=self.in_norm.eps, bn_eps=bn.eps, attn_keep=attn_keep,
-                attn_drop_p=attn_p, mlp_keep=mlp_keep, mlp_drop_p=mlp_p)
+                attn_drop_p=attn_p, mlp_keep=mlp_keep, mlp_drop_p=mlp_p, **self._folded_args())
         if stats is not None and self.training and bn.track_running_stats:
             self._update_running_stats(bn, stats, b * h * w)
         return out, (attn if return_att else None)
@@ -272,7 +298,7 @@ class LTAE4WTAE(_LTAEBase):
             x, batch_positions, pad_mask, params, n_head=self.n_head, d_k=self.d_k,
             d_model=self.d_model, has_inconv=self.inconv is not None, c_out=0, pe_mode=self._pe_mode(),
             pe_abs=self.use_abs_rel_enc, attn_only=True, zero_padded=self.assume_zero_padded,
-            gn_eps=self.in_norm.eps, attn_keep=attn_keep, attn_drop_p=attn_p)
+            gn_eps=self.in_norm.eps, attn_keep=attn_keep, attn_drop_p=attn_p, **self._folded_args())
         return attn
 
 

@@ -14,6 +14,7 @@ from . import _lib
 
 _AGG_MODES = {"att_group": _lib.AGG_ATT_GROUP, "att_mean": _lib.AGG_ATT_MEAN, "mean": _lib.AGG_MEAN}
 _DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+_FOLDED_CACHE_MAX_BYTES = 64 << 20  # larger L-TAE workspaces are transient (their preparation is noise there)
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -151,11 +152,15 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
                  has_inconv: bool, c_out: int, pe_mode: int, pe_abs: bool = False, attn_only: bool = False,
                  need_attn: bool = True, zero_padded: bool = False, bn_batch_stats: bool = False,
                  gn_eps: float = 1e-5, bn_eps: float = 1e-5, attn_keep: Optional[torch.Tensor] = None,
-                 attn_drop_p: float = 0.0, mlp_keep: Optional[torch.Tensor] = None, mlp_drop_p: float = 0.0
+                 attn_drop_p: float = 0.0, mlp_keep: Optional[torch.Tensor] = None, mlp_drop_p: float = 0.0,
+                 folded_cache: Optional[dict] = None, folded_key=None
                  ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[Tuple[torch.Tensor, torch.Tensor]]]:
     """Fused ``LTAE.forward`` / ``LTAE4WTAE.forward`` (tae.py:451-504, 589-635).
 
     ``params`` maps the field names of ``c2s_ltae_params`` to tensors (or None).
+    ``folded_cache`` (a dict owned by the caller) with ``folded_key`` (anything that changes whenever a parameter
+    does) keeps the workspace between calls: while key, shapes and flags repeat, the weight-only preparation kernels
+    are skipped (``C2S_LTAE_REUSE_FOLDED``).  Workspaces above 64 MiB are never kept.
     Returns ``(out[B,c_out,H,W] | None, attn[h,B,T,H,W] | None, (batch_mean, batch_var) | None)``.
     """
     if x.dim() != 5:
@@ -217,7 +222,18 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
     lib = _lib.load()
     with torch.cuda.device(dev):
         ws_bytes = lib.c2s_ltae_workspace_bytes(ctypes.byref(desc))
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        ws = None
+        if folded_cache is not None and ws_bytes <= _FOLDED_CACHE_MAX_BYTES:
+            key = (folded_key, dev, b, t, c, h, w, n_head, d_k, d_model, desc.c_out, int(has_inconv), pe_mode,
+                   int(pe_abs), desc.dtype, flags, float(gn_eps), float(bn_eps))
+            if folded_cache.get("key") == key and folded_cache.get("ws") is not None:
+                ws = folded_cache["ws"]
+                desc.flags = flags | _lib.LTAE_REUSE_FOLDED
+            else:
+                ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+                folded_cache["key"], folded_cache["ws"] = key, ws
+        if ws is None:
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         status = lib.c2s_ltae_forward(ctypes.byref(desc), ctypes.byref(cparams), x.data_ptr(), _ptr(pos), _ptr(pad),
                                       _ptr(out), _ptr(attn), _ptr(stats[0]) if stats else None,
                                       _ptr(stats[1]) if stats else None, ws.data_ptr(), ws_bytes, _stream(dev))

@@ -54,7 +54,10 @@ enum c2s_ltae_flags {
   C2S_LTAE_SKIP_ATTN_STORE = 1 << 1, /* caller does not consume attn (model-level return_att=False)  */
   C2S_LTAE_ZERO_PADDED = 1 << 2,     /* caller guarantees x == 0 on padded frames (temp_shared_block.py:30-40):
                                         padded frames are then never read                             */
-  C2S_LTAE_BN_BATCH_STATS = 1 << 3   /* training: BatchNorm1d uses batch statistics (tae.py:445)     */
+  C2S_LTAE_BN_BATCH_STATS = 1 << 3,  /* training: BatchNorm1d uses batch statistics (tae.py:445)     */
+  C2S_LTAE_REUSE_FOLDED = 1 << 4     /* the workspace is the one of the previous call with the same descriptor and
+                                        UNCHANGED parameters: the weight-only preparation (folded score / projection
+                                        weights, fragment orders) is not rebuilt; positions and masks still are */
 };
 
 /* ------------------------------------------------------------------------------------------

@@ -166,3 +166,25 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         c2s.shard_bounds(4, 2, 2)
+
+
+def test_copy_valid_frames_skips_padding():
+    import torch
+    from crop2seg_b200 import copy_valid_frames_, valid_lengths
+    src = torch.arange(4 * 5 * 3, dtype=torch.float32).reshape(4, 5, 3)
+    dst = torch.full_like(src, -1.0)
+    lengths = [5, 2, 0, 5]
+    n = copy_valid_frames_(dst, src, lengths)
+    assert n == (5 + 2 + 0 + 5) * 3 * 4
+    for b, L in enumerate(lengths):
+        assert torch.equal(dst[b, :L], src[b, :L]) and bool((dst[b, L:] == -1).all())
+    copy_valid_frames_(dst, src, lengths, zero_rest=True)
+    assert bool((dst[1, 2:] == 0).all()) and bool((dst[2] == 0).all())
+    pad = torch.tensor([[False] * 5, [False, False, True, True, True], [True] * 5, [False] * 5])
+    assert valid_lengths(pad) == lengths
+    bad = torch.tensor([[False, True, False]])
+    import pytest
+    with pytest.raises(ValueError):
+        valid_lengths(bad)
+    with pytest.raises(ValueError):
+        copy_valid_frames_(dst, src[:, :4], lengths)

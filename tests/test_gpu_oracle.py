@@ -205,3 +205,35 @@ def test_pipelined_aggregator_matches_oracle(name, dtype):
         assert rel_err(outs[no_pipe].float().cpu().numpy(), ref) < (1e-5 if dtype == torch.float32 else 1e-2)
     # same taps, same accumulation order: the two kernels agree bit for bit
     assert torch.equal(outs[False], outs[True])
+
+
+def test_folded_weights_are_reused_until_a_parameter_changes():
+    kind, kw, (b, t, h, w), lengths, _ = LTAE_CASES["utae"]
+    m, rng = _build(kind, kw, 31)
+    x, pos, pad = synth_inputs(rng, b, t, 128, h, w, lengths)
+    args = (to_dev(x, dtype=torch.bfloat16),)
+    kwargs = dict(batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+    with torch.no_grad():
+        _lib.reset_launch_count()
+        out0, attn0 = m(*args, **kwargs)
+        first = _lib.launch_count()
+        _lib.reset_launch_count()
+        out1, attn1 = m(*args, **kwargs)
+        second = _lib.launch_count()
+        assert second < first, (first, second)          # the weight-only preparation kernels were skipped
+        assert torch.equal(out0, out1) and torch.equal(attn0, attn1)
+        m.attention_head.Q.mul_(1.5)                     # in-place update: the version counter moves
+        m.mlp[0].weight.add_(0.01)
+        _lib.reset_launch_count()
+        out2, attn2 = m(*args, **kwargs)
+        assert _lib.launch_count() == first
+    ref_out, ref_attn = ltae_forward(oracle_config(kind, kw), oracle_params(m), bf16_round(x), pos, pad)
+    assert rel_err(attn2.cpu().numpy(), ref_attn) < 1e-3
+    assert rel_err(out2.float().cpu().numpy(), ref_out) < 1e-2
+    assert not torch.equal(attn2, attn0)
+    m.cache_folded_weights = False
+    with torch.no_grad():
+        _lib.reset_launch_count()
+        out3, attn3 = m(*args, **kwargs)
+        assert _lib.launch_count() == first
+    assert torch.equal(out3, out2) and torch.equal(attn3, attn2)
