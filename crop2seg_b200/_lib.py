@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 2
+C2S_ABI_VERSION = 3
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -23,7 +23,7 @@ EXPORTS = (
     "c2s_abi_version", "c2s_last_error", "c2s_launch_count", "c2s_reset_launch_count", "c2s_last_kernel",
     "c2s_last_ltae_kernel",
     "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_agg_backward_workspace_bytes", "c2s_agg_backward",
-    "c2s_ltae_workspace_bytes", "c2s_ltae_forward",
+    "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
 )
 
 
@@ -48,7 +48,15 @@ LTAE_MASK_FIELDS = ("attn_keep", "mlp_keep")  # uint8 dropout keep masks (traini
 
 
 class LtaeParams(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_PARAM_FIELDS + LTAE_MASK_FIELDS]
+    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_PARAM_FIELDS + LTAE_MASK_FIELDS + ("save_o",)]
+
+
+LTAE_BWD_IO_FIELDS = ("grad_o", "grad_attn", "grad_x", "grad_u", "grad_cpos", "grad_gamma", "grad_beta", "zn_rows",
+                      "sa_rows", "grad_pe")
+
+
+class LtaeBwdIo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_BWD_IO_FIELDS]
 
 
 class C2SError(RuntimeError):
@@ -92,6 +100,11 @@ def load() -> ctypes.CDLL:
         lib.c2s_ltae_forward.restype = i32
         lib.c2s_ltae_forward.argtypes = [ctypes.POINTER(LtaeDesc), ctypes.POINTER(LtaeParams), vp, vp, vp, vp, vp,
                                          vp, vp, vp, sz, vp]
+        lib.c2s_ltae_backward_workspace_bytes.restype = sz
+        lib.c2s_ltae_backward_workspace_bytes.argtypes = [ctypes.POINTER(LtaeDesc)]
+        lib.c2s_ltae_backward.restype = i32
+        lib.c2s_ltae_backward.argtypes = [ctypes.POINTER(LtaeDesc), ctypes.POINTER(LtaeParams), vp, vp, vp,
+                                          ctypes.POINTER(LtaeBwdIo), vp, sz, vp]
         got = lib.c2s_abi_version()
         if got != C2S_ABI_VERSION:
             raise C2SError(f"ABI mismatch: library reports version {got}, binding expects {C2S_ABI_VERSION}")

@@ -3,14 +3,23 @@
 * ``AggregateFunction``: forward AND backward are CUDA kernels (``c2s_agg_forward`` / ``c2s_agg_backward``) --
   the aggregations move 97.7 % of the hot path's bytes.
 * ``LtaeFunction``: the forward is the fused CUDA kernel (train-mode BatchNorm statistics and injected dropout masks
-  included).  INTERIM: its backward re-evaluates the encoder with differentiable torch operations on the device
-  (as-written algorithm, tae.py:451-504, same masks and batch statistics) and lets autograd produce the gradients.
-  It materialises the [N,T,D] activations the forward kernel avoids, which is fine at the U-TAE / W-TAE placement
-  (N = B*256 rows) and is the item to replace by backward kernels next.
+  included).  The backward has three stages:
+    M  the rows after the attention (MLP Linear, BatchNorm, ReLU, dropout mask, output GroupNorm on [N, 256] /
+       [N, c_out] rows, N = B*H*W) are differentiated with torch autograd -- library GEMMs on a few MB;
+    A  ``c2s_ltae_backward`` (CUDA, ``csrc/c2s_ltae_bwd.cu``) does everything that touches the [N, T, C] features:
+       it recomputes the attention, back-propagates through the value sums, the softmax, the scores and the input
+       GroupNorm, writes grad_x and reduces the gradients of the folded score weights U[C,16] and cpos[B,T,16];
+    F  the chain from (grad_U, grad_cpos, grad_pe) to the state_dict tensors (Q, fc1_k, inconv, in_norm,
+       positional tables) runs through a differentiable torch restatement of the weight folding on [16, 256]-sized
+       tensors.
+  No [N, T, D] activation is ever materialised.  Encoders without ``inconv`` (d_model=None) keep the older
+  torch-recompute backward (``ltae_torch``), which is also what the gradient tests compare against.
 """
 from __future__ import annotations
 
 from typing import Dict, Optional
+
+import os
 
 import torch
 import torch.nn.functional as F
@@ -108,6 +117,112 @@ def ltae_torch(x, positions, pad_mask, P: Dict[str, Optional[torch.Tensor]], cfg
 _GRAD_PARAM_ORDER = tuple(_lib.LTAE_PARAM_FIELDS)
 
 
+def _folded(cfg: Dict, P: Dict[str, Optional[torch.Tensor]], positions, b: int, t: int):
+    """Differentiable restatement of the weight folding of ``csrc/c2s_ltae_prep.cu`` (stage F of the backward):
+    returns ``U[C,h]``, ``cpos[B,T,h]`` and the positional table ``pe[B,T,D] | None``."""
+    h, dk, D = cfg["n_head"], cfg["d_k"], cfg["d_model"]
+    wc = P["inconv_weight"].reshape(D, -1)
+    qk = torch.einsum("hj,hjd->hd", P["query"].reshape(h, dk), P["key_weight"].reshape(h, dk, D)) / (dk ** 0.5)
+    U = (qk @ wc).t() * P["in_norm_weight"][:, None]
+    wb = P["inconv_bias"] + wc @ P["in_norm_bias"]
+    ub = qk @ wb + (P["query"].reshape(h, dk) * P["key_bias"].reshape(h, dk)).sum(1) / (dk ** 0.5)
+    pe = None
+    cpos = ub[None, None, :].expand(b, t, h)
+    if cfg["pe_mode"] != _lib.PE_NONE:
+        pe = _positional(cfg, P, positions, 0)
+        cpos = cpos + pe @ qk.t()
+    return U, cpos, pe
+
+
+def _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params, g_out, g_attn):
+    b, t, c, hh, ww = x.shape
+    n, h, D = b * hh * ww, cfg["n_head"], cfg["d_model"]
+    dh = D // h
+    need = dict(zip(_GRAD_PARAM_ORDER, ctx.needs_input_grad[6:]))
+    raw = dict(zip(_GRAD_PARAM_ORDER, params))
+    attn_only = cfg["attn_only"]
+    grads: Dict[str, torch.Tensor] = {}
+
+    # ---- stage M: rows after the attention ------------------------------------------------------------------
+    g_o = None
+    if not attn_only:
+        if g_out is None:
+            g_o = torch.zeros((n, D), dtype=torch.float32, device=x.device)
+        else:
+            with torch.enable_grad():
+                o = ctx.o_rows.detach().requires_grad_(True)
+                names = ("mlp_weight", "mlp_bias", "bn_weight", "bn_bias", "out_norm_weight", "out_norm_bias")
+                L = {k: raw[k].detach().float().requires_grad_(bool(need[k])) for k in names}
+                y = F.linear(o, L["mlp_weight"], L["mlp_bias"])
+                if cfg["bn_batch_stats"]:
+                    y = F.batch_norm(y, None, None, L["bn_weight"], L["bn_bias"], True, 0.0, cfg["bn_eps"])
+                else:
+                    y = F.batch_norm(y, raw["bn_running_mean"].float(), raw["bn_running_var"].float(), L["bn_weight"],
+                                     L["bn_bias"], False, 0.0, cfg["bn_eps"])
+                y = F.relu(y)
+                if mlp_keep is not None:
+                    mk = mlp_keep.view(b, -1, hh * ww).permute(0, 2, 1).reshape(n, -1)
+                    y = y * mk.to(y.dtype) * cfg["mlp_keep_scale"]
+                y = F.group_norm(y[:, :, None], h, L["out_norm_weight"], L["out_norm_bias"], cfg["gn_eps"])[:, :, 0]
+                out = y.view(b, hh, ww, -1).permute(0, 3, 1, 2)
+                wanted = [o] + [L[k] for k in names if need[k]]
+                got = list(torch.autograd.grad(out, wanted, g_out.to(out.dtype), allow_unused=True))
+            g_o = got.pop(0)
+            for k in names:
+                if need[k]:
+                    grads[k] = got.pop(0)
+
+    # ---- stage A: the CUDA kernel over the features ------------------------------------------------------------
+    pe_learnable = any(need.get(k) for k in ("pe_fc_weight", "pe_fc_bias", "pe_abs_fc_weight", "pe_abs_fc_bias"))
+    res = ops.ltae_backward(
+        x, positions, pad_mask, raw, g_o, g_attn, n_head=h, d_k=cfg["d_k"], d_model=D, has_inconv=True,
+        c_out=cfg["c_out"], pe_mode=cfg["pe_mode"], pe_abs=cfg["pe_abs"], attn_only=attn_only,
+        zero_padded=cfg["zero_padded"], gn_eps=cfg["gn_eps"], attn_keep=attn_keep,
+        attn_drop_p=1.0 - 1.0 / cfg["attn_keep_scale"], need_grad_pe=pe_learnable)
+
+    # ---- stage F: folded quantities -> state_dict tensors -----------------------------------------------------
+    front = ("in_norm_weight", "in_norm_bias", "inconv_weight", "inconv_bias", "query", "key_weight", "key_bias",
+             "pe_fc_weight", "pe_fc_bias", "pe_abs_fc_weight", "pe_abs_fc_bias")
+    if any(need.get(k) for k in front):
+        with torch.enable_grad():
+            L = {}
+            for k in _GRAD_PARAM_ORDER:
+                v = raw[k]
+                if v is None:
+                    L[k] = None
+                elif k in front and need[k]:
+                    L[k] = v.detach().float().requires_grad_(True)
+                else:
+                    L[k] = v.detach().float() if v.is_floating_point() else v
+            U, cpos, pe = _folded(cfg, L, positions, b, t)
+            total = (U * res["grad_u"][:, :h]).sum() + (cpos * res["grad_cpos"][:, :, :h]).sum()
+            if pe is not None and res["grad_pe"] is not None:
+                total = total + (pe * res["grad_pe"]).sum()
+            wanted = [k for k in front if need.get(k) and L[k] is not None]
+            got = torch.autograd.grad(total, [L[k] for k in wanted], allow_unused=True)
+        for k, g in zip(wanted, got):
+            if g is not None:
+                grads[k] = g
+        if not attn_only:
+            go3 = g_o.view(n, h, dh)
+            if need["in_norm_weight"]:
+                grads["in_norm_weight"] = grads.get("in_norm_weight", 0) + res["grad_gamma"]
+            if need["in_norm_bias"]:
+                grads["in_norm_bias"] = grads.get("in_norm_bias", 0) + res["grad_beta"]
+            if need["inconv_weight"]:
+                direct = torch.einsum("nhi,nhc->hic", go3, res["zn_rows"]).reshape(D, c)
+                grads["inconv_weight"] = grads.get("inconv_weight", 0) + direct.reshape(raw["inconv_weight"].shape)
+            if need["inconv_bias"]:
+                direct = torch.einsum("nhi,nh->hi", go3, res["sa_rows"][:, :h]).reshape(D)
+                grads["inconv_bias"] = grads.get("inconv_bias", 0) + direct
+    gx = res["grad_x"] if ctx.needs_input_grad[0] else None
+    gparams = []
+    for k, p in zip(_GRAD_PARAM_ORDER, params):
+        g = grads.get(k)
+        gparams.append(None if g is None or p is None or not need[k] else g.to(p.dtype).reshape(p.shape))
+    return (gx, None, None, None, None, None, *gparams)
+
+
 class LtaeFunction(torch.autograd.Function):
     """apply(x, positions, pad_mask, attn_keep, mlp_keep, cfg, *params in LTAE_PARAM_FIELDS order)
     -> (out | None, attn, bn_batch_mean | None, bn_batch_var | None)"""
@@ -115,13 +230,17 @@ class LtaeFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, positions, pad_mask, attn_keep, mlp_keep, cfg, *params):
         P = dict(zip(_GRAD_PARAM_ORDER, params))
-        out, attn, stats = ops.ltae_forward(
+        ctx.cuda_backward = bool(cfg["has_inconv"]) and os.environ.get("C2S_LTAE_TORCH_BACKWARD") is None
+        res = ops.ltae_forward(
             x, positions, pad_mask, P, n_head=cfg["n_head"], d_k=cfg["d_k"], d_model=cfg["d_model"],
             has_inconv=cfg["has_inconv"], c_out=cfg["c_out"], pe_mode=cfg["pe_mode"], pe_abs=cfg["pe_abs"],
             attn_only=cfg["attn_only"], need_attn=True, zero_padded=cfg["zero_padded"],
             bn_batch_stats=cfg["bn_batch_stats"], gn_eps=cfg["gn_eps"], bn_eps=cfg["bn_eps"],
             attn_keep=attn_keep, attn_drop_p=1.0 - 1.0 / cfg["attn_keep_scale"],
-            mlp_keep=mlp_keep, mlp_drop_p=1.0 - 1.0 / cfg["mlp_keep_scale"])
+            mlp_keep=mlp_keep, mlp_drop_p=1.0 - 1.0 / cfg["mlp_keep_scale"],
+            save_o=ctx.cuda_backward and not cfg["attn_only"])
+        out, attn, stats = res[:3]
+        ctx.o_rows = res[3] if len(res) > 3 else None
         ctx.cfg = cfg
         # the running statistics are updated in place right after a training-mode forward and are not needed by
         # its backward (batch statistics are recomputed), so they are not saved in that case
@@ -143,6 +262,8 @@ class LtaeFunction(torch.autograd.Function):
         positions, pad_mask, attn_keep, mlp_keep = ctx.opt
         params = [rest.pop(0) if present else None for present in ctx.present]
         g_out, g_attn = grads[0], grads[1]
+        if ctx.cuda_backward:
+            return _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params, g_out, g_attn)
         with torch.enable_grad():
             xr = x.detach().requires_grad_(ctx.needs_input_grad[0])
             leaves, P = [], {}

@@ -44,6 +44,7 @@ struct LtaeArgs {
   const float* on_w;  // out_norm.weight
   const float* on_b;
   float* ypre;        // [N, c_out] pre-BatchNorm rows (training mode)
+  float* save_o;      // [N, D] rows entering the MLP (saved for the backward) or nullptr
   const uint8_t* attn_keep;  // [h, B, T, hw] dropout keep mask or nullptr
   const uint8_t* mlp_keep;   // [B, c_out, hw] or nullptr
   float attn_keep_scale, mlp_keep_scale;
@@ -315,6 +316,8 @@ __global__ void __launch_bounds__(kLtaeThreads) ltae_forward_kernel(const LtaeAr
     }
 #pragma unroll
     for (int p = 0; p < kPT; ++p) s_os[d * kPT + p] = acc[p];
+    if (a.save_o != nullptr)
+      for (int p = 0; p < n_pix; ++p) a.save_o[(static_cast<size_t>(b) * a.hw + pix0 + p) * a.D + d] = acc[p];
   }
   __syncthreads();
 
@@ -477,6 +480,7 @@ int launch_general(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void*
   a.bnf = (attn_only || train) ? nullptr : ws + lay.bnf;
   a.on_w = p.out_norm_weight, a.on_b = p.out_norm_bias;
   a.ypre = train ? ws + lay.ypre : nullptr;
+  a.save_o = p.save_o;
   a.attn_keep = p.attn_keep, a.mlp_keep = p.mlp_keep;
   a.attn_keep_scale = d.attn_keep_scale, a.mlp_keep_scale = d.mlp_keep_scale;
   a.B = d.B, a.T = d.T, a.C = d.C, a.hw = hw;
@@ -598,7 +602,7 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
   float* ws = static_cast<float*>(workspace);
   const bool force_general = getenv("C2S_LTAE_FORCE_GENERAL") != nullptr;  // test hook: compare both kernels
   const bool use_mma = !force_general && ltae_mma_eligible(d, x, out);
-  const bool use_fa = use_mma && !ltae_tc_enabled() && ltae_fa_eligible(d);
+  const bool use_fa = use_mma && (!ltae_tc_enabled() || p.save_o != nullptr) && ltae_fa_eligible(d);
   // the reuse flag is honoured only if the previous call on this very workspace went through the same (persistent) path
   if (!(use_fa && fa_prepared(workspace, /*mark=*/use_fa))) d.flags &= ~C2S_LTAE_REUSE_FOLDED;
   status = ltae_prepare(d, p, positions, ws, lay, /*need_transposed=*/!use_mma, stream);
@@ -609,7 +613,7 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
   if (use_fa) {
     status = ltae_fa_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.fa, stream);
     if (status != C2S_OK) return status;
-  } else if (use_mma && ltae_tc_enabled() && ltae_tc_eligible(d)) {
+  } else if (use_mma && ltae_tc_enabled() && ltae_tc_eligible(d) && p.save_o == nullptr) {
     status = ltae_tc_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.tca, stream);
     if (status != C2S_OK) return status;
   } else if (use_mma) {

@@ -72,6 +72,7 @@ struct FaArgs {
   float attn_keep_scale, mlp_keep_scale;
   __nv_bfloat16* o_hi;       // [B*hw][256] rows for the tcgen05 MLP kernel
   __nv_bfloat16* o_lo;
+  float* save_o;             // [B*hw][256] fp32 copy of the same rows for the backward, or nullptr
   int B, T, hw;
   int attn_only, skip_attn_store, zero_padded;
   float gn_eps;
@@ -739,6 +740,7 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
           const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
           os_hi[pp * kOsRow + d] = *reinterpret_cast<const uint16_t*>(&hi);
           os_lo[pp * kOsRow + d] = *reinterpret_cast<const uint16_t*>(&lo);
+          if (a.save_o != nullptr) a.save_o[(static_cast<size_t>(b) * a.hw + pix0 + pp) * kD + d] = v;
         }
       }
       FA_DBG(15);
@@ -956,6 +958,7 @@ int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void
   a.on_w = p.out_norm_weight, a.on_b = p.out_norm_bias;
   a.ypre = train ? ws + lay.ypre : nullptr;
   a.attn_keep = p.attn_keep, a.mlp_keep = p.mlp_keep;
+  a.save_o = p.save_o;
   a.attn_keep_scale = d.attn_keep_scale, a.mlp_keep_scale = d.mlp_keep_scale;
   a.B = d.B, a.T = d.T, a.hw = hw;
   a.attn_only = attn_only;

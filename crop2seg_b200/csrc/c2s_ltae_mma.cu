@@ -58,6 +58,7 @@ struct MmaArgs {
   float attn_keep_scale, mlp_keep_scale;
   __nv_bfloat16* o_hi;       // [B*hw][256] rows for the tcgen05 MLP kernel (nullptr: MLP runs in this kernel)
   __nv_bfloat16* o_lo;
+  float* save_o;             // [B*hw][256] fp32 rows for the backward, or nullptr
   int B, T, hw, c_out;
   int attn_only, skip_attn_store, zero_padded;
   float gn_eps;
@@ -533,6 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) ltae_mma_kernel(const MmaArgs a) 
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       s_os_hi[pp * kOsRow + d] = hi;
       s_os_lo[pp * kOsRow + d] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      if (a.save_o != nullptr) a.save_o[(static_cast<size_t>(b) * a.hw + pix0 + pp) * kD + d] = v;
     }
   }
   __syncthreads();
@@ -707,6 +709,7 @@ int ltae_mma_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const voi
   a.on_w = p.out_norm_weight, a.on_b = p.out_norm_bias;
   a.ypre = train ? ws + lay.ypre : nullptr;
   a.attn_keep = p.attn_keep, a.mlp_keep = p.mlp_keep;
+  a.save_o = p.save_o;
   a.attn_keep_scale = d.attn_keep_scale, a.mlp_keep_scale = d.mlp_keep_scale;
   a.B = d.B, a.T = d.T, a.hw = d.H * d.W, a.c_out = attn_only ? 0 : d.c_out;
   a.attn_only = attn_only;

@@ -153,7 +153,7 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
                  need_attn: bool = True, zero_padded: bool = False, bn_batch_stats: bool = False,
                  gn_eps: float = 1e-5, bn_eps: float = 1e-5, attn_keep: Optional[torch.Tensor] = None,
                  attn_drop_p: float = 0.0, mlp_keep: Optional[torch.Tensor] = None, mlp_drop_p: float = 0.0,
-                 folded_cache: Optional[dict] = None, folded_key=None
+                 folded_cache: Optional[dict] = None, folded_key=None, save_o: bool = False
                  ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[Tuple[torch.Tensor, torch.Tensor]]]:
     """Fused ``LTAE.forward`` / ``LTAE4WTAE.forward`` (tae.py:451-504, 589-635).
 
@@ -161,7 +161,8 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
     ``folded_cache`` (a dict owned by the caller) with ``folded_key`` (anything that changes whenever a parameter
     does) keeps the workspace between calls: while key, shapes and flags repeat, the weight-only preparation kernels
     are skipped (``C2S_LTAE_REUSE_FOLDED``).  Workspaces above 64 MiB are never kept.
-    Returns ``(out[B,c_out,H,W] | None, attn[h,B,T,H,W] | None, (batch_mean, batch_var) | None)``.
+    Returns ``(out[B,c_out,H,W] | None, attn[h,B,T,H,W] | None, (batch_mean, batch_var) | None)``; with ``save_o`` a
+    fourth item, the float32 rows ``o[B*H*W, d_model]`` that enter the MLP (needed by :func:`ltae_backward`'s caller).
     """
     if x.dim() != 5:
         raise RuntimeError(f"crop2seg_b200: x must be [B,T,C,H,W], got {tuple(x.shape)}")
@@ -212,6 +213,10 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
         m = mlp_keep.to(device=dev, dtype=torch.uint8).contiguous()
         keep.append(m)
         cparams.mlp_keep = m.data_ptr()
+    o_rows = None
+    if save_o and not attn_only:
+        o_rows = torch.empty((b * h * w, d_model), dtype=torch.float32, device=dev)
+        cparams.save_o = o_rows.data_ptr()
     pad = _mask_u8(pad_mask, b, t, dev)
     out = None if attn_only else torch.empty((b, c_out, h, w), dtype=x.dtype, device=dev)
     attn = torch.empty((n_head, b, t, h, w), dtype=torch.float32, device=dev) if need_attn else None
@@ -238,4 +243,78 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
                                       _ptr(out), _ptr(attn), _ptr(stats[0]) if stats else None,
                                       _ptr(stats[1]) if stats else None, ws.data_ptr(), ws_bytes, _stream(dev))
     _lib.check(status, "c2s_ltae_forward")
+    if save_o:
+        return out, attn, stats, o_rows
     return out, attn, stats
+
+
+def ltae_backward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: Optional[torch.Tensor],
+                  params: Dict[str, Optional[torch.Tensor]], grad_o: Optional[torch.Tensor],
+                  grad_attn: Optional[torch.Tensor], *, n_head: int, d_k: int, d_model: int, has_inconv: bool,
+                  c_out: int, pe_mode: int, pe_abs: bool = False, attn_only: bool = False, zero_padded: bool = False,
+                  gn_eps: float = 1e-5, attn_keep: Optional[torch.Tensor] = None, attn_drop_p: float = 0.0,
+                  need_grad_pe: bool = False) -> Dict[str, Optional[torch.Tensor]]:
+    """``c2s_ltae_backward``: everything of the L-TAE backward that touches the [B*H*W, T, C] features.
+
+    ``grad_o`` [B*H*W, d_model] is the gradient w.r.t. the rows entering the MLP, ``grad_attn`` [h,B,T,H,W] the one
+    w.r.t. the returned attention.  Returns ``grad_x`` and the gradients of the folded quantities (``grad_u`` [C,16],
+    ``grad_cpos`` [B,T,16], ``grad_gamma`` / ``grad_beta`` [C] direct terms, ``zn_rows`` [B*H*W,h,C], ``sa_rows``
+    [B*H*W,16], ``grad_pe`` [B,T,d_model] | None); see ``include/crop2seg_b200.h``."""
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    dev = x.device
+    b, t, c, h, w = x.shape
+    n = b * h * w
+    flags = (_lib.LTAE_ATTN_ONLY if attn_only else 0) | (_lib.LTAE_ZERO_PADDED if zero_padded else 0)
+    pos, pos_dtype = None, 0
+    if pe_mode != _lib.PE_NONE:
+        pos = positions.to(device=dev)
+        if pos.dtype.is_floating_point:
+            pos, pos_dtype = pos.to(torch.float32), 1
+        else:
+            pos = pos.to(torch.int64)
+        pos = pos.contiguous()
+    desc = _lib.LtaeDesc(B=b, T=t, C=c, H=h, W=w, n_head=n_head, d_k=d_k, d_model=d_model,
+                         c_out=0 if attn_only else c_out, has_inconv=int(has_inconv), pe_mode=pe_mode,
+                         pe_abs=int(pe_abs), pos_dtype=pos_dtype, dtype=_dtype_code(x, "x"), flags=flags,
+                         gn_eps=gn_eps, bn_eps=1e-5, attn_keep_scale=1.0 / (1.0 - attn_drop_p), mlp_keep_scale=1.0)
+    keep = []
+    cparams = _lib.LtaeParams(**{k: _f32(params.get(k), dev, keep) for k in _lib.LTAE_PARAM_FIELDS})
+    if attn_keep is not None:
+        m = attn_keep.to(device=dev, dtype=torch.uint8).contiguous()
+        keep.append(m)
+        cparams.attn_keep = m.data_ptr()
+    f32 = dict(dtype=torch.float32, device=dev)
+    res = {
+        "grad_x": torch.empty_like(x), "grad_u": torch.zeros((c, 16), **f32), "grad_cpos": torch.zeros((b, t, 16), **f32),
+        "grad_gamma": None, "grad_beta": None, "zn_rows": None, "sa_rows": None, "grad_pe": None,
+    }
+    io = _lib.LtaeBwdIo()
+    if not attn_only:
+        if grad_o is None or tuple(grad_o.shape) != (n, d_model):
+            raise RuntimeError(f"crop2seg_b200: grad_o must be [{n},{d_model}]")
+        go = grad_o.to(**f32).contiguous()
+        keep.append(go)
+        io.grad_o = go.data_ptr()
+        res["grad_gamma"], res["grad_beta"] = torch.zeros(c, **f32), torch.zeros(c, **f32)
+        res["zn_rows"], res["sa_rows"] = torch.empty((n, n_head, c), **f32), torch.empty((n, 16), **f32)
+        if need_grad_pe and pe_mode != _lib.PE_NONE:
+            res["grad_pe"] = torch.zeros((b, t, d_model), **f32)
+    if grad_attn is not None:
+        ga = grad_attn.to(**f32).contiguous()
+        if tuple(ga.shape) != (n_head, b, t, h, w):
+            raise RuntimeError(f"crop2seg_b200: grad_attn has shape {tuple(ga.shape)}")
+        keep.append(ga)
+        io.grad_attn = ga.data_ptr()
+    for k in ("grad_x", "grad_u", "grad_cpos", "grad_gamma", "grad_beta", "zn_rows", "sa_rows", "grad_pe"):
+        if res[k] is not None:
+            setattr(io, k, res[k].data_ptr())
+    pad = _mask_u8(pad_mask, b, t, dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.c2s_ltae_backward_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        status = lib.c2s_ltae_backward(ctypes.byref(desc), ctypes.byref(cparams), x.data_ptr(), _ptr(pos), _ptr(pad),
+                                       ctypes.byref(io), ws.data_ptr(), ws_bytes, _stream(dev))
+    _lib.check(status, "c2s_ltae_backward")
+    return res

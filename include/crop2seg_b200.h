@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 2
+#define C2S_ABI_VERSION 3
 
 enum c2s_status {
   C2S_OK = 0,
@@ -141,6 +141,9 @@ typedef struct c2s_ltae_params {
    * uint8 keep masks, NULL = no dropout.  The attention is masked BEFORE it is returned (tae.py:836-837). */
   const uint8_t* attn_keep;      /* [n_head, B, T, H, W]                                        */
   const uint8_t* mlp_keep;       /* [B, c_out, H, W], applied after the ReLU (tae.py:447-448)   */
+  /* training: if not NULL, c2s_ltae_forward also writes the rows o[B*H*W][d_model] that enter the MLP
+   * (tae.py:479-486, the concatenated heads); c2s_ltae_backward's caller needs them for the MLP gradients */
+  float* save_o;
 } c2s_ltae_params;
 
 /* Scratch bytes for c2s_ltae_forward (folded weights + per-sample positional tables). */
@@ -161,6 +164,32 @@ int c2s_ltae_forward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, c
                      const void* positions, const uint8_t* pad_mask, void* out, float* attn,
                      float* bn_batch_mean, float* bn_batch_var, void* workspace,
                      size_t workspace_bytes, void* stream);
+
+/* Backward of LTAE.forward / LTAE4WTAE.forward through everything that touches the [B*H*W, T, C] features
+ * (autograd of tae.py:451-504 in the reference).  The rows after the attention (MLP, BatchNorm, ReLU, output
+ * GroupNorm on [B*H*W, d_model] / [B*H*W, c_out]) are differentiated by the caller, who passes grad_o; the kernel
+ * returns grad_x and the gradients of the FOLDED quantities of c2s_ltae_prep.cuh, from which the caller derives the
+ * state_dict gradients on [16, C] / [B, T, 16] sized tensors:
+ *     U[c][h]      = gamma_c sum_d qk[h][d] Wc[d][c]           (score weights; qk = q_h^T Wk_h / sqrt(d_k))
+ *     cpos[b][t][h] = qk[h] . (bc + Wc beta + PE[b][t]) + q_h . bk_h / sqrt(d_k)
+ * Buffers marked acc are accumulated with float atomics and must be zeroed by the caller. */
+typedef struct c2s_ltae_bwd_io {
+  const float* grad_o;    /* in  [B*H*W][d_model] d loss / d o (NULL with C2S_LTAE_ATTN_ONLY)              */
+  const float* grad_attn; /* in  [n_head][B][T][H][W] d loss / d attn (as returned, after dropout) or NULL */
+  void* grad_x;           /* out [B][T][C][H][W] in desc->dtype                                            */
+  float* grad_u;          /* acc [C][16]                                                                   */
+  float* grad_cpos;       /* acc [B][T][16]                                                                */
+  float* grad_gamma;      /* acc [C]  direct term of in_norm.weight (zn = gamma zr + beta sa)              */
+  float* grad_beta;       /* acc [C]  direct term of in_norm.bias                                          */
+  float* zn_rows;         /* out [B*H*W][n_head][C]: grad_Wc[d][c] (direct) = sum_n grad_o[n][d] zn[n][h(d)][c] */
+  float* sa_rows;         /* out [B*H*W][16]:        grad_bc[d]   (direct) = sum_n grad_o[n][d] sa[n][h(d)]   */
+  float* grad_pe;         /* acc [B][T][d_model] direct term of the positional table, or NULL              */
+} c2s_ltae_bwd_io;
+
+size_t c2s_ltae_backward_workspace_bytes(const c2s_ltae_desc* desc);
+int c2s_ltae_backward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const void* x, const void* positions,
+                      const uint8_t* pad_mask, const c2s_ltae_bwd_io* io, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * library services

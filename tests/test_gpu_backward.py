@@ -3,8 +3,11 @@
 * TemporalAggregator: forward and backward are CUDA kernels; gradients are compared with autograd through the
   torch-CPU oracle (oracle/torch_port.py) on the same inputs.
 * L-TAE: the training-mode forward kernel (BatchNorm batch statistics + injected dropout masks) is compared with the
-  numpy oracle; its (interim, torch-recompute) backward is compared with autograd through the torch-CPU oracle.
+  numpy oracle; its backward (``c2s_ltae_backward`` for everything that touches the features + autograd on the small
+  rows / folded weights) is compared with autograd through the torch-CPU oracle, and, at the shipped shapes in
+  training mode, with the torch restatement on the device (``C2S_LTAE_TORCH_BACKWARD``).
 """
+import os
 import numpy as np
 import pytest
 import torch
@@ -131,6 +134,7 @@ def test_ltae_backward_matches_autograd_of_the_oracle(variant):
     out, attn = m(xd, batch_positions=to_dev(pos), pad_mask=to_dev(pad))
     assert "ltae_forward" in _lib.last_kernel()
     ((out * to_dev(wo)).sum() + (attn * to_dev(wa)).sum()).backward()
+    assert _lib.last_kernel() == "ltae_backward<general>"  # the feature-sized part of the backward is the CUDA kernel
     assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-3
     gmax = max(float(P[name].grad.abs().max()) for name, _ in m.named_parameters())
     for name, p in m.named_parameters():
@@ -172,3 +176,54 @@ def test_utae_bottleneck_trains_end_to_end():
     assert x4d.grad is not None and x3d.grad is not None and x1d.grad is not None
     assert int(m.mlp[2].num_batches_tracked) == 3
     assert losses[-1] < losses[0]
+
+
+def _grads(m, kind, x, pos, pad, wo, wa, dtype, torch_backward, seed):
+    if torch_backward:
+        os.environ["C2S_LTAE_TORCH_BACKWARD"] = "1"
+    else:
+        os.environ.pop("C2S_LTAE_TORCH_BACKWARD", None)
+    try:
+        m.zero_grad()
+        xd = to_dev(x, dtype=dtype).requires_grad_(True)
+        torch.manual_seed(seed)  # same dropout masks on both paths
+        res = m(xd, batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+        out, attn = res if kind == "ltae" else (None, res)
+        loss = (attn * to_dev(wa)).sum()
+        if out is not None:
+            loss = loss + (out.float() * to_dev(wo)).sum()
+        loss.backward()
+        kernel = _lib.last_kernel()
+        return xd.grad.float().cpu().numpy(), {n: p.grad.cpu().numpy().copy() for n, p in m.named_parameters()}, kernel
+    finally:
+        os.environ.pop("C2S_LTAE_TORCH_BACKWARD", None)
+
+
+@pytest.mark.parametrize("case", ["utae_train_bf16", "timeunet_train_f32", "wtae_train_bf16", "utae_eval_bf16"])
+def test_ltae_cuda_backward_matches_the_torch_restatement(case):
+    """Shipped shapes (16 heads, d_model 256), training mode with both dropout masks and batch statistics: the CUDA
+    backward against autograd through the differentiable torch restatement on the same device."""
+    kind = "ltae4wtae" if case.startswith("wtae") else "ltae"
+    C = 64 if case.startswith("timeunet") else 128
+    kw = dict(in_channels=C, n_head=16, d_k=4, d_model=256)
+    if kind == "ltae":
+        kw["mlp"] = [256, C]
+    m, rng = _ltae(kw, 400 + len(case), kind)
+    m.train("train" in case)
+    m.assume_zero_padded = True
+    dtype = torch.bfloat16 if case.endswith("bf16") else torch.float32
+    b, t, h, w = 3, 13, 4, 4
+    x, pos, pad = synth_inputs(rng, b, t, C, h, w, [13, 6, 9])
+    x = x + 0.3 * rng.standard_normal(x.shape).astype(np.float32) * (~pad)[:, :, None, None, None]
+    if dtype == torch.bfloat16:
+        x = bf16_round(x)
+    wo, wa = _loss_weights(rng, (b, C, h, w), (16, b, t, h, w))
+    gx_t, gp_t, _ = _grads(m, kind, x, pos, pad, wo, wa, dtype, True, 5)
+    gx_c, gp_c, kernel = _grads(m, kind, x, pos, pad, wo, wa, dtype, False, 5)
+    assert kernel == "ltae_backward<general>"
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-3
+    assert rel_err(gx_c, gx_t) < tol
+    gmax = max(float(np.abs(v).max()) for v in gp_t.values())
+    for name, ref in gp_t.items():
+        diff = float(np.abs(gp_c[name] - ref).max())
+        assert diff <= 2e-3 * max(float(np.abs(ref).max()), 1e-3 * gmax), (name, diff, float(np.abs(ref).max()))
