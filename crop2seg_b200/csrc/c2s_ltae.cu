@@ -412,13 +412,20 @@ __global__ void bn_partial_kernel(const float* __restrict__ ypre, float* __restr
 
 __global__ void bn_finish_kernel(const float* __restrict__ ypre, const float* __restrict__ part, size_t n_rows,
                                  int c_out, int parts, float* __restrict__ mean, float* __restrict__ var) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel; lanes stride over the partial sums, fixed-order (deterministic) tree reduction in double
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= c_out) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int p = 0; p < parts; ++p) {
+  for (int p = lane; p < parts; p += 32) {
     s1 += part[(0 * c_out + j) * parts + p];
     s2 += part[(1 * c_out + j) * parts + p];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane != 0) return;
   const double n = static_cast<double>(n_rows);
   const double m = s1 / n;
   double v = s2 / n - m * m;
@@ -631,7 +638,7 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
     dim3 grid(parts, ceil_div(d.c_out, 128));
     bn_partial_kernel<<<grid, 128, 0, stream>>>(ypre, part, n_rows, d.c_out, parts);
     C2S_LAUNCH_CHECK("ltae_bn_partial");
-    bn_finish_kernel<<<ceil_div(d.c_out, 128), 128, 0, stream>>>(ypre, part, n_rows, d.c_out, parts, bn_batch_mean,
+    bn_finish_kernel<<<ceil_div(d.c_out, 8), 256, 0, stream>>>(ypre, part, n_rows, d.c_out, parts, bn_batch_mean,
                                                                  bn_batch_var);
     C2S_LAUNCH_CHECK("ltae_bn_finish");
     const size_t n_items = n_rows * d.n_head;

@@ -27,7 +27,7 @@ namespace c2s {
 namespace {
 
 constexpr int kPT = 8;
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 512;
 constexpr int kHP = kMaxHeads + 4;
 constexpr float kMaskFill = -1e6f;
 
@@ -195,9 +195,13 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
         const float4 c = __ldg(cp + k4);
         acc[4 * k4] = c.x, acc[4 * k4 + 1] = c.y, acc[4 * k4 + 2] = c.z, acc[4 * k4 + 3] = c.w;
       }
+      const bool rd = (s_flag[t] & 2) != 0;  // hoisted: the loads of the unrolled loop go out back to back
+      const T* xt = xb + static_cast<size_t>(t) * frame_stride + p;
+#pragma unroll 8
       for (int c = 0; c < a.C; ++c) {
         const int g = c / a.cpg;
-        const float xn = fmaf(xval(t, c, p), s_rstd[g * kPT + p], -s_mu[g * kPT + p]);
+        const float xv = rd ? Elem<T>::load(xt + static_cast<size_t>(c) * a.hw) : 0.f;
+        const float xn = fmaf(xv, s_rstd[g * kPT + p], -s_mu[g * kPT + p]);
         const float4* up = reinterpret_cast<const float4*>(s_u + c * kMaxHeads);
 #pragma unroll
         for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
@@ -289,9 +293,13 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
             }
           }
         }
+        const bool rd = (s_flag[t] & 2) != 0;
+        const T* xt = xb + static_cast<size_t>(t) * frame_stride + p;
+#pragma unroll 8
         for (int c = 0; c < a.C; ++c) {
           const int g = c / a.cpg;
-          const float xn = fmaf(xval(t, c, p), s_rstd[g * kPT + p], -s_mu[g * kPT + p]) * __ldg(a.gamma + c);
+          const float xv = rd ? Elem<T>::load(xt + static_cast<size_t>(c) * a.hw) : 0.f;
+          const float xn = fmaf(xv, s_rstd[g * kPT + p], -s_mu[g * kPT + p]) * __ldg(a.gamma + c);
           const float4* gp = reinterpret_cast<const float4*>(s_gzn + (c * kPT + p) * kHP);
 #pragma unroll
           for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
@@ -359,8 +367,11 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
     for (int k = 0; k < kMaxHeads; ++k) au[k] = 0.f, az[k] = 0.f;
     if (p < n_pix) {
       const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
+      const T* xc = xb + static_cast<size_t>(c) * a.hw + p;
+#pragma unroll 4
       for (int t = 0; t < a.T; ++t) {
-        const float xn = fmaf(xval(t, c, p), r, -m);
+        const float xv = (s_flag[t] & 2) ? Elem<T>::load(xc + static_cast<size_t>(t) * frame_stride) : 0.f;
+        const float xn = fmaf(xv, r, -m);
         const float4* gp = reinterpret_cast<const float4*>(s_ga + (t * kPT + p) * kHP);
         const float4* ap = reinterpret_cast<const float4*>(s_sc + (t * kPT + p) * kHP);
 #pragma unroll
@@ -445,6 +456,7 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
       float s1 = 0.f, s2 = 0.f;
       if (p < n_pix) {
         const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
+#pragma unroll 4
         for (int e = sub; e < n_el; e += kSub) {
           const int t = e / a.cpg, c = g * a.cpg + (e - t * a.cpg);
           const float gv = gxh(t, c, p);
@@ -464,6 +476,7 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
   {
     T* gx = static_cast<T*>(a.g_x) + static_cast<size_t>(b) * a.T * frame_stride + pix0;
     const int n_el = a.T * a.C * kPT;
+#pragma unroll 4
     for (int item = tid; item < n_el; item += kBwdThreads) {
       const int p = item % kPT, tc = item / kPT;
       const int t = tc / a.C, c = tc - t * a.C;
