@@ -611,7 +611,8 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
   const bool use_mma = !force_general && ltae_mma_eligible(d, x, out);
   const bool use_fa = use_mma && (!ltae_tc_enabled() || p.save_o != nullptr) && ltae_fa_eligible(d);
   // the reuse flag is honoured only if the previous call on this very workspace went through the same (persistent) path
-  if (!(use_fa && fa_prepared(workspace, /*mark=*/use_fa))) d.flags &= ~C2S_LTAE_REUSE_FOLDED;
+  const bool was_prepared = fa_prepared(workspace, /*mark=*/use_fa);  // every call updates the set: another path unmarks
+  if (!(use_fa && was_prepared)) d.flags &= ~C2S_LTAE_REUSE_FOLDED;
   status = ltae_prepare(d, p, positions, ws, lay, /*need_transposed=*/!use_mma, stream);
   if (status != C2S_OK) return status;
 

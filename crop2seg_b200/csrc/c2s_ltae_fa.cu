@@ -36,9 +36,7 @@
 namespace c2s {
 namespace {
 
-constexpr int kFaThreads = 512;
-constexpr int kFaWarps = kFaThreads / 32;
-constexpr int kPix = 8;            // pixels per tile; two warps share a pixel
+constexpr int kPix = 8;            // pixels per tile; WPP warps (2 for C = 128, 1 for C = 64) share a pixel
 constexpr int kTP = 64;            // frames in the slab
 constexpr int kH = 16;             // heads
 constexpr int kD = 256;            // d_model
@@ -81,16 +79,18 @@ struct FaArgs {
   unsigned long long* dbg;
 };
 
-template <int C>
+template <int C, int WPP>
 struct FaSmem {
-  static constexpr int NBUF = (C == 64) ? 2 : 1;
+  static constexpr int NW = kPix * WPP;                            // warps per CTA
+  static constexpr int NBUF = (C == 64 && WPP == 2) ? 2 : 1;      // WPP = 1: two CTAs per SM overlap instead
   static constexpr int kFB = C * 16;                              // one frame: [C][8 px] bf16
   static constexpr int kSlab = kTP * kFB;
   static constexpr int oSlab = 0;
   static constexpr int oWc = NBUF * kSlab;                        // resident in-projection weights (fp16 fragments):
   static constexpr int kWcHalf = kD * C * 2;                      // hi and, with C = 64, lo
-  static constexpr bool kLoResident = (C == 64);
-  static constexpr int kWc = kLoResident ? 2 * kWcHalf : kWcHalf;
+  static constexpr bool kHiResident = (WPP == 2);                 // WPP = 1: both halves are streamed from L2
+  static constexpr bool kLoResident = (WPP == 2 && C == 64);
+  static constexpr int kWc = kLoResident ? 2 * kWcHalf : (kHiResident ? kWcHalf : 0);
   static constexpr int oUf = oWc + kWc;                           // float4 [C/16][2][32] score weights
   static constexpr int oCpos = oUf + C * 64;                      // float [16][kAP]
   static constexpr int oPeHi = oCpos + kH * kAP * 4;              // bf16 [16][kPeRow]
@@ -103,7 +103,7 @@ struct FaSmem {
   static constexpr int oSaP = oRed + kPix * 2 * 2 * kH * 4;       // float [8 px][2 warps][16]
   static constexpr int oPart = oSaP + kPix * 2 * kH * 4;          // float2 [16 warps][4][subgroups][8 px] statistics partials
   static constexpr int kSub = (C == 64) ? 2 : 1;                  // GroupNorm groups per 8-channel block
-  static constexpr int oRaw = oPart + kFaWarps * 4 * kSub * kPix * 8;  // float cpos[64][16], pe[64][16] of the next sample
+  static constexpr int oRaw = oPart + NW * 4 * kSub * kPix * 8;  // float cpos[64][16], pe[64][16] of the next sample
   static constexpr int oMask = oRaw + 2 * kTP * 16 * 4;           // frame masks of the tile that takes over the slab, [k & 1][2]
   static constexpr int oBar = oMask + 32;
   static constexpr int kTotal = oBar + 64;
@@ -111,8 +111,8 @@ struct FaSmem {
   // ---- epilogue scratch, aliased onto the slab once every warp is done with x ----
   static constexpr int ZH = C / 16;                               // channel n-tiles finalised per warp
   static constexpr int NR = ZH * 4 + 4;                           // exchanged registers per thread (z + positional)
-  static constexpr int PB = 2 * NR * 128 + 16;                    // per-pixel block: exchange, later zn hi/lo
   static constexpr int kZn = kH * (C + 8) * 2;                    // zn_hi [16 h][C + 8] fp16
+  static constexpr int PB = (WPP == 2 ? 2 * NR * 128 : 2 * kZn) + 16;  // per-pixel block: exchange (WPP = 2), then zn hi/lo
   static_assert(2 * kZn <= PB && (PB / 4) % 32 == 4, "zn tiles must fit; pixel blocks 4 banks apart");
   static constexpr int oStage = kPix * PB;                        // attention staging float [8][kAsP]
   static constexpr bool kStageApart = oStage + kPix * kAsP * 4 + 8192 + 2 * kPix * kOsRow * 2 <= kSlab;
@@ -215,15 +215,16 @@ __device__ __forceinline__ float ex2(float v) {
 #define FA_DBG(k)
 #endif
 
-template <int C>
-__global__ void __launch_bounds__(kFaThreads, 1)
+template <int C, int WPP>
+__global__ void __launch_bounds__(256 * WPP, WPP == 1 ? 2 : 1)
 ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant__ CUtensorMap map4,
                const __grid_constant__ CUtensorMap map1, const FaArgs a) {
-  using S = FaSmem<C>;
+  using S = FaSmem<C, WPP>;
+  constexpr int NW = S::NW, NT = 32 * NW;  // warps, threads
   constexpr int CPG = C / kH;            // channels per GroupNorm group (8 or 4)
   constexpr int KS = C / 16;             // k-steps over channels
   constexpr int NQ = C / 32;             // 4-block quads per frame (one ldmatrix.x4 each)
-  constexpr int TSTEP = kFaWarps / NQ;   // frames between two items of a warp in the transposition pass
+  constexpr int TSTEP = NW / NQ;   // frames between two items of a warp in the transposition pass
   constexpr int NBUF = S::NBUF;
   constexpr int FB = S::kFB;
   constexpr int ZH = S::ZH;
@@ -245,7 +246,9 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
   const uint32_t bars = s32(smem + S::oBar);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int p = warp >> 1, half = warp & 1;   // pixel of this warp, which half of the frames it owns
+  const int p = warp / WPP, half = warp % WPP;  // pixel of this warp, which part of the frames it owns (WPP = 2)
+  constexpr int FPW = kTP / WPP;               // frames per warp
+  constexpr int FN = FPW / 8;                  // score n-tiles per warp
   const int j = lane & 3, g = lane >> 2;       // fragment coordinates: row g (and g + 8), column pair 2j
   const int mat = lane >> 3, mr = lane & 7;    // ldmatrix: this lane supplies row mr of matrix mat
   const uint32_t pair_bar = 1 + p;
@@ -257,14 +260,14 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
   }
   {
     uint4* wc = reinterpret_cast<uint4*>(smem + S::oWc);
-    if (!a.attn_only)
-      for (int i = tid; i < S::kWc / 16; i += kFaThreads) wc[i] = __ldg(a.wc16 + i);
-    for (int i = tid; i < KS * 64; i += kFaThreads) {  // source order [ks][lane][2] -> [ks][2][lane]
+    if (!a.attn_only && S::kWc > 0)
+      for (int i = tid; i < S::kWc / 16; i += NT) wc[i] = __ldg(a.wc16 + i);
+    for (int i = tid; i < KS * 64; i += NT) {  // source order [ks][lane][2] -> [ks][2][lane]
       const int ks = i >> 6, e = i & 63;
       s_uf[ks * 64 + (e & 1) * 32 + (e >> 1)] = __ldg(reinterpret_cast<const float4*>(a.ufrag) + i);
     }
-    for (int i = tid; i < C; i += kFaThreads) s_gam[i] = __ldg(a.gamma + i), s_gam[C + i] = __ldg(a.beta + i);
-    for (int i = tid; i < 2 * kTP * 16; i += kFaThreads) s_raw[i] = 0.f;  // rows t >= T and a missing table stay zero
+    for (int i = tid; i < C; i += NT) s_gam[i] = __ldg(a.gamma + i), s_gam[C + i] = __ldg(a.beta + i);
+    for (int i = tid; i < 2 * kTP * 16; i += NT) s_raw[i] = 0.f;  // rows t >= T and a missing table stay zero
   }
   const float inv_sc = a.attn_only ? 1.f : __ldg(a.wscale + 1);
   __syncthreads();
@@ -273,8 +276,8 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
   // elements from the copy to the conversion at the top of the tile that needs them: no barrier in between)
   auto fetch_consts = [&](int bn) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int i = tid + q * kFaThreads, t = i >> 4, h = i & 15;
+    for (int q = 0; q < kTP * 16 / NT; ++q) {
+      const int i = tid + q * NT, t = i >> 4, h = i & 15;
       if (t < a.T) {
         cp_async4(s_raw + i, a.cpos + (static_cast<size_t>(bn) * a.T + t) * kMaxHeads + h);
         if (!a.attn_only && a.pe != nullptr) cp_async4(s_raw + kTP * 16 + i, a.pe + (static_cast<size_t>(bn) * a.T + t) * kD + h);
@@ -355,8 +358,8 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
       cp_async_wait_all();
       if (new_b) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int i = tid + q * kFaThreads, t = i >> 4, h = i & 15;
+        for (int q = 0; q < kTP * 16 / NT; ++q) {
+          const int i = tid + q * NT, t = i >> 4, h = i & 15;
           s_cpos[h * kAP + t] = s_raw[i] * kLog2e;
           if (!a.attn_only) {
             const float pe = s_raw[kTP * 16 + i];
@@ -447,17 +450,17 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
 
     FA_DBG(5);
     // ---- scores S^T[h, t] for the frames 32 half .. 32 half + 31 of pixel p ---------------- tae.py:827-831
-    float sacc[4][4];
+    float sacc[FN][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int t = (4 * half + nt) * 8 + 2 * j;
+    for (int nt = 0; nt < FN; ++nt) {
+      const int t = (FN * half + nt) * 8 + 2 * j;
       const float2 c0 = *reinterpret_cast<const float2*>(s_cpos + g * kAP + t);
       const float2 c1 = *reinterpret_cast<const float2*>(s_cpos + (g + 8) * kAP + t);
       sacc[nt][0] = c0.x, sacc[nt][1] = c0.y, sacc[nt][2] = c1.x, sacc[nt][3] = c1.y;
     }
-    const uint32_t live_h = static_cast<uint32_t>(live >> (32 * half));  // this warp's 32 frames
+    const unsigned long long live_w = (WPP == 1) ? live : ((live >> (FPW * half)) & 0xffffffffull);  // this warp's frames
     {
-      const uint32_t xrow = slab + ((p ^ mr) << 4) + (mat & 1) * 128 + (32 * half + (mat >> 1) * 8 + mr) * FB;
+      const uint32_t xrow = slab + ((p ^ mr) << 4) + (mat & 1) * 128 + (FPW * half + (mat >> 1) * 8 + mr) * FB;
 #pragma unroll 2
       for (int ks = 0; ks < KS; ++ks) {
         const float4 u0 = s_uf[ks * 64 + lane], u1 = s_uf[ks * 64 + 32 + lane];
@@ -469,8 +472,8 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
         split_bf16(u1.x * r1, u1.y * r1, ahi[2], alo[2]);  // (row g,     k 2j+8, 2j+9)
         split_bf16(u1.z * r1, u1.w * r1, ahi[3], alo[3]);  // (row g + 8, k 2j+8, 2j+9)
 #pragma unroll
-        for (int ntp = 0; ntp < 2; ++ntp) {
-          if (((live_h >> (16 * ntp)) & 0xffffu) == 0) continue;  // both frame blocks hold zeros
+        for (int ntp = 0; ntp < FN / 2; ++ntp) {
+          if (((live_w >> (16 * ntp)) & 0xffffull) == 0) continue;  // both frame blocks hold zeros
           uint32_t bfr[4];  // (block 2 ntp, channels 16 ks..+7), (.., +8..15), (block 2 ntp + 1, ..), (..)
           ldsm_x4(bfr, xrow + ntp * 16 * FB + ks * 256);
           mma_bf16(sacc[2 * ntp], ahi, bfr[0], bfr[1]);
@@ -483,19 +486,20 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
 
     FA_DBG(6);
     // ---- softmax over t for rows h = g and g + 8 (base 2: the scores carry log2 e) --------- tae.py:831-836
+    float sa0 = 0.f, sa1 = 0.f;  // sum_t a of this warp's frames, rows g and g + 8
     {
       float* red = s_red + (p * 2 + half) * 2 * kH;
       const float* red_other = s_red + (p * 2 + (half ^ 1)) * 2 * kH;
-      const uint32_t pad_h = static_cast<uint32_t>(padm >> (32 * half));
+      const unsigned long long pad_w = (WPP == 1) ? padm : ((padm >> (FPW * half)) & 0xffffffffull);
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < FN; ++nt) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int tl = nt * 8 + 2 * j + e;
           float v0 = sacc[nt][e], v1 = sacc[nt][2 + e];
-          if ((pad_h >> tl) & 1u) v0 = -1e6f, v1 = -1e6f;
-          if (32 * half + tl >= a.T) v0 = -INFINITY, v1 = -INFINITY;
+          if ((pad_w >> tl) & 1ull) v0 = -1e6f, v1 = -1e6f;
+          if (FPW * half + tl >= a.T) v0 = -INFINITY, v1 = -INFINITY;
           sacc[nt][e] = v0, sacc[nt][2 + e] = v1;
           mx0 = fmaxf(mx0, v0), mx1 = fmaxf(mx1, v1);
         }
@@ -504,13 +508,15 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      if (j == 0) red[g] = mx0, red[g + 8] = mx1;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      mx0 = fmaxf(mx0, red_other[g]);  // T >= 1: at least one side is finite
-      mx1 = fmaxf(mx1, red_other[g + 8]);
+      if constexpr (WPP == 2) {
+        if (j == 0) red[g] = mx0, red[g + 8] = mx1;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mx0 = fmaxf(mx0, red_other[g]);  // T >= 1: at least one side is finite
+        mx1 = fmaxf(mx1, red_other[g + 8]);
+      }
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < FN; ++nt) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           sacc[nt][e] = ex2(sacc[nt][e] - mx0);
@@ -522,18 +528,23 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
       d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
       d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
       d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-      if (j == 0) red[kH + g] = d0, red[kH + g + 8] = d1;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      // the sum is formed in the same order by both warps so that they normalise identically
-      const float lo0 = half ? red_other[kH + g] : d0, hi0 = half ? d0 : red_other[kH + g];
-      const float lo1 = half ? red_other[kH + g + 8] : d1, hi1 = half ? d1 : red_other[kH + g + 8];
-      const float inv0 = 1.f / (lo0 + hi0), inv1 = 1.f / (lo1 + hi1);
-      float sa0 = 0.f, sa1 = 0.f;
+      float inv0, inv1;
+      if constexpr (WPP == 2) {
+        if (j == 0) red[kH + g] = d0, red[kH + g + 8] = d1;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        // the sum is formed in the same order by both warps so that they normalise identically
+        const float lo0 = half ? red_other[kH + g] : d0, hi0 = half ? d0 : red_other[kH + g];
+        const float lo1 = half ? red_other[kH + g + 8] : d1, hi1 = half ? d1 : red_other[kH + g + 8];
+        inv0 = 1.f / (lo0 + hi0), inv1 = 1.f / (lo1 + hi1);
+      } else {
+        inv0 = 1.f / d0, inv1 = 1.f / d1;
+      }
+      sa0 = 0.f, sa1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < FN; ++nt) {
         sacc[nt][0] *= inv0, sacc[nt][1] *= inv0, sacc[nt][2] *= inv1, sacc[nt][3] *= inv1;
         if (a.attn_keep != nullptr) {  // training: dropout acts on the attention that is returned (tae.py:837)
-          const int t = (4 * half + nt) * 8 + 2 * j;
+          const int t = (FN * half + nt) * 8 + 2 * j;
           const uint8_t* k0 = a.attn_keep + ((static_cast<size_t>(g) * a.B + b) * a.T + t) * a.hw + pix0 + p;
           const uint8_t* k1 = a.attn_keep + ((static_cast<size_t>(g + 8) * a.B + b) * a.T + t) * a.hw + pix0 + p;
           const float sc = a.attn_keep_scale;
@@ -549,7 +560,7 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
       sa0 += __shfl_xor_sync(0xffffffffu, sa0, 2);
       sa1 += __shfl_xor_sync(0xffffffffu, sa1, 1);
       sa1 += __shfl_xor_sync(0xffffffffu, sa1, 2);
-      if (j == 0) s_sap[(p * 2 + half) * kH + g] = sa0, s_sap[(p * 2 + half) * kH + g + 8] = sa1;
+      if (WPP == 2 && j == 0) s_sap[(p * 2 + half) * kH + g] = sa0, s_sap[(p * 2 + half) * kH + g + 8] = sa1;
     }
 
     FA_DBG(7);
@@ -566,16 +577,16 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 4; ++i) pacc[nt][i] = 0.f;
       // lane's row of the transposed loads: frame (mat >> 1) * 8 + mr of the k-step, channel block mat & 1 of the pair
-      const uint32_t xrow = slab + ((p ^ mr) << 4) + (mat & 1) * 128 + (32 * half + (mat >> 1) * 8 + mr) * FB;
-      const uint32_t pe_row = s32((mat >> 1) ? s_pe_lo : s_pe_hi) + static_cast<uint32_t>(mr * kPeRow + 32 * half + (mat & 1) * 8) * 2u;
+      const uint32_t xrow = slab + ((p ^ mr) << 4) + (mat & 1) * 128 + (FPW * half + (mat >> 1) * 8 + mr) * FB;
+      const uint32_t pe_row = s32((mat >> 1) ? s_pe_lo : s_pe_hi) + static_cast<uint32_t>(mr * kPeRow + FPW * half + (mat & 1) * 8) * 2u;
 #pragma unroll
-      for (int ksl = 0; ksl < 2; ++ksl) {
+      for (int ksl = 0; ksl < FN / 2; ++ksl) {
         uint32_t ahi[4], alo[4];
         split_bf16(sacc[2 * ksl][0], sacc[2 * ksl][1], ahi[0], alo[0]);
         split_bf16(sacc[2 * ksl][2], sacc[2 * ksl][3], ahi[1], alo[1]);
         split_bf16(sacc[2 * ksl + 1][0], sacc[2 * ksl + 1][1], ahi[2], alo[2]);
         split_bf16(sacc[2 * ksl + 1][2], sacc[2 * ksl + 1][3], ahi[3], alo[3]);
-        if (((live_h >> (16 * ksl)) & 0xffffu) != 0) {
+        if (((live_w >> (16 * ksl)) & 0xffffull) != 0) {
 #pragma unroll
           for (int cbp = 0; cbp < C / 16; ++cbp) {
             uint32_t v[4];  // (frames 0-7, block 2 cbp), (0-7, 2 cbp + 1), (8-15, 2 cbp), (8-15, 2 cbp + 1)
@@ -606,24 +617,26 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
     if (store_attn) {
       float* as = s_stage + p * kAsP;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int t = (4 * half + nt) * 8 + 2 * j;
+      for (int nt = 0; nt < FN; ++nt) {
+        const int t = (FN * half + nt) * 8 + 2 * j;
         *reinterpret_cast<float2*>(as + g * kAP + t) = make_float2(sacc[nt][0], sacc[nt][1]);
         *reinterpret_cast<float2*>(as + (g + 8) * kAP + t) = make_float2(sacc[nt][2], sacc[nt][3]);
       }
     }
     auto store_attention = [&]() {  // attn[h, b, t, pix0 .. pix0 + 7]: 32-byte segments            tae.py:490-493
       const int pp = lane & 7, tq = lane >> 3;
-      const int h = warp;
-      float* dst = a.attn + ((static_cast<size_t>(h) * a.B + b) * a.T + tq) * a.hw + pix0 + pp;
-      const float* src = s_stage + pp * kAsP + h * kAP + tq;
-      const size_t step = static_cast<size_t>(4) * a.hw;
-      float v[kTP / 4];
 #pragma unroll
-      for (int u = 0; u < kTP / 4; ++u) v[u] = src[4 * u];  // t = tq + 4 u <= 63: inside the staging rows
+      for (int h = warp; h < kH; h += NW) {
+        float* dst = a.attn + ((static_cast<size_t>(h) * a.B + b) * a.T + tq) * a.hw + pix0 + pp;
+        const float* src = s_stage + pp * kAsP + h * kAP + tq;
+        const size_t step = static_cast<size_t>(4) * a.hw;
+        float v[kTP / 4];
 #pragma unroll
-      for (int u = 0; u < kTP / 4; ++u)
-        if (tq + 4 * u < a.T) dst[u * step] = v[u];
+        for (int u = 0; u < kTP / 4; ++u) v[u] = src[4 * u];  // t = tq + 4 u <= 63: inside the staging rows
+#pragma unroll
+        for (int u = 0; u < kTP / 4; ++u)
+          if (tq + 4 * u < a.T) dst[u * step] = v[u];
+      }
     };
     if (store_attn && (!S::kStageApart || a.attn_only)) {  // the staging area shares its space with the exchange
       __syncthreads();
@@ -632,53 +645,26 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
     }
 
     FA_DBG(10);
-    uint4 wlo[S::kLoResident ? 1 : KS];  // lo fragments of head `warp` of the in-projection weights (C = 128)
+    uint4 wlo[(WPP == 2 && !S::kLoResident) ? KS : 1];  // lo fragments of head `warp` of the in-projection weights (C = 128)
     if (!a.attn_only) {
-      // ---- the two partial sums of a pixel meet: each warp finalises half of the channel tiles ----------
-      float* ex = reinterpret_cast<float*>(slab_ptr + p * S::PB);
-      auto meet = [&](auto hf_) {  // generic over the half so that every register index is static
-        constexpr int HF = decltype(hf_)::value;
-        {
-          float* mine = ex + (HF * NR) * 32 + lane;
-#pragma unroll
-          for (int i = 0; i < ZH; ++i)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) mine[(i * 4 + e) * 32] = zacc[(1 - HF) * ZH + i][e];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) mine[(ZH * 4 + e) * 32] = pacc[1 - HF][e];
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        {
-          const float* theirs = ex + ((1 - HF) * NR) * 32 + lane;
-#pragma unroll
-          for (int i = 0; i < ZH; ++i)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) zacc[HF * ZH + i][e] += theirs[(i * 4 + e) * 32];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) pacc[HF][e] += theirs[(ZH * 4 + e) * 32];
-        }
-        const float sa0 = s_sap[(p * 2) * kH + g] + s_sap[(p * 2 + 1) * kH + g];
-        const float sa1 = s_sap[(p * 2) * kH + g + 8] + s_sap[(p * 2 + 1) * kH + g + 8];
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // the exchange is read: zn may overwrite it
-        if constexpr (!S::kLoResident) {  // in flight while zn is finalised
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks) wlo[ks] = __ldg(a.wc16 + S::kWcHalf / 16 + (warp * KS + ks) * 32 + lane);
-        }
-        FA_DBG(11);
-        // GroupNorm affine on the weighted sums -> fp16 hi/lo tiles zn[p][h][c]                          tae.py:461
+      // GroupNorm affine on the weighted sums -> fp16 hi/lo tiles zn[p][h][c] (tae.py:461) for the channel tiles
+      // FIRST .. FIRST + COUNT - 1, the positional sums of the 8-column tiles PFIRST .. PFIRST + PCOUNT - 1
+      auto write_zn = [&](auto first_, auto count_, auto pfirst_, auto pcount_, float sa_lo, float sa_hi) {
+        constexpr int FIRST = decltype(first_)::value, COUNT = decltype(count_)::value;
+        constexpr int PFIRST = decltype(pfirst_)::value, PCOUNT = decltype(pcount_)::value;
         unsigned char* zb = slab_ptr + p * S::PB;
 #pragma unroll
-        for (int i = 0; i < ZH; ++i) {
-          const int c = (HF * ZH + i) * 8 + 2 * j;
+        for (int i = 0; i < COUNT; ++i) {
+          const int c = (FIRST + i) * 8 + 2 * j;
           const int grp = c / CPG;
           const float r = s_rstd[grp * kPix + p], m = s_mu[grp * kPix + p];
           const float gm0 = s_gam[c], gm1 = s_gam[c + 1], bt0 = s_gam[C + c], bt1 = s_gam[C + c + 1];
-          const float(&z)[4] = zacc[HF * ZH + i];
+          const float(&z)[4] = zacc[FIRST + i];
           // sum_t a (x rstd - mean rstd) gamma + beta sum_t a
-          const float z00 = fmaf(gm0, fmaf(z[0], r, -m * sa0), bt0 * sa0);
-          const float z01 = fmaf(gm1, fmaf(z[1], r, -m * sa0), bt1 * sa0);
-          const float z10 = fmaf(gm0, fmaf(z[2], r, -m * sa1), bt0 * sa1);
-          const float z11 = fmaf(gm1, fmaf(z[3], r, -m * sa1), bt1 * sa1);
+          const float z00 = fmaf(gm0, fmaf(z[0], r, -m * sa_lo), bt0 * sa_lo);
+          const float z01 = fmaf(gm1, fmaf(z[1], r, -m * sa_lo), bt1 * sa_lo);
+          const float z10 = fmaf(gm0, fmaf(z[2], r, -m * sa_hi), bt0 * sa_hi);
+          const float z11 = fmaf(gm1, fmaf(z[3], r, -m * sa_hi), bt1 * sa_hi);
           uint32_t hi, lo;
           split_f16(z00, z01, hi, lo);
           *reinterpret_cast<uint32_t*>(zb + (g * (C + 8) + c) * 2) = hi;
@@ -688,15 +674,59 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
           *reinterpret_cast<uint32_t*>(zb + S::kZn + ((g + 8) * (C + 8) + c) * 2) = lo;
         }
         float* s_pa = reinterpret_cast<float*>(slab_ptr + S::oPa);
-        const int i0 = HF * 8 + 2 * j;
-        s_pa[(g * 16 + i0) * kPix + p] = pacc[HF][0];
-        s_pa[(g * 16 + i0 + 1) * kPix + p] = pacc[HF][1];
-        s_pa[((g + 8) * 16 + i0) * kPix + p] = pacc[HF][2];
-        s_pa[((g + 8) * 16 + i0 + 1) * kPix + p] = pacc[HF][3];
-        if (j == 0 && HF == 0) s_sa[g * kPix + p] = sa0, s_sa[(g + 8) * kPix + p] = sa1;
+#pragma unroll
+        for (int q = 0; q < PCOUNT; ++q) {
+          const int i0 = (PFIRST + q) * 8 + 2 * j;
+          s_pa[(g * 16 + i0) * kPix + p] = pacc[PFIRST + q][0];
+          s_pa[(g * 16 + i0 + 1) * kPix + p] = pacc[PFIRST + q][1];
+          s_pa[((g + 8) * 16 + i0) * kPix + p] = pacc[PFIRST + q][2];
+          s_pa[((g + 8) * 16 + i0 + 1) * kPix + p] = pacc[PFIRST + q][3];
+        }
+        if (j == 0 && PFIRST == 0) s_sa[g * kPix + p] = sa_lo, s_sa[(g + 8) * kPix + p] = sa_hi;
       };
-      if (half == 0) meet(std::integral_constant<int, 0>{});
-      else meet(std::integral_constant<int, 1>{});
+      using std::integral_constant;
+      if constexpr (WPP == 1) {  // the warp holds the complete sums
+        FA_DBG(11);
+        write_zn(integral_constant<int, 0>{}, integral_constant<int, C / 8>{}, integral_constant<int, 0>{},
+                 integral_constant<int, 2>{}, sa0, sa1);
+      } else {
+        // ---- the two partial sums of a pixel meet: each warp finalises half of the channel tiles ----------
+        float* ex = reinterpret_cast<float*>(slab_ptr + p * S::PB);
+        auto meet = [&](auto hf_) {  // generic over the half so that every register index is static
+          constexpr int HF = decltype(hf_)::value;
+          {
+            float* mine = ex + (HF * NR) * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < ZH; ++i)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) mine[(i * 4 + e) * 32] = zacc[(1 - HF) * ZH + i][e];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mine[(ZH * 4 + e) * 32] = pacc[1 - HF][e];
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          {
+            const float* theirs = ex + ((1 - HF) * NR) * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < ZH; ++i)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) zacc[HF * ZH + i][e] += theirs[(i * 4 + e) * 32];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pacc[HF][e] += theirs[(ZH * 4 + e) * 32];
+          }
+          const float st0 = s_sap[(p * 2) * kH + g] + s_sap[(p * 2 + 1) * kH + g];
+          const float st1 = s_sap[(p * 2) * kH + g + 8] + s_sap[(p * 2 + 1) * kH + g + 8];
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // the exchange is read: zn may overwrite it
+          if constexpr (!S::kLoResident) {  // in flight while zn is finalised
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) wlo[ks] = __ldg(a.wc16 + S::kWcHalf / 16 + (warp * KS + ks) * 32 + lane);
+          }
+          FA_DBG(11);
+          write_zn(integral_constant<int, HF * ZH>{}, integral_constant<int, ZH>{}, integral_constant<int, HF>{},
+                   integral_constant<int, 1>{}, st0, st1);
+        };
+        if (half == 0) meet(integral_constant<int, 0>{});
+        else meet(integral_constant<int, 1>{});
+      }
     }
     FA_DBG(12);
     __syncthreads();
@@ -708,17 +738,22 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
     if (!a.attn_only) {
       // ---- in-projection of head `warp`: o[16 h + i, px] = Wc[16 h + i, :] . zn[px, h, :] + sa bc + sum_t a PE
       //                                                                              tae.py:463, 479, 839
-      {
-        const int h = warp;
+#pragma unroll
+      for (int h = warp; h < kH; h += NW) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         const unsigned char* zb = slab_ptr + g * S::PB + (h * (C + 8) + 2 * j) * 2;  // B[k = c][n = pixel g]
-        const uint4* wc = reinterpret_cast<const uint4*>(smem + S::oWc) + (h * KS) * 32 + lane;
+        const uint4* wc = (S::kHiResident ? reinterpret_cast<const uint4*>(smem + S::oWc) : a.wc16) + (h * KS) * 32 + lane;
+        uint4 wha[S::kHiResident ? 1 : KS], wla[S::kHiResident ? 1 : KS];
+        if constexpr (!S::kHiResident) {  // streamed from L2: all loads of the head go out before the first product
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) wha[ks] = __ldg(wc + ks * 32), wla[ks] = __ldg(wc + S::kWcHalf / 16 + ks * 32);
+        }
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          const uint4 wa = wc[ks * 32];
-          uint4 wl;
-          if constexpr (S::kLoResident) wl = wc[S::kWcHalf / 16 + ks * 32];
-          else wl = wlo[ks];
+          uint4 wa, wl;
+          if constexpr (!S::kHiResident) wa = wha[ks], wl = wla[ks];
+          else if constexpr (S::kLoResident) wa = wc[ks * 32], wl = wc[S::kWcHalf / 16 + ks * 32];
+          else wa = wc[ks * 32], wl = wlo[ks];
           const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(zb + ks * 32);
           const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(zb + ks * 32 + 16);
           const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(zb + S::kZn + ks * 32);
@@ -751,7 +786,7 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
         const size_t row0 = static_cast<size_t>(b) * a.hw + pix0;
         const uint16_t* os_hi = reinterpret_cast<const uint16_t*>(slab_ptr + S::oOsHi);
         const uint16_t* os_lo = reinterpret_cast<const uint16_t*>(slab_ptr + S::oOsLo);
-        for (int i = tid; i < 2 * kPix * (kD / 8); i += kFaThreads) {  // 16-byte pieces of the 8 rows, hi then lo
+        for (int i = tid; i < 2 * kPix * (kD / 8); i += NT) {  // 16-byte pieces of the 8 rows, hi then lo
           const int plane = i / (kPix * (kD / 8)), r = i - plane * (kPix * (kD / 8));
           const int pp = r / (kD / 8), q = r - pp * (kD / 8);
           const uint16_t* src = (plane ? os_lo : os_hi) + pp * kOsRow + q * 8;
@@ -871,13 +906,14 @@ int fa_sm_count() {
   return n;
 }
 
-template <int C>
+template <int C, int WPP>
 int fa_launch(const CUtensorMap& map16, const CUtensorMap& map4, const CUtensorMap& map1, const FaArgs& a,
               cudaStream_t stream, const char* name) {
-  using S = FaSmem<C>;
-  C2S_CUDA(cudaFuncSetAttribute(ltae_fa_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-  const int grid = a.n_tiles < fa_sm_count() ? a.n_tiles : fa_sm_count();
-  ltae_fa_kernel<C><<<static_cast<unsigned>(grid), kFaThreads, S::kTotal, stream>>>(map16, map4, map1, a);
+  using S = FaSmem<C, WPP>;
+  C2S_CUDA(cudaFuncSetAttribute(ltae_fa_kernel<C, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  const int slots = fa_sm_count() * (WPP == 1 ? 2 : 1);  // persistent CTAs: one per SM, two for the single-warp tiles
+  const int grid = a.n_tiles < slots ? a.n_tiles : slots;
+  ltae_fa_kernel<C, WPP><<<static_cast<unsigned>(grid), 256 * WPP, S::kTotal, stream>>>(map16, map4, map1, a);
   C2S_LAUNCH_CHECK(name);
   return C2S_OK;
 }
@@ -989,9 +1025,11 @@ int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void
   }
   int status;
   if (C == 128)
-    status = fa_launch<128>(map16, map4, map1, a, stream, "ltae_forward<fa,C=128>");
+    status = fa_launch<128, 2>(map16, map4, map1, a, stream, "ltae_forward<fa,C=128>");
+  else if (getenv("C2S_LTAE_FA_PAIR") != nullptr)  // comparison hook: two warps per pixel, double-buffered slabs
+    status = fa_launch<64, 2>(map16, map4, map1, a, stream, "ltae_forward<fa,C=64,pair>");
   else
-    status = fa_launch<64>(map16, map4, map1, a, stream, "ltae_forward<fa,C=64>");
+    status = fa_launch<64, 1>(map16, map4, map1, a, stream, "ltae_forward<fa,C=64>");
   if (status != C2S_OK) return status;
   if (!attn_only)
     return ltae_mlp_tc_forward(d, p, ws + lay.tc, a.bnf, a.ypre, out, stream);
