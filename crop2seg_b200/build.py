@@ -60,6 +60,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(obj_dir, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("C2S_NVCC_EXTRA", "").split()  # development only, e.g. -DC2S_FA_TIMING
 
     def compile_one(src):
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")

@@ -447,6 +447,9 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
     }
     return s;
   };
+  // g_xh is formed once: the first sweep parks it in grad_x (in the features' dtype; for bf16 that costs one extra
+  // rounding of the same size as the final one), the second sweep corrects it in place
+  T* gx = static_cast<T*>(a.g_x) + static_cast<size_t>(b) * a.T * frame_stride + pix0;
   {
     const int p = lane % kPT, sub = lane / kPT;
     constexpr int kSub = 32 / kPT;
@@ -459,7 +462,9 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
 #pragma unroll 4
         for (int e = sub; e < n_el; e += kSub) {
           const int t = e / a.cpg, c = g * a.cpg + (e - t * a.cpg);
-          const float gv = gxh(t, c, p);
+          T* dst = gx + static_cast<size_t>(t) * frame_stride + static_cast<size_t>(c) * a.hw + p;
+          Elem<T>::store(dst, gxh(t, c, p));
+          const float gv = Elem<T>::load(dst);  // the value the second sweep will see
           s1 += gv;
           s2 = fmaf(gv, fmaf(xval(t, c, p), r, -m), s2);
         }
@@ -474,7 +479,6 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
   }
   __syncthreads();
   {
-    T* gx = static_cast<T*>(a.g_x) + static_cast<size_t>(b) * a.T * frame_stride + pix0;
     const int n_el = a.T * a.C * kPT;
 #pragma unroll 4
     for (int item = tid; item < n_el; item += kBwdThreads) {
@@ -484,8 +488,8 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
       const int g = c / a.cpg;
       const float r = s_rstd[g * kPT + p];
       const float xn = fmaf(xval(t, c, p), r, -s_mu[g * kPT + p]);
-      const float v = r * (gxh(t, c, p) - s_m1[g * kPT + p] - xn * s_m2[g * kPT + p]);
-      Elem<T>::store(gx + static_cast<size_t>(t) * frame_stride + static_cast<size_t>(c) * a.hw + p, v);
+      T* dst = gx + static_cast<size_t>(t) * frame_stride + static_cast<size_t>(c) * a.hw + p;
+      Elem<T>::store(dst, r * (Elem<T>::load(dst) - s_m1[g * kPT + p] - xn * s_m2[g * kPT + p]));
     }
   }
 }
