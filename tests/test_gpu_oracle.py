@@ -237,3 +237,17 @@ def test_folded_weights_are_reused_until_a_parameter_changes():
         out3, attn3 = m(*args, **kwargs)
         assert _lib.launch_count() == first
     assert torch.equal(out3, out2) and torch.equal(attn3, attn2)
+
+
+@pytest.mark.parametrize("name", ["utae", "timeunet"])
+def test_ltae_without_attention_store(name):
+    """``return_att=False`` (model-level flag of the reference, timeunet.py:205): same output, no attention tensor."""
+    kind, kw, (b, t, h, w), lengths, _ = LTAE_CASES[name]
+    m, rng = _build(kind, kw, 77 + len(name))
+    x, pos, pad = synth_inputs(rng, b, t, kw["in_channels"], h, w, lengths)
+    for dtype in (torch.bfloat16, torch.float32):
+        with torch.no_grad():
+            out, attn = m(to_dev(x, dtype=dtype), batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+            out2, none = m(to_dev(x, dtype=dtype), batch_positions=to_dev(pos), pad_mask=to_dev(pad), return_att=False)
+        assert none is None and attn is not None
+        assert torch.equal(out, out2)
