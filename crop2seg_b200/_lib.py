@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 3
+C2S_ABI_VERSION = 4
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -24,6 +24,7 @@ EXPORTS = (
     "c2s_last_ltae_kernel",
     "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_agg_backward_workspace_bytes", "c2s_agg_backward",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
+    "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward",
 )
 
 
@@ -57,6 +58,14 @@ LTAE_BWD_IO_FIELDS = ("grad_o", "grad_attn", "grad_x", "grad_u", "grad_cpos", "g
 
 class LtaeBwdIo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in LTAE_BWD_IO_FIELDS]
+
+
+LTAE_MLP_BWD_IO_FIELDS = ("o_rows", "grad_out", "bn_mean", "bn_var", "grad_o", "grad_mlp_weight", "grad_mlp_bias",
+                          "grad_bn_weight", "grad_bn_bias", "grad_out_norm_weight", "grad_out_norm_bias")
+
+
+class LtaeMlpBwdIo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_MLP_BWD_IO_FIELDS]
 
 
 class C2SError(RuntimeError):
@@ -105,6 +114,11 @@ def load() -> ctypes.CDLL:
         lib.c2s_ltae_backward.restype = i32
         lib.c2s_ltae_backward.argtypes = [ctypes.POINTER(LtaeDesc), ctypes.POINTER(LtaeParams), vp, vp, vp,
                                           ctypes.POINTER(LtaeBwdIo), vp, sz, vp]
+        lib.c2s_ltae_mlp_backward_workspace_bytes.restype = sz
+        lib.c2s_ltae_mlp_backward_workspace_bytes.argtypes = [ctypes.POINTER(LtaeDesc)]
+        lib.c2s_ltae_mlp_backward.restype = i32
+        lib.c2s_ltae_mlp_backward.argtypes = [ctypes.POINTER(LtaeDesc), ctypes.POINTER(LtaeParams),
+                                              ctypes.POINTER(LtaeMlpBwdIo), vp, sz, vp]
         got = lib.c2s_abi_version()
         if got != C2S_ABI_VERSION:
             raise C2SError(f"ABI mismatch: library reports version {got}, binding expects {C2S_ABI_VERSION}")

@@ -143,12 +143,25 @@ def _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params
     attn_only = cfg["attn_only"]
     grads: Dict[str, torch.Tensor] = {}
 
-    # ---- stage M: rows after the attention ------------------------------------------------------------------
+    # ---- stage M: rows after the attention (c2s_ltae_mlp_backward) ---------------------------------------------
     g_o = None
     if not attn_only:
         if g_out is None:
             g_o = torch.zeros((n, D), dtype=torch.float32, device=x.device)
-        else:
+        elif cfg["c_out"] // h <= 16 and os.environ.get("C2S_LTAE_TORCH_MLP_BACKWARD") is None:
+            if cfg["bn_batch_stats"]:
+                mean, var = ctx.bn_stats
+            else:
+                mean, var = raw["bn_running_mean"], raw["bn_running_var"]
+            m_res = ops.ltae_mlp_backward(
+                ctx.o_rows, g_out.to(x.dtype), raw, mean, var, n_head=h, d_model=D, c_out=cfg["c_out"],
+                bn_batch_stats=cfg["bn_batch_stats"], gn_eps=cfg["gn_eps"], bn_eps=cfg["bn_eps"], mlp_keep=mlp_keep,
+                mlp_drop_p=1.0 - 1.0 / cfg["mlp_keep_scale"])
+            g_o = m_res["grad_o"]
+            for k in ("mlp_weight", "mlp_bias", "bn_weight", "bn_bias", "out_norm_weight", "out_norm_bias"):
+                if need[k]:
+                    grads[k] = m_res[k]
+        else:  # more than 16 channels per out_norm group: torch autograd on the small rows
             with torch.enable_grad():
                 o = ctx.o_rows.detach().requires_grad_(True)
                 names = ("mlp_weight", "mlp_bias", "bn_weight", "bn_bias", "out_norm_weight", "out_norm_bias")
@@ -180,41 +193,68 @@ def _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params
         zero_padded=cfg["zero_padded"], gn_eps=cfg["gn_eps"], attn_keep=attn_keep,
         attn_drop_p=1.0 - 1.0 / cfg["attn_keep_scale"], need_grad_pe=pe_learnable)
 
-    # ---- stage F: folded quantities -> state_dict tensors -----------------------------------------------------
+    # ---- stage F: folded quantities -> state_dict tensors (the adjoint of csrc/c2s_ltae_prep.cu, written out) -----
     front = ("in_norm_weight", "in_norm_bias", "inconv_weight", "inconv_bias", "query", "key_weight", "key_bias",
              "pe_fc_weight", "pe_fc_bias", "pe_abs_fc_weight", "pe_abs_fc_bias")
     if any(need.get(k) for k in front):
-        with torch.enable_grad():
-            L = {}
-            for k in _GRAD_PARAM_ORDER:
-                v = raw[k]
-                if v is None:
-                    L[k] = None
-                elif k in front and need[k]:
-                    L[k] = v.detach().float().requires_grad_(True)
-                else:
-                    L[k] = v.detach().float() if v.is_floating_point() else v
-            U, cpos, pe = _folded(cfg, L, positions, b, t)
-            total = (U * res["grad_u"][:, :h]).sum() + (cpos * res["grad_cpos"][:, :, :h]).sum()
-            if pe is not None and res["grad_pe"] is not None:
-                total = total + (pe * res["grad_pe"]).sum()
-            wanted = [k for k in front if need.get(k) and L[k] is not None]
-            got = torch.autograd.grad(total, [L[k] for k in wanted], allow_unused=True)
-        for k, g in zip(wanted, got):
-            if g is not None:
-                grads[k] = g
-        if not attn_only:
-            go3 = g_o.view(n, h, dh)
+        with torch.no_grad():
+            dk = cfg["d_k"]
+            rs = 1.0 / (dk ** 0.5)
+            gamma, beta = raw["in_norm_weight"].float(), raw["in_norm_bias"].float()
+            wc, bc = raw["inconv_weight"].float().reshape(D, c), raw["inconv_bias"].float()
+            q, wk = raw["query"].float().reshape(h, dk), raw["key_weight"].float().reshape(h, dk, D)
+            bk = raw["key_bias"].float().reshape(h, dk)
+            qk = torch.einsum("hj,hjd->hd", q, wk) * rs           # [h, D]
+            m = qk @ wc                                            # [h, C]: U = m^T * gamma
+            g_u = res["grad_u"][:, :h]                             # [C, h]
+            g_cpos = res["grad_cpos"][:, :, :h].reshape(b * t, h)  # [B T, h]
+            g_m = g_u.t() * gamma[None, :]
+            g_qk = g_m @ wc.t()
+            g_wc = qk.t() @ g_m
+            g_gamma = (g_u * m.t()).sum(1)
+            wb = bc + wc @ beta                                    # cpos = qk (wb + pe) + q . bk / sqrt(dk)
+            g_ub = g_cpos.sum(0)
+            g_qk += g_ub[:, None] * wb[None, :]
+            g_wb = g_ub @ qk
+            g_pe = res["grad_pe"]
+            if cfg["pe_mode"] != _lib.PE_NONE:
+                pe = _positional(cfg, {k: (v.float() if v is not None and v.is_floating_point() else v)
+                                       for k, v in raw.items()}, positions, 0).reshape(b * t, D)
+                g_qk += g_cpos.t() @ pe
+                via_cpos = (g_cpos @ qk).view(b, t, D)
+                g_pe = via_cpos if g_pe is None else g_pe + via_cpos
+            g_wc += g_wb[:, None] * beta[None, :]
             if need["in_norm_weight"]:
-                grads["in_norm_weight"] = grads.get("in_norm_weight", 0) + res["grad_gamma"]
+                grads["in_norm_weight"] = g_gamma + (0 if attn_only else res["grad_gamma"])
             if need["in_norm_bias"]:
-                grads["in_norm_bias"] = grads.get("in_norm_bias", 0) + res["grad_beta"]
+                grads["in_norm_bias"] = wc.t() @ g_wb + (0 if attn_only else res["grad_beta"])
+            if not attn_only:
+                go3 = g_o.view(n, h, dh)
+                if need["inconv_weight"]:
+                    g_wc += torch.einsum("nhi,nhc->hic", go3, res["zn_rows"]).reshape(D, c)
+                if need["inconv_bias"]:
+                    g_wb = g_wb + torch.einsum("nhi,nh->hi", go3, res["sa_rows"][:, :h]).reshape(D)
             if need["inconv_weight"]:
-                direct = torch.einsum("nhi,nhc->hic", go3, res["zn_rows"]).reshape(D, c)
-                grads["inconv_weight"] = grads.get("inconv_weight", 0) + direct.reshape(raw["inconv_weight"].shape)
+                grads["inconv_weight"] = g_wc
             if need["inconv_bias"]:
-                direct = torch.einsum("nhi,nh->hi", go3, res["sa_rows"][:, :h]).reshape(D)
-                grads["inconv_bias"] = grads.get("inconv_bias", 0) + direct
+                grads["inconv_bias"] = g_wb
+            if need["query"]:
+                grads["query"] = torch.einsum("hd,hjd->hj", g_qk, wk) * rs + g_ub[:, None] * bk * rs
+            if need["key_weight"]:
+                grads["key_weight"] = q[:, :, None] * g_qk[:, None, :] * rs
+            if need["key_bias"]:
+                grads["key_bias"] = g_ub[:, None] * q * rs
+        pe_names = [k for k in ("pe_fc_weight", "pe_fc_bias", "pe_abs_fc_weight", "pe_abs_fc_bias")
+                    if need.get(k) and raw[k] is not None]
+        if pe_names and g_pe is not None:  # learnable tables / add_linear: the small table graph through autograd
+            with torch.enable_grad():
+                L = {k: (v.detach().float().requires_grad_(k in pe_names) if v is not None and v.is_floating_point() else v)
+                     for k, v in raw.items()}
+                got = torch.autograd.grad(_positional(cfg, L, positions, 0), [L[k] for k in pe_names], g_pe,
+                                          allow_unused=True)
+            for k, gk in zip(pe_names, got):
+                if gk is not None:
+                    grads[k] = gk
     gx = res["grad_x"] if ctx.needs_input_grad[0] else None
     gparams = []
     for k, p in zip(_GRAD_PARAM_ORDER, params):
@@ -250,6 +290,7 @@ class LtaeFunction(torch.autograd.Function):
         ctx.opt = (positions, pad_mask, attn_keep, mlp_keep)
         ctx.save_for_backward(x, *[p for p in params if p is not None])
         mean, var = stats if stats is not None else (None, None)
+        ctx.bn_stats = stats  # batch statistics the forward normalised with (training mode)
         if stats is not None:
             ctx.mark_non_differentiable(mean, var)
         return out, attn, mean, var

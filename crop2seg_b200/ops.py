@@ -318,3 +318,50 @@ def ltae_backward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: 
                                        ctypes.byref(io), ws.data_ptr(), ws_bytes, _stream(dev))
     _lib.check(status, "c2s_ltae_backward")
     return res
+
+
+def ltae_mlp_backward(o_rows: torch.Tensor, grad_out: torch.Tensor, params: Dict[str, Optional[torch.Tensor]],
+                      bn_mean: torch.Tensor, bn_var: torch.Tensor, *, n_head: int, d_model: int, c_out: int,
+                      bn_batch_stats: bool, gn_eps: float = 1e-5, bn_eps: float = 1e-5,
+                      mlp_keep: Optional[torch.Tensor] = None, mlp_drop_p: float = 0.0) -> Dict[str, torch.Tensor]:
+    """``c2s_ltae_mlp_backward``: backward of mlp.0 / mlp.2 / ReLU / dropout / out_norm on the pixel rows.
+
+    ``o_rows`` [B*H*W, d_model] are the rows saved by the forward, ``grad_out`` [B, c_out, H, W] the incoming gradient,
+    ``bn_mean`` / ``bn_var`` the statistics the forward normalised with.  Returns ``grad_o`` and the parameter
+    gradients keyed like ``c2s_ltae_params``."""
+    _require_cuda(grad_out, "grad_out")
+    dev = grad_out.device
+    b, co, h, w = grad_out.shape
+    n = b * h * w
+    if co != c_out or tuple(o_rows.shape) != (n, d_model):
+        raise RuntimeError(f"crop2seg_b200: grad_out {tuple(grad_out.shape)} / o_rows {tuple(o_rows.shape)} do not match")
+    g = grad_out.contiguous()
+    flags = _lib.LTAE_BN_BATCH_STATS if bn_batch_stats else 0
+    desc = _lib.LtaeDesc(B=b, T=1, C=n_head, H=h, W=w, n_head=n_head, d_k=1, d_model=d_model, c_out=c_out, has_inconv=1,
+                         pe_mode=_lib.PE_NONE, pe_abs=0, pos_dtype=0, dtype=_dtype_code(g, "grad_out"), flags=flags,
+                         gn_eps=gn_eps, bn_eps=bn_eps, attn_keep_scale=1.0, mlp_keep_scale=1.0 / (1.0 - mlp_drop_p))
+    keep = []
+    cparams = _lib.LtaeParams(**{k: _f32(params.get(k), dev, keep) for k in _lib.LTAE_PARAM_FIELDS})
+    if mlp_keep is not None:
+        m = mlp_keep.to(device=dev, dtype=torch.uint8).contiguous()
+        keep.append(m)
+        cparams.mlp_keep = m.data_ptr()
+    f32 = dict(dtype=torch.float32, device=dev)
+    res = {"grad_o": torch.empty((n, d_model), **f32), "mlp_weight": torch.zeros((c_out, d_model), **f32)}
+    for k in ("mlp_bias", "bn_weight", "bn_bias", "out_norm_weight", "out_norm_bias"):
+        res[k] = torch.zeros(c_out, **f32)
+    o = o_rows.to(**f32).contiguous()
+    mean, var = bn_mean.to(**f32).contiguous(), bn_var.to(**f32).contiguous()
+    io = _lib.LtaeMlpBwdIo(o_rows=o.data_ptr(), grad_out=g.data_ptr(), bn_mean=mean.data_ptr(), bn_var=var.data_ptr(),
+                           grad_o=res["grad_o"].data_ptr(), grad_mlp_weight=res["mlp_weight"].data_ptr(),
+                           grad_mlp_bias=res["mlp_bias"].data_ptr(), grad_bn_weight=res["bn_weight"].data_ptr(),
+                           grad_bn_bias=res["bn_bias"].data_ptr(), grad_out_norm_weight=res["out_norm_weight"].data_ptr(),
+                           grad_out_norm_bias=res["out_norm_bias"].data_ptr())
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.c2s_ltae_mlp_backward_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        status = lib.c2s_ltae_mlp_backward(ctypes.byref(desc), ctypes.byref(cparams), ctypes.byref(io), ws.data_ptr(),
+                                           ws_bytes, _stream(dev))
+    _lib.check(status, "c2s_ltae_mlp_backward")
+    return res

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 3
+#define C2S_ABI_VERSION 4
 
 enum c2s_status {
   C2S_OK = 0,
@@ -185,6 +185,27 @@ typedef struct c2s_ltae_bwd_io {
   float* sa_rows;         /* out [B*H*W][16]:        grad_bc[d]   (direct) = sum_n grad_o[n][d] sa[n][h(d)]   */
   float* grad_pe;         /* acc [B][T][d_model] direct term of the positional table, or NULL              */
 } c2s_ltae_bwd_io;
+
+/* Backward of the rows behind the attention: mlp.0 (Linear), mlp.2 (BatchNorm1d, batch statistics with
+ * C2S_LTAE_BN_BATCH_STATS, running statistics otherwise), ReLU, dropout mask (params->mlp_keep), out_norm
+ * (autograd through tae.py:442-449, 486-488).  Produces grad_o for c2s_ltae_backward.  acc buffers must be zeroed. */
+typedef struct c2s_ltae_mlp_bwd_io {
+  const float* o_rows;          /* in  [B*H*W][d_model] rows saved by c2s_ltae_forward (params->save_o)   */
+  const void* grad_out;         /* in  [B][c_out][H][W] in desc->dtype                                     */
+  const float* bn_mean;         /* in  [c_out] batch mean of the forward (training) or running_mean        */
+  const float* bn_var;          /* in  [c_out] biased batch variance (training) or running_var             */
+  float* grad_o;                /* out [B*H*W][d_model]                                                    */
+  float* grad_mlp_weight;       /* acc [c_out][d_model]                                                    */
+  float* grad_mlp_bias;         /* acc [c_out]                                                             */
+  float* grad_bn_weight;        /* acc [c_out]                                                             */
+  float* grad_bn_bias;          /* acc [c_out]                                                             */
+  float* grad_out_norm_weight;  /* acc [c_out]                                                             */
+  float* grad_out_norm_bias;    /* acc [c_out]                                                             */
+} c2s_ltae_mlp_bwd_io;
+
+size_t c2s_ltae_mlp_backward_workspace_bytes(const c2s_ltae_desc* desc);
+int c2s_ltae_mlp_backward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const c2s_ltae_mlp_bwd_io* io,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 size_t c2s_ltae_backward_workspace_bytes(const c2s_ltae_desc* desc);
 int c2s_ltae_backward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const void* x, const void* positions,
