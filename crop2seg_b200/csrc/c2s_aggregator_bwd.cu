@@ -11,6 +11,8 @@
 // HBM traffic: e*T_valid*C*H*W read (x) + e*T*C*H*W written (grad_x) + e*C*H*W (grad_out) per sample.
 #include <type_traits>
 
+#include <cstdlib>
+
 #include "c2s_common.cuh"
 
 namespace c2s {
@@ -30,6 +32,7 @@ struct AggBwdArgs {
   int uniform;       // 'mean' mode
   float sy, sx;
   int hw, vecs_per_plane;
+  int t_chunks, t_per_chunk;  // the frame loop is split over blockIdx.z (set by launch_bwd)
 };
 
 __device__ __forceinline__ void bwd_source_index(float scale, int dst, int in_size, int& i0, int& i1, float& l1) {
@@ -68,7 +71,11 @@ template <typename T, int VEC, int CPT, int S>
 __global__ void __launch_bounds__(kBwdThreads) agg_backward_kernel(const AggBwdArgs a) {
   __shared__ uint8_t s_pad[1024];
   __shared__ int s_nvalid;
-  const int b = blockIdx.z;
+  // blockIdx.z = sample * t_chunks + chunk: the frames are independent (grad_x per frame, grad_attn per frame), so small
+  // planes, which have few pixel blocks, are also split over T to fill the SMs
+  const int b = blockIdx.z / a.t_chunks;
+  const int t_begin = (blockIdx.z - b * a.t_chunks) * a.t_per_chunk;
+  const int t_end = min(a.T, t_begin + a.t_per_chunk);
   if (threadIdx.x < 32) {
     int count = 0;
     for (int base = 0; base < a.T; base += 32) {
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(kBwdThreads) agg_backward_kernel(const AggBwdA
   const bool has_left = active && lane > 0 && lane_in_row > 0;
   const bool has_right = active && lane < 31 && lane_in_row < lanes_per_row - 1 && (pv + 1) < a.vecs_per_plane;
 
-  for (int t = 0; t < a.T; ++t) {
+  for (int t = t_begin; t < t_end; ++t) {
     const bool padded = s_pad[t] != 0;  // block-uniform
     float w[VEC];
     if (padded) {
@@ -251,6 +258,240 @@ __global__ void __launch_bounds__(kBwdThreads) agg_backward_kernel(const AggBwdA
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Pipelined variant for the shipped shapes (power-of-two up-sampling S with VEC >= S, 4-channel head groups, whole
+// 16-byte vectors, grad_x AND grad_attn wanted): same arithmetic as agg_backward_kernel, but x travels HBM -> shared
+// memory through the bulk-copy engine (cp.async.bulk + mbarrier transaction counts, as in agg_pipe_kernel of the
+// forward), so the bytes in flight per SM are set by the ring of stages, not by the registers of the consumers, which
+// are busy with the stores of grad_x and the adjoint.  One CTA = one sample x one head (4 channels) x n_consumers
+// pixel vectors x one chunk of frames; one producer thread issues four row copies per valid frame.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBwdPipeCPT = 4;
+constexpr int kBwdPipeMaxConsumers = 256;
+
+__device__ __forceinline__ uint32_t bsmem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void bmbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bmbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bmbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bmbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bbulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint4 blds_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+template <typename T, int S>
+__global__ void __launch_bounds__(kBwdPipeMaxConsumers + 32, 2)
+agg_backward_pipe_kernel(const AggBwdArgs a, int n_stages, int n_consumers, int pblocks) {
+  constexpr int VEC = Elem<T>::kVec;
+  constexpr int CPT = kBwdPipeCPT;
+  constexpr int M = VEC / S;   // attention cells per thread
+  constexpr int NCOL = M + 2;
+  extern __shared__ __align__(128) unsigned char bpipe_smem[];
+  __shared__ uint8_t s_pad[1024];
+  __shared__ __align__(8) unsigned long long bars[2 * 16];  // full[0..15], empty[0..15]
+
+  const int b = blockIdx.y / a.t_chunks;
+  const int t_begin = (blockIdx.y - b * a.t_chunks) * a.t_per_chunk;
+  const int t_end = min(a.T, t_begin + a.t_per_chunk);
+  const int cchunk = blockIdx.x / pblocks;
+  const int pblk = blockIdx.x - cchunk * pblocks;
+  const int c0 = cchunk * CPT;
+  const uint32_t row_bytes = n_consumers * 16;
+  const uint32_t stage_bytes = CPT * row_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cwarps = n_consumers >> 5;
+
+  for (int t = threadIdx.x; t < a.T; t += blockDim.x) s_pad[t] = a.pad != nullptr && a.pad[b * a.T + t] != 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      bmbar_init(bsmem_addr(&bars[s]), 1);
+      bmbar_init(bsmem_addr(&bars[16 + s]), n_cwarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const size_t frame_stride = static_cast<size_t>(a.C) * a.hw;
+  const uint32_t stage0 = bsmem_addr(bpipe_smem);
+  const size_t plane0 = static_cast<size_t>(c0) * a.hw + static_cast<size_t>(pblk) * n_consumers * VEC;
+
+  if (warp == n_cwarps) {  // ---- producer: the valid frames of the chunk, in order ------------------------
+    if (lane == 0) {
+      const T* src = static_cast<const T*>(a.x) + static_cast<size_t>(b) * a.T * frame_stride + plane0;
+      int i = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        if (s_pad[t]) continue;
+        const int s = i % n_stages, round = i / n_stages;
+        if (round > 0) bmbar_wait(bsmem_addr(&bars[16 + s]), (round - 1) & 1);
+        const uint32_t full = bsmem_addr(&bars[s]);
+        bmbar_expect_tx(full, stage_bytes);
+        const T* fp = src + static_cast<size_t>(t) * frame_stride;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k)
+          bbulk_g2s(stage0 + s * stage_bytes + k * row_bytes, fp + static_cast<size_t>(k) * a.hw, row_bytes, full);
+        ++i;
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ------------------------------------------------------------------------------------------
+  const int pv = pblk * n_consumers + threadIdx.x;  // pixel vector of the plane
+  const int p0 = pv * VEC;
+  const int y = p0 / a.W, x0 = p0 - y * a.W;
+  int iy0, iy1;
+  float ly1;
+  bwd_source_index(a.sy, y, a.ha, iy0, iy1, ly1);
+  const int row0 = iy0 * a.wa, row1 = iy1 * a.wa;
+  const float ly0 = 1.f - ly1;
+  float lx1[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    int i0, i1;
+    bwd_source_index(a.sx, x0 + j, a.wa, i0, i1, lx1[j]);
+  }
+  const int cmin = x0 / S - 1;
+  auto clampc = [&](int c) { return c < 0 ? 0 : (c > a.wa - 1 ? a.wa - 1 : c); };
+  T* gxb = static_cast<T*>(a.gx) + static_cast<size_t>(b) * a.T * frame_stride + plane0 + static_cast<size_t>(threadIdx.x) * VEC;
+  const int amap = a.ha * a.wa;
+  const size_t abase = (static_cast<size_t>(c0 / a.cpg) * a.B + b) * a.T * amap;
+
+  float go[CPT][VEC];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k)
+    BVec<T, VEC>::load(static_cast<const T*>(a.gout) + (static_cast<size_t>(b) * a.C + c0 + k) * a.hw + p0, go[k]);
+
+  // lanes of the same image row that sit next to each other in the warp exchange their edge columns
+  const int lanes_per_row = a.W / VEC;
+  const int lane_in_row = pv % lanes_per_row;
+  const bool has_left = lane > 0 && lane_in_row > 0;
+  const bool has_right = lane < 31 && lane_in_row < lanes_per_row - 1;
+  const uint32_t my_off = threadIdx.x * 16;
+
+  int i = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    if (s_pad[t]) {  // block-uniform
+      float z[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) z[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) BVec<T, VEC>::store(gxb + static_cast<size_t>(t) * frame_stride + static_cast<size_t>(k) * a.hw, z);
+      continue;
+    }
+    // forward weights (identical arithmetic to agg_forward_kernel); the taps travel while the stage is awaited
+    const float* ap = a.attn + abase + static_cast<size_t>(t) * amap;
+    float r[NCOL];
+#pragma unroll
+    for (int jj = 0; jj < NCOL; ++jj) {
+      const int cj = clampc(cmin + jj);
+      r[jj] = fmaf(ly1, __ldg(ap + row1 + cj), ly0 * __ldg(ap + row0 + cj));
+    }
+    const int s = i % n_stages;
+    bmbar_wait(bsmem_addr(&bars[s]), (i / n_stages) & 1);
+    uint4 xv[CPT];
+    const uint32_t base = stage0 + s * stage_bytes + my_off;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) xv[k] = blds_v4(base + k * row_bytes);
+    __syncwarp();
+    if (lane == 0) bmbar_arrive(bsmem_addr(&bars[16 + s]));  // the stage's data now lives in registers
+    ++i;
+
+    float g[VEC];  // sum_c x * grad_out of this thread's pixels
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) g[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      float f[VEC], d[VEC];
+      Elem<T>::unpack(xv[k], f);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int i0w = j / S + ((j % S) < S / 2 ? 0 : 1);
+        const float w = fmaf(lx1[j], r[i0w + 1], (1.f - lx1[j]) * r[i0w]);
+        g[j] = fmaf(f[j], go[k][j], g[j]);
+        d[j] = w * go[k][j];
+      }
+      BVec<T, VEC>::store(gxb + static_cast<size_t>(t) * frame_stride + static_cast<size_t>(k) * a.hw, d);
+    }
+    // horizontal adjoint into the NCOL-column window, then edge columns travel to the neighbouring lanes
+    float* gp = a.gattn + abase + static_cast<size_t>(t) * amap;
+    float win[NCOL];
+#pragma unroll
+    for (int jj = 0; jj < NCOL; ++jj) win[jj] = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int i0w = j / S + ((j % S) < S / 2 ? 0 : 1);
+      win[i0w] = fmaf(g[j], 1.f - lx1[j], win[i0w]);
+      win[i0w + 1] = fmaf(g[j], lx1[j], win[i0w + 1]);
+    }
+    const float from_left = __shfl_up_sync(0xffffffffu, win[NCOL - 1], 1);
+    const float from_right = __shfl_down_sync(0xffffffffu, win[0], 1);
+    float own[M];
+#pragma unroll
+    for (int q = 0; q < M; ++q) own[q] = win[q + 1];
+    if (has_left) own[0] += from_left;
+    if (has_right) own[M - 1] += from_right;
+#pragma unroll
+    for (int q = 0; q < M; ++q) {
+      const int cj = cmin + 1 + q;  // own columns are always inside [0, wa)
+      atomicAdd(gp + row0 + cj, ly0 * own[q]);
+      if (ly1 != 0.f) atomicAdd(gp + row1 + cj, ly1 * own[q]);
+    }
+    if (!has_left) {  // edge columns nobody picked up (image border: clamped; warp or row boundary)
+      const int cj = clampc(cmin);
+      atomicAdd(gp + row0 + cj, ly0 * win[0]);
+      if (ly1 != 0.f) atomicAdd(gp + row1 + cj, ly1 * win[0]);
+    }
+    if (!has_right) {
+      const int cj = clampc(cmin + NCOL - 1);
+      atomicAdd(gp + row0 + cj, ly0 * win[NCOL - 1]);
+      if (ly1 != 0.f) atomicAdd(gp + row1 + cj, ly1 * win[NCOL - 1]);
+    }
+  }
+}
+
+template <typename T, int S>
+int launch_bwd_pipe_s(const AggBwdArgs& a, int n_consumers, int n_stages, cudaStream_t stream, const char* name) {
+  constexpr int VEC = Elem<T>::kVec;
+  AggBwdArgs b = a;
+  const int pblocks = a.vecs_per_plane / n_consumers;
+  const long long ctas = static_cast<long long>(a.C / kBwdPipeCPT) * pblocks * a.B;
+  int chunks = 1;
+  while (ctas * chunks < 8 * 148 && ceil_div(a.T, chunks * 2) >= 8 && static_cast<long long>(a.B) * chunks * 2 <= 65535) chunks *= 2;
+  b.t_per_chunk = ceil_div(a.T, chunks);
+  b.t_chunks = ceil_div(a.T, b.t_per_chunk);
+  const size_t smem = static_cast<size_t>(n_stages) * kBwdPipeCPT * n_consumers * 16;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    C2S_CUDA(cudaFuncSetAttribute(agg_backward_pipe_kernel<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 16384));
+    attr_done = true;
+  }
+  dim3 grid((a.C / kBwdPipeCPT) * pblocks, a.B * b.t_chunks);
+  agg_backward_pipe_kernel<T, S><<<grid, n_consumers + 32, smem, stream>>>(b, n_stages, n_consumers, pblocks);
+  C2S_LAUNCH_CHECK(name);
+  (void)VEC;
+  return C2S_OK;
+}
+
 // att_mean: every head receives grad(mean) / n_heads                       (temporal_aggregator.py:48)
 __global__ void spread_head_mean_kernel(const float* __restrict__ gmean, float* __restrict__ gattn, int n_heads, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -268,8 +509,15 @@ __global__ void head_mean_bwd_fwd_kernel(const float* __restrict__ attn, float* 
 
 template <typename T, int VEC, int CPT, int S>
 int launch_bwd(const AggBwdArgs& a, cudaStream_t stream, const char* name) {
-  dim3 grid(ceil_div(a.vecs_per_plane, kBwdThreads), a.C / CPT, a.B);
-  agg_backward_kernel<T, VEC, CPT, S><<<grid, kBwdThreads, 0, stream>>>(a);
+  AggBwdArgs b = a;
+  const long long ctas = static_cast<long long>(ceil_div(a.vecs_per_plane, kBwdThreads)) * (a.C / CPT) * a.B;
+  int chunks = 1;  // enough CTAs for ~8 per SM, at least 8 frames per CTA (the prologue loads grad_out once per CTA)
+  while (ctas * chunks < 8 * 148 && ceil_div(a.T, chunks * 2) >= 8 && static_cast<long long>(a.B) * chunks * 2 <= 65535) chunks *= 2;
+  if (getenv("C2S_AGG_BWD_CHUNKS") != nullptr) chunks = atoi(getenv("C2S_AGG_BWD_CHUNKS")) > 0 ? atoi(getenv("C2S_AGG_BWD_CHUNKS")) : 1;  // tuning hook
+  b.t_per_chunk = ceil_div(a.T, chunks);
+  b.t_chunks = ceil_div(a.T, b.t_per_chunk);
+  dim3 grid(ceil_div(a.vecs_per_plane, kBwdThreads), a.C / CPT, a.B * b.t_chunks);
+  agg_backward_kernel<T, VEC, CPT, S><<<grid, kBwdThreads, 0, stream>>>(b);
   C2S_LAUNCH_CHECK(name);
   return C2S_OK;
 }
@@ -375,6 +623,39 @@ int c2s_agg_backward(const c2s_agg_desc* d, const void* x, const float* attn, co
   a.vecs_per_plane = a.hw / vec;
   if (scale_class > 0 && (vec == 1 || vec < scale_class)) scale_class = 0;  // whole attention cells per thread only
 
+  // pipelined variant: both gradients wanted, power-of-two up-sampling with whole attention cells per thread
+  const bool no_pipe = getenv("C2S_AGG_NO_PIPE") != nullptr;  // test hook: A/B against the register kernel
+  if (!no_pipe && scale_class > 0 && vec == vec_full && vec >= scale_class && a.cpg % kBwdPipeCPT == 0 && a.gx != nullptr &&
+      a.gattn != nullptr && x != nullptr && a.W % vec == 0) {
+    const int vecs = a.vecs_per_plane;
+    int n_consumers = vecs < kBwdPipeMaxConsumers ? vecs : kBwdPipeMaxConsumers;
+    if (n_consumers >= 64 && n_consumers % 32 == 0 && vecs % n_consumers == 0) {
+      int n_stages = getenv("C2S_AGG_BWD_STAGES") ? atoi(getenv("C2S_AGG_BWD_STAGES")) : 4;
+      n_stages = n_stages > 16 ? 16 : (n_stages < 2 ? 2 : n_stages);
+      while (static_cast<size_t>(n_stages) * kBwdPipeCPT * n_consumers * 16 > 12 * 16384) --n_stages;
+      auto go = [&](auto tag) {
+        using TT = decltype(tag);
+        switch (scale_class) {
+          case 2: return launch_bwd_pipe_s<TT, 2>(a, n_consumers, n_stages, stream, "agg_backward_pipe<x2>");
+          case 4: return launch_bwd_pipe_s<TT, 4>(a, n_consumers, n_stages, stream, "agg_backward_pipe<x4>");
+          default:
+            if constexpr (Elem<TT>::kVec >= 8)
+              return launch_bwd_pipe_s<TT, 8>(a, n_consumers, n_stages, stream, "agg_backward_pipe<x8>");
+            else
+              return -1;  // fp32 vectors hold 4 pixels: no whole x8 cell per thread, the register kernel takes it
+        }
+      };
+      status = bf16 ? go(__nv_bfloat16{}) : go(float{});
+      if (status != -1) {
+        if (status != C2S_OK) return status;
+        if (gmean != nullptr) {
+          spread_head_mean_kernel<<<ceil_div(n_mean, 256), 256, 0, stream>>>(gmean, grad_attn, d->n_heads, n_mean);
+          C2S_LAUNCH_CHECK("spread_head_mean");
+        }
+        return C2S_OK;
+      }
+    }
+  }
   if (bf16)
     status = vec == 8 ? launch_bwd_cpt<__nv_bfloat16, 8>(a, cpt, scale_class, stream)
                       : launch_bwd_cpt<__nv_bfloat16, 1>(a, cpt, scale_class, stream);
