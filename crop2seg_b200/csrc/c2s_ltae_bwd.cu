@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
     s_flag[t] = (padded ? 1 : 0) | ((padded && a.zero_padded) ? 0 : 2);
   }
   for (int i = tid; i < a.C * kMaxHeads; i += kBwdThreads) s_u[i] = a.u[i];
+  for (int i = tid; i < kMaxHeads * kPT; i += kBwdThreads) s_m1[i] = 0.f, s_m2[i] = 0.f;
   if (!a.attn_only)
     for (int i = tid; i < a.D * kPT; i += kBwdThreads) {
       const int p = i / a.D, d = i - p * a.D;
@@ -128,55 +129,68 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
   auto xval = [&](int t, int c, int p) -> float {
     return (s_flag[t] & 2) ? Elem<T>::load(xb + static_cast<size_t>(t) * frame_stride + static_cast<size_t>(c) * a.hw + p) : 0.f;
   };
+  const bool vec4 = (a.dh & 3) == 0;  // float4 loads of the Wc^T / PE rows
   auto keepf = [&](int hh, int t, int p) -> float {
     if (a.attn_keep == nullptr) return 1.f;
     return a.attn_keep[((static_cast<size_t>(hh) * a.B + b) * a.T + t) * a.hw + pix0 + p] ? a.attn_keep_scale : 0.f;
   };
 
   // ---- phase 1: GroupNorm statistics (tae.py:461; all T frames, zero frames included) -------------------------
+  // One thread = one (frame, pixel); sums are shifted by a pivot (first frame that is read, first channel of the group),
+  // added over the 4 frames of a warp by shuffles and over the warps in shared memory.
   {
-    const int p = lane % kPT, sub = lane / kPT;
-    constexpr int kSub = 32 / kPT;
-    const bool live = p < n_pix;
-    const float n_all = static_cast<float>(a.T) * a.cpg;
-    for (int g = warp; g < a.n_head; g += kBwdThreads / 32) {
-      float pivot = 0.f;  // first frame that is read, first channel of the group
-      if (live) {
-        for (int t = 0; t < a.T; ++t)
-          if (s_flag[t] & 2) {
-            pivot = xval(t, g * a.cpg, p);
-            break;
-          }
+    int t_first = -1, n_read = 0;
+    for (int t = 0; t < a.T; ++t)
+      if (s_flag[t] & 2) {
+        if (t_first < 0) t_first = t;
+        ++n_read;
       }
-      float s1 = 0.f, s2 = 0.f;
-      int n_read = 0;
-      if (live) {
-        for (int t = 0; t < a.T; ++t) {
-          if (!(s_flag[t] & 2)) continue;
-          ++n_read;
-          for (int cc = sub; cc < a.cpg; cc += kSub) {
-            const float v = xval(t, g * a.cpg + cc, p) - pivot;
+    for (int it0 = 0; it0 < a.T * kPT; it0 += kBwdThreads) {  // uniform trip count: every lane joins the shuffles
+      const int item = it0 + tid;
+      const int t = item / kPT, p = item - t * kPT;
+      const bool live = item < a.T * kPT && p < n_pix && (s_flag[t] & 2);
+      const T* xt = xb + static_cast<size_t>(live ? t : 0) * frame_stride + p;
+      const T* xp = xb + static_cast<size_t>(t_first < 0 ? 0 : t_first) * frame_stride + p;
+      for (int g = 0, c = 0; g < a.n_head; ++g) {
+        float s1 = 0.f, s2 = 0.f;
+        if (live) {
+          const float pivot = Elem<T>::load(xp + static_cast<size_t>(c) * a.hw);
+#pragma unroll 8
+          for (int cc = 0; cc < a.cpg; ++cc) {
+            const float v = Elem<T>::load(xt + static_cast<size_t>(c + cc) * a.hw) - pivot;
             s1 += v;
             s2 = fmaf(v, v, s2);
           }
         }
-      }
+        c += a.cpg;
 #pragma unroll
-      for (int o = kPT; o < 32; o <<= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        for (int o = kPT; o < 32; o <<= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane < kPT && lane < n_pix) {
+          atomicAdd(s_m1 + g * kPT + lane, s1);
+          atomicAdd(s_m2 + g * kPT + lane, s2);
+        }
       }
-      if (sub == 0) {
-        const float n_skip = n_all - static_cast<float>(n_read) * a.cpg;
-        s1 -= n_skip * pivot;
-        s2 = fmaf(n_skip * pivot, pivot, s2);
-        const float m = s1 / n_all;
-        float var = s2 / n_all - m * m;
-        var = var < 0.f ? 0.f : var;
-        const float rstd = 1.f / sqrtf(var + a.gn_eps);
-        s_rstd[g * kPT + p] = rstd;
-        s_mu[g * kPT + p] = (m + pivot) * rstd;
-      }
+    }
+    __syncthreads();
+    const float n_all = static_cast<float>(a.T) * a.cpg;
+    for (int i = tid; i < a.n_head * kPT; i += kBwdThreads) {
+      const int g = i / kPT, p = i - g * kPT;
+      float s1 = s_m1[i], s2 = s_m2[i];
+      s_m1[i] = 0.f, s_m2[i] = 0.f;  // phase 7 accumulates the GroupNorm-backward means here
+      if (p >= n_pix) continue;
+      const float pivot = t_first < 0 ? 0.f : xval(t_first, g * a.cpg, p);
+      const float n_skip = n_all - static_cast<float>(n_read) * a.cpg;
+      s1 -= n_skip * pivot;
+      s2 = fmaf(n_skip * pivot, pivot, s2);
+      const float m = s1 / n_all;
+      float var = s2 / n_all - m * m;
+      var = var < 0.f ? 0.f : var;
+      const float rstd = 1.f / sqrtf(var + a.gn_eps);
+      s_rstd[i] = rstd;
+      s_mu[i] = (m + pivot) * rstd;
     }
   }
   __syncthreads();
@@ -197,19 +211,21 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
       }
       const bool rd = (s_flag[t] & 2) != 0;  // hoisted: the loads of the unrolled loop go out back to back
       const T* xt = xb + static_cast<size_t>(t) * frame_stride + p;
-#pragma unroll 8
-      for (int c = 0; c < a.C; ++c) {
-        const int g = c / a.cpg;
-        const float xv = rd ? Elem<T>::load(xt + static_cast<size_t>(c) * a.hw) : 0.f;
-        const float xn = fmaf(xv, s_rstd[g * kPT + p], -s_mu[g * kPT + p]);
-        const float4* up = reinterpret_cast<const float4*>(s_u + c * kMaxHeads);
+      for (int g = 0, c = 0; g < a.n_head; ++g) {
+        const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
+#pragma unroll 4
+        for (int cc = 0; cc < a.cpg; ++cc, ++c) {
+          const float xv = rd ? Elem<T>::load(xt + static_cast<size_t>(c) * a.hw) : 0.f;
+          const float xn = fmaf(xv, r, -m);
+          const float4* up = reinterpret_cast<const float4*>(s_u + c * kMaxHeads);
 #pragma unroll
-        for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
-          const float4 w = up[k4];
-          acc[4 * k4] = fmaf(w.x, xn, acc[4 * k4]);
-          acc[4 * k4 + 1] = fmaf(w.y, xn, acc[4 * k4 + 1]);
-          acc[4 * k4 + 2] = fmaf(w.z, xn, acc[4 * k4 + 2]);
-          acc[4 * k4 + 3] = fmaf(w.w, xn, acc[4 * k4 + 3]);
+          for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
+            const float4 w = up[k4];
+            acc[4 * k4] = fmaf(w.x, xn, acc[4 * k4]);
+            acc[4 * k4 + 1] = fmaf(w.y, xn, acc[4 * k4 + 1]);
+            acc[4 * k4 + 2] = fmaf(w.z, xn, acc[4 * k4 + 2]);
+            acc[4 * k4 + 3] = fmaf(w.w, xn, acc[4 * k4 + 3]);
+          }
         }
       }
     }
@@ -248,8 +264,18 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
       float* dst = s_gzn + (c * kPT + p) * kHP;
       for (int hh = 0; hh < kMaxHeads; ++hh) {
         float acc = 0.f;
-        if (hh < a.n_head)
-          for (int i = 0; i < a.dh; ++i) acc = fmaf(__ldg(w + hh * a.dh + i), s_go[(hh * a.dh + i) * kPT + p], acc);
+        if (hh < a.n_head) {
+          if (vec4) {
+            for (int i = 0; i < a.dh; i += 4) {
+              const float4 wv = __ldg(reinterpret_cast<const float4*>(w + hh * a.dh + i));
+              const float* gq = s_go + (hh * a.dh + i) * kPT + p;
+              acc = fmaf(wv.x, gq[0], acc), acc = fmaf(wv.y, gq[kPT], acc);
+              acc = fmaf(wv.z, gq[2 * kPT], acc), acc = fmaf(wv.w, gq[3 * kPT], acc);
+            }
+          } else {
+            for (int i = 0; i < a.dh; ++i) acc = fmaf(__ldg(w + hh * a.dh + i), s_go[(hh * a.dh + i) * kPT + p], acc);
+          }
+        }
         dst[hh] = acc;
       }
     }
@@ -288,26 +314,37 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
           for (int k = 0; k < kMaxHeads; ++k) {
             if (k < a.n_head) {
               float s = 0.f;
-              for (int i = 0; i < a.dh; ++i) s = fmaf(s_go[(k * a.dh + i) * kPT + p], __ldg(pe + k * a.dh + i), s);
+              if (vec4) {
+                for (int i = 0; i < a.dh; i += 4) {
+                  const float4 pv = __ldg(reinterpret_cast<const float4*>(pe + k * a.dh + i));
+                  const float* gq = s_go + (k * a.dh + i) * kPT + p;
+                  s = fmaf(gq[0], pv.x, s), s = fmaf(gq[kPT], pv.y, s);
+                  s = fmaf(gq[2 * kPT], pv.z, s), s = fmaf(gq[3 * kPT], pv.w, s);
+                }
+              } else {
+                for (int i = 0; i < a.dh; ++i) s = fmaf(s_go[(k * a.dh + i) * kPT + p], __ldg(pe + k * a.dh + i), s);
+              }
               acc[k] += s;
             }
           }
         }
         const bool rd = (s_flag[t] & 2) != 0;
         const T* xt = xb + static_cast<size_t>(t) * frame_stride + p;
-#pragma unroll 8
-        for (int c = 0; c < a.C; ++c) {
-          const int g = c / a.cpg;
-          const float xv = rd ? Elem<T>::load(xt + static_cast<size_t>(c) * a.hw) : 0.f;
-          const float xn = fmaf(xv, s_rstd[g * kPT + p], -s_mu[g * kPT + p]) * __ldg(a.gamma + c);
-          const float4* gp = reinterpret_cast<const float4*>(s_gzn + (c * kPT + p) * kHP);
+        for (int g = 0, c = 0; g < a.n_head; ++g) {
+          const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
+#pragma unroll 4
+          for (int cc = 0; cc < a.cpg; ++cc, ++c) {
+            const float xv = rd ? Elem<T>::load(xt + static_cast<size_t>(c) * a.hw) : 0.f;
+            const float xn = fmaf(xv, r, -m) * __ldg(a.gamma + c);
+            const float4* gp = reinterpret_cast<const float4*>(s_gzn + (c * kPT + p) * kHP);
 #pragma unroll
-          for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
-            const float4 w = gp[k4];
-            acc[4 * k4] = fmaf(w.x, xn, acc[4 * k4]);
-            acc[4 * k4 + 1] = fmaf(w.y, xn, acc[4 * k4 + 1]);
-            acc[4 * k4 + 2] = fmaf(w.z, xn, acc[4 * k4 + 2]);
-            acc[4 * k4 + 3] = fmaf(w.w, xn, acc[4 * k4 + 3]);
+            for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
+              const float4 w = gp[k4];
+              acc[4 * k4] = fmaf(w.x, xn, acc[4 * k4]);
+              acc[4 * k4 + 1] = fmaf(w.y, xn, acc[4 * k4 + 1]);
+              acc[4 * k4 + 2] = fmaf(w.z, xn, acc[4 * k4 + 2]);
+              acc[4 * k4 + 3] = fmaf(w.w, xn, acc[4 * k4 + 3]);
+            }
           }
         }
       }
@@ -327,16 +364,19 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
     float* ac = s_sc + p * kHP + hh;
     float* gc = s_ga + p * kHP + hh;
     const int stride = kPT * kHP;
-    float dot = 0.f, sa = 0.f;
+    float dot = 0.f, sa = 0.f, sgs = 0.f;
     for (int t = 0; t < a.T; ++t) dot = fmaf(ac[t * stride], gc[t * stride], dot);
     for (int t = 0; t < a.T; ++t) {
       const float av = ac[t * stride];
-      gc[t * stride] = av * (gc[t * stride] - dot);
+      const float gsv = av * (gc[t * stride] - dot);
+      gc[t * stride] = gsv;
+      sgs += gsv;
       const float at = (hh < a.n_head && p < n_pix) ? av * keepf(hh, t, p) : 0.f;
       ac[t * stride] = at;
       sa += at;
     }
     s_sa[p * kHP + hh] = sa;
+    s_gsa[p * kHP + hh] = sgs;  // g_sa is dead after phase 5: the slot now holds sum_t gs (zero up to rounding)
     if (a.sa_rows != nullptr && p < n_pix) a.sa_rows[(row0 + p) * kMaxHeads + hh] = sa;
   }
   __syncthreads();
@@ -391,6 +431,17 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
         }
       }
     }
+    // GroupNorm-backward means without forming g_xh:  sum_t g_xh[t,c] = U[c,:] . sum_t gs + gamma_c gzn[c,:] . sa  and
+    // sum_t g_xh[t,c] xh[t,c] = U[c,:] . au + gamma_c gzn[c,:] . az  (au, az are this pixel's sums, not yet reduced)
+    float q1 = 0.f, q2 = 0.f;
+    if (p < n_pix) {
+#pragma unroll
+      for (int k = 0; k < kMaxHeads; ++k) {
+        const float uk = s_u[c * kMaxHeads + k];
+        q1 = fmaf(uk, s_gsa[p * kHP + k], q1);
+        q2 = fmaf(uk, au[k], q2);
+      }
+    }
     float gg = 0.f, gb = 0.f;
     if (!a.attn_only && p < n_pix) {
       const float gm = __ldg(a.gamma + c), bt = __ldg(a.beta + c);
@@ -403,6 +454,12 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
           a.zn_rows[((row0 + p) * a.n_head + k) * a.C + c] = fmaf(gm, az[k], bt * sa);
         }
       }
+      q1 = fmaf(gm, gb, q1);
+      q2 = fmaf(gm, gg, q2);
+    }
+    if (p < n_pix) {
+      atomicAdd(s_m1 + g * kPT + p, q1);
+      atomicAdd(s_m2 + g * kPT + p, q2);
     }
     // the 8 lanes of a channel: sum over the pixels, one atomic per (channel, head)
 #pragma unroll
@@ -425,71 +482,58 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
 
   // ---- phase 8: g_xh[t,c] = sum_h gs[h,t] U[h,c] + gamma_c sum_h at[h,t] gzn[h,c]; GroupNorm backward over (T, c in g):
   //               grad_x = rstd (g_xh - mean(g_xh) - xh mean(g_xh xh)) --------------------------------------------
-  auto gxh = [&](int t, int c, int p) -> float {
-    const float4* gp = reinterpret_cast<const float4*>(s_ga + (t * kPT + p) * kHP);
-    const float4* up = reinterpret_cast<const float4*>(s_u + c * kMaxHeads);
-    float s = 0.f;
-#pragma unroll
-    for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
-      const float4 w = gp[k4], uu = up[k4];
-      s = fmaf(w.x, uu.x, s), s = fmaf(w.y, uu.y, s), s = fmaf(w.z, uu.z, s), s = fmaf(w.w, uu.w, s);
-    }
-    if (!a.attn_only) {
-      const float4* ap = reinterpret_cast<const float4*>(s_sc + (t * kPT + p) * kHP);
-      const float4* zp = reinterpret_cast<const float4*>(s_gzn + (c * kPT + p) * kHP);
-      float z = 0.f;
-#pragma unroll
-      for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
-        const float4 w = ap[k4], zz = zp[k4];
-        z = fmaf(w.x, zz.x, z), z = fmaf(w.y, zz.y, z), z = fmaf(w.z, zz.z, z), z = fmaf(w.w, zz.w, z);
-      }
-      s = fmaf(__ldg(a.gamma + c), z, s);
-    }
-    return s;
-  };
-  // g_xh is formed once: the first sweep parks it in grad_x (in the features' dtype; for bf16 that costs one extra
-  // rounding of the same size as the final one), the second sweep corrects it in place
-  T* gx = static_cast<T*>(a.g_x) + static_cast<size_t>(b) * a.T * frame_stride + pix0;
-  {
-    const int p = lane % kPT, sub = lane / kPT;
-    constexpr int kSub = 32 / kPT;
-    const float n_all = static_cast<float>(a.T) * a.cpg;
-    const int n_el = a.T * a.cpg;
-    for (int g = warp; g < a.n_head; g += kBwdThreads / 32) {
-      float s1 = 0.f, s2 = 0.f;
-      if (p < n_pix) {
-        const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
-#pragma unroll 4
-        for (int e = sub; e < n_el; e += kSub) {
-          const int t = e / a.cpg, c = g * a.cpg + (e - t * a.cpg);
-          T* dst = gx + static_cast<size_t>(t) * frame_stride + static_cast<size_t>(c) * a.hw + p;
-          Elem<T>::store(dst, gxh(t, c, p));
-          const float gv = Elem<T>::load(dst);  // the value the second sweep will see
-          s1 += gv;
-          s2 = fmaf(gv, fmaf(xval(t, c, p), r, -m), s2);
-        }
-      }
-#pragma unroll
-      for (int o = kPT; o < 32; o <<= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-      }
-      if (sub == 0) s_m1[g * kPT + p] = s1 / n_all, s_m2[g * kPT + p] = s2 / n_all;
-    }
-  }
+  // One thread = one (frame, pixel): the gs / at rows stay in registers while it walks over the channels.  The two group
+  // means come from phase 7, so g_xh is formed, corrected and stored in one sweep; x is loaded four channels ahead.
+  T* __restrict__ gx = static_cast<T*>(a.g_x) + static_cast<size_t>(b) * a.T * frame_stride + pix0;
   __syncthreads();
   {
-    const int n_el = a.T * a.C * kPT;
-#pragma unroll 4
-    for (int item = tid; item < n_el; item += kBwdThreads) {
-      const int p = item % kPT, tc = item / kPT;
-      const int t = tc / a.C, c = tc - t * a.C;
+    const float inv_n = 1.f / (static_cast<float>(a.T) * a.cpg);
+    for (int item = tid; item < a.T * kPT; item += kBwdThreads) {
+      const int t = item / kPT, p = item - t * kPT;
       if (p >= n_pix) continue;
-      const int g = c / a.cpg;
-      const float r = s_rstd[g * kPT + p];
-      const float xn = fmaf(xval(t, c, p), r, -s_mu[g * kPT + p]);
-      T* dst = gx + static_cast<size_t>(t) * frame_stride + static_cast<size_t>(c) * a.hw + p;
-      Elem<T>::store(dst, r * (Elem<T>::load(dst) - s_m1[g * kPT + p] - xn * s_m2[g * kPT + p]));
+      float4 gs[kMaxHeads / 4], at[kMaxHeads / 4];
+#pragma unroll
+      for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
+        gs[k4] = reinterpret_cast<const float4*>(s_ga + (t * kPT + p) * kHP)[k4];
+        at[k4] = reinterpret_cast<const float4*>(s_sc + (t * kPT + p) * kHP)[k4];
+      }
+      const bool rd = (s_flag[t] & 2) != 0;
+      const T* __restrict__ xt = xb + static_cast<size_t>(t) * frame_stride + p;
+      T* __restrict__ gt = gx + static_cast<size_t>(t) * frame_stride + p;
+      for (int g = 0, c0 = 0; g < a.n_head; ++g, c0 += a.cpg) {
+        const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
+        const float m1 = s_m1[g * kPT + p] * inv_n, m2 = s_m2[g * kPT + p] * inv_n;
+        for (int cb = 0; cb < a.cpg; cb += 4) {
+          const int nb = min(4, a.cpg - cb);
+          float xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            xv[u] = (rd && u < nb) ? Elem<T>::load(xt + static_cast<size_t>(c0 + cb + u) * a.hw) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (u >= nb) break;
+            const int c = c0 + cb + u;
+            const float4* up = reinterpret_cast<const float4*>(s_u + c * kMaxHeads);
+            float v = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
+              const float4 uu = up[k4];
+              v = fmaf(gs[k4].x, uu.x, v), v = fmaf(gs[k4].y, uu.y, v), v = fmaf(gs[k4].z, uu.z, v), v = fmaf(gs[k4].w, uu.w, v);
+            }
+            if (!a.attn_only) {
+              const float4* zp = reinterpret_cast<const float4*>(s_gzn + (c * kPT + p) * kHP);
+              float z = 0.f;
+#pragma unroll
+              for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
+                const float4 zz = zp[k4];
+                z = fmaf(at[k4].x, zz.x, z), z = fmaf(at[k4].y, zz.y, z), z = fmaf(at[k4].z, zz.z, z), z = fmaf(at[k4].w, zz.w, z);
+              }
+              v = fmaf(__ldg(a.gamma + c), z, v);
+            }
+            Elem<T>::store(gt + static_cast<size_t>(c) * a.hw, r * (v - m1 - fmaf(xv[u], r, -m) * m2));
+          }
+        }
+      }
     }
   }
 }
