@@ -60,7 +60,7 @@ struct BwdArgs {
 };
 
 struct BwdSmem {
-  int mu, rstd, u, sc, ga, gzn, go, gsa, sa, m1, m2, frames, total;  // offsets in floats
+  int mu, rstd, u, sc, ga, gzn, go, gsa, sa, m1, m2, red, frames, total;  // offsets in floats
 };
 
 __host__ __device__ inline BwdSmem bwd_smem(int T, int C, int D, bool attn_only) {
@@ -82,9 +82,37 @@ __host__ __device__ inline BwdSmem bwd_smem(int T, int C, int D, bool attn_only)
   s.sa = take(kPT * kHP);
   s.m1 = take(kMaxHeads * kPT);
   s.m2 = take(kMaxHeads * kPT);
+  s.red = take(2 * kBwdThreads);
   s.frames = take((T + 3) / 4 + 4);  // uint8[T]: bit 0 = padded, bit 1 = read from memory
   s.total = off;
   return s;
+}
+
+constexpr int kSoftSplit = kBwdThreads / (kPT * kMaxHeads);  // frame slices per (pixel, head) column in the softmax passes
+constexpr int kBatch = 8;                                     // channels per batch of stream_channels
+
+// Walks over the channels of one (frame, pixel) column, group by group, in batches of up to kBatch channels of one group.
+// The loads of the next batch are issued before the current one is handed to ``body(g, c0, n, values)``, so the L2
+// latency of the 2-byte column reads overlaps the arithmetic instead of stalling it.
+template <typename T, typename Body>
+__device__ __forceinline__ void stream_channels(const T* __restrict__ xt, bool rd, int hw, int n_head, int cpg, Body&& body) {
+  float cur[kBatch], nxt[kBatch];
+  auto fetch = [&](float* dst, int g, int cb) {
+    const int c0 = g * cpg + cb, n = min(kBatch, cpg - cb);
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) dst[u] = (rd && u < n) ? Elem<T>::load(xt + static_cast<size_t>(c0 + u) * hw) : 0.f;
+  };
+  int g = 0, cb = 0;
+  fetch(cur, 0, 0);
+  while (g < n_head) {
+    int g2 = g, cb2 = cb + kBatch;
+    if (cb2 >= cpg) cb2 = 0, ++g2;
+    if (g2 < n_head) fetch(nxt, g2, cb2);
+    body(g, g * cpg + cb, min(kBatch, cpg - cb), cur);
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) cur[u] = nxt[u];
+    g = g2, cb = cb2;
+  }
 }
 
 template <typename T>
@@ -102,6 +130,7 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
   float* s_sa = smem + L.sa;      // [p][kHP]
   float* s_m1 = smem + L.m1;      // [g][p]
   float* s_m2 = smem + L.m2;
+  float* s_red = smem + L.red;    // [2][kSoftSplit][p][h] partial results of the softmax passes
   uint8_t* s_flag = reinterpret_cast<uint8_t*>(smem + L.frames);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -211,13 +240,13 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
       }
       const bool rd = (s_flag[t] & 2) != 0;  // hoisted: the loads of the unrolled loop go out back to back
       const T* xt = xb + static_cast<size_t>(t) * frame_stride + p;
-      for (int g = 0, c = 0; g < a.n_head; ++g) {
+      stream_channels(xt, rd, a.hw, a.n_head, a.cpg, [&](int g, int c0, int n, const float* xv) {
         const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
-#pragma unroll 4
-        for (int cc = 0; cc < a.cpg; ++cc, ++c) {
-          const float xv = rd ? Elem<T>::load(xt + static_cast<size_t>(c) * a.hw) : 0.f;
-          const float xn = fmaf(xv, r, -m);
-          const float4* up = reinterpret_cast<const float4*>(s_u + c * kMaxHeads);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          if (u >= n) break;
+          const float xn = fmaf(xv[u], r, -m);
+          const float4* up = reinterpret_cast<const float4*>(s_u + (c0 + u) * kMaxHeads);
 #pragma unroll
           for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
             const float4 w = up[k4];
@@ -227,7 +256,7 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
             acc[4 * k4 + 3] = fmaf(w.w, xn, acc[4 * k4 + 3]);
           }
         }
-      }
+      });
     }
     float4* sp = reinterpret_cast<float4*>(s_sc + (t * kPT + p) * kHP);
 #pragma unroll
@@ -236,24 +265,39 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
   }
   __syncthreads();
 
-  // ---- phase 3: softmax over T (tae.py:836): s_sc = a (before dropout) ------------------------------------------
-  for (int item = tid; item < kPT * kMaxHeads; item += kBwdThreads) {
-    const int p = item / kMaxHeads, hh = item - p * kMaxHeads;
-    float* col = s_sc + p * kHP + hh;
-    const int stride = kPT * kHP;
-    if (hh < a.n_head) {
-      float mx = -INFINITY;
-      for (int t = 0; t < a.T; ++t) mx = fmaxf(mx, col[t * stride]);
-      float den = 0.f;
-      for (int t = 0; t < a.T; ++t) {
-        const float e = expf(col[t * stride] - mx);
-        col[t * stride] = e;
+  // ---- phase 3: softmax over T (tae.py:836): s_sc = a (before dropout).  Every (pixel, head) column is cut into
+  //               kSoftSplit frame slices, one thread each; the slices meet through s_red ------------------------------
+  const int col_id = tid % (kPT * kMaxHeads), slice = tid / (kPT * kMaxHeads);
+  const int t_per = (a.T + kSoftSplit - 1) / kSoftSplit;
+  const int t_lo = min(a.T, slice * t_per), t_hi = min(a.T, t_lo + t_per);
+  const int col_p = col_id / kMaxHeads, col_h = col_id - col_p * kMaxHeads;
+  const int col_stride = kPT * kHP;
+  auto col_sum = [&](const float* part) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < kSoftSplit; ++q) v += part[q * (kPT * kMaxHeads) + col_id];
+    return v;
+  };
+  {
+    float* col = s_sc + col_p * kHP + col_h;
+    float mx = -INFINITY;
+    for (int t = t_lo; t < t_hi; ++t) mx = fmaxf(mx, col[t * col_stride]);
+    s_red[tid] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kSoftSplit; ++q) mx = fmaxf(mx, s_red[q * (kPT * kMaxHeads) + col_id]);
+    float den = 0.f;
+    if (col_h < a.n_head)
+      for (int t = t_lo; t < t_hi; ++t) {
+        const float e = expf(col[t * col_stride] - mx);
+        col[t * col_stride] = e;
         den += e;
       }
-      for (int t = 0; t < a.T; ++t) col[t * stride] = col[t * stride] / den;
-    } else {
-      for (int t = 0; t < a.T; ++t) col[t * stride] = 0.f;
-    }
+    s_red[kBwdThreads + tid] = den;
+    __syncthreads();
+    den = col_sum(s_red + kBwdThreads);
+    const float inv = 1.f / den;
+    for (int t = t_lo; t < t_hi; ++t) col[t * col_stride] = col_h < a.n_head ? col[t * col_stride] * inv : 0.f;
   }
 
   // ---- phase 4: gzn[h,c] = sum_{d in head h} Wc[d,c] grad_o[d]; g_sa[h] = bc . grad_o + beta . gzn -------------
@@ -330,12 +374,13 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
         }
         const bool rd = (s_flag[t] & 2) != 0;
         const T* xt = xb + static_cast<size_t>(t) * frame_stride + p;
-        for (int g = 0, c = 0; g < a.n_head; ++g) {
+        stream_channels(xt, rd, a.hw, a.n_head, a.cpg, [&](int g, int c0, int n, const float* xv) {
           const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
-#pragma unroll 4
-          for (int cc = 0; cc < a.cpg; ++cc, ++c) {
-            const float xv = rd ? Elem<T>::load(xt + static_cast<size_t>(c) * a.hw) : 0.f;
-            const float xn = fmaf(xv, r, -m) * __ldg(a.gamma + c);
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            if (u >= n) break;
+            const int c = c0 + u;
+            const float xn = fmaf(xv[u], r, -m) * __ldg(a.gamma + c);
             const float4* gp = reinterpret_cast<const float4*>(s_gzn + (c * kPT + p) * kHP);
 #pragma unroll
             for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
@@ -346,7 +391,7 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
               acc[4 * k4 + 3] = fmaf(w.w, xn, acc[4 * k4 + 3]);
             }
           }
-        }
+        });
       }
 #pragma unroll
       for (int k = 0; k < kMaxHeads; ++k) acc[k] = k < a.n_head ? acc[k] * keepf(k, t, p) : 0.f;
@@ -359,25 +404,35 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
   __syncthreads();
 
   // ---- phase 6: softmax backward gs = a (g_a - sum_t a g_a); s_sc becomes at = a * keep * scale; sa = sum_t at ----
-  for (int item = tid; item < kPT * kMaxHeads; item += kBwdThreads) {
-    const int p = item / kMaxHeads, hh = item - p * kMaxHeads;
-    float* ac = s_sc + p * kHP + hh;
-    float* gc = s_ga + p * kHP + hh;
-    const int stride = kPT * kHP;
-    float dot = 0.f, sa = 0.f, sgs = 0.f;
-    for (int t = 0; t < a.T; ++t) dot = fmaf(ac[t * stride], gc[t * stride], dot);
-    for (int t = 0; t < a.T; ++t) {
-      const float av = ac[t * stride];
-      const float gsv = av * (gc[t * stride] - dot);
-      gc[t * stride] = gsv;
+  {
+    float* ac = s_sc + col_p * kHP + col_h;
+    float* gc = s_ga + col_p * kHP + col_h;
+    float dot = 0.f;
+    for (int t = t_lo; t < t_hi; ++t) dot = fmaf(ac[t * col_stride], gc[t * col_stride], dot);
+    s_red[tid] = dot;
+    __syncthreads();
+    dot = col_sum(s_red);
+    float sa = 0.f, sgs = 0.f;
+    const bool live = col_h < a.n_head && col_p < n_pix;
+    for (int t = t_lo; t < t_hi; ++t) {
+      const float av = ac[t * col_stride];
+      const float gsv = av * (gc[t * col_stride] - dot);
+      gc[t * col_stride] = gsv;
       sgs += gsv;
-      const float at = (hh < a.n_head && p < n_pix) ? av * keepf(hh, t, p) : 0.f;
-      ac[t * stride] = at;
+      const float at = live ? av * keepf(col_h, t, col_p) : 0.f;
+      ac[t * col_stride] = at;
       sa += at;
     }
-    s_sa[p * kHP + hh] = sa;
-    s_gsa[p * kHP + hh] = sgs;  // g_sa is dead after phase 5: the slot now holds sum_t gs (zero up to rounding)
-    if (a.sa_rows != nullptr && p < n_pix) a.sa_rows[(row0 + p) * kMaxHeads + hh] = sa;
+    __syncthreads();  // every thread has read the dot partials
+    s_red[tid] = sa;
+    s_red[kBwdThreads + tid] = sgs;
+    __syncthreads();
+    if (slice == 0) {
+      sa = col_sum(s_red);
+      s_sa[col_p * kHP + col_h] = sa;
+      s_gsa[col_p * kHP + col_h] = col_sum(s_red + kBwdThreads);  // g_sa is dead after phase 5: now sum_t gs (zero up to rounding)
+      if (a.sa_rows != nullptr && col_p < n_pix) a.sa_rows[(row0 + col_p) * kMaxHeads + col_h] = sa;
+    }
   }
   __syncthreads();
   for (int item = tid; item < a.T * kMaxHeads; item += kBwdThreads) {  // grad_cpos[b,t,h] += sum_p gs
@@ -408,10 +463,21 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
     if (p < n_pix) {
       const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
       const T* xc = xb + static_cast<size_t>(c) * a.hw + p;
-#pragma unroll 4
-      for (int t = 0; t < a.T; ++t) {
-        const float xv = (s_flag[t] & 2) ? Elem<T>::load(xc + static_cast<size_t>(t) * frame_stride) : 0.f;
-        const float xn = fmaf(xv, r, -m);
+      constexpr int kF = 4;  // frames per batch; the next batch's loads are in flight while this one is consumed
+      float cur[kF], nxt[kF];
+      auto fetch = [&](float* dst, int t0) {
+#pragma unroll
+        for (int u = 0; u < kF; ++u)
+          dst[u] = (t0 + u < a.T && (s_flag[t0 + u] & 2)) ? Elem<T>::load(xc + static_cast<size_t>(t0 + u) * frame_stride) : 0.f;
+      };
+      fetch(cur, 0);
+      for (int t0 = 0; t0 < a.T; t0 += kF) {
+        if (t0 + kF < a.T) fetch(nxt, t0 + kF);
+#pragma unroll
+        for (int u = 0; u < kF; ++u) {
+        const int t = t0 + u;
+        if (t >= a.T) break;
+        const float xn = fmaf(cur[u], r, -m);
         const float4* gp = reinterpret_cast<const float4*>(s_ga + (t * kPT + p) * kHP);
         const float4* ap = reinterpret_cast<const float4*>(s_sc + (t * kPT + p) * kHP);
 #pragma unroll
@@ -429,6 +495,9 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
             az[4 * k4 + 3] = fmaf(v.w, xn, az[4 * k4 + 3]);
           }
         }
+        }
+#pragma unroll
+        for (int u = 0; u < kF; ++u) cur[u] = nxt[u];
       }
     }
     // GroupNorm-backward means without forming g_xh:  sum_t g_xh[t,c] = U[c,:] . sum_t gs + gamma_c gzn[c,:] . sa  and
@@ -500,40 +569,33 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
       const bool rd = (s_flag[t] & 2) != 0;
       const T* __restrict__ xt = xb + static_cast<size_t>(t) * frame_stride + p;
       T* __restrict__ gt = gx + static_cast<size_t>(t) * frame_stride + p;
-      for (int g = 0, c0 = 0; g < a.n_head; ++g, c0 += a.cpg) {
+      stream_channels(xt, rd, a.hw, a.n_head, a.cpg, [&](int g, int c0, int n, const float* xv) {
         const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
         const float m1 = s_m1[g * kPT + p] * inv_n, m2 = s_m2[g * kPT + p] * inv_n;
-        for (int cb = 0; cb < a.cpg; cb += 4) {
-          const int nb = min(4, a.cpg - cb);
-          float xv[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            xv[u] = (rd && u < nb) ? Elem<T>::load(xt + static_cast<size_t>(c0 + cb + u) * a.hw) : 0.f;
+        for (int u = 0; u < kBatch; ++u) {
+          if (u >= n) break;
+          const int c = c0 + u;
+          const float4* up = reinterpret_cast<const float4*>(s_u + c * kMaxHeads);
+          float v = 0.f;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (u >= nb) break;
-            const int c = c0 + cb + u;
-            const float4* up = reinterpret_cast<const float4*>(s_u + c * kMaxHeads);
-            float v = 0.f;
+          for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
+            const float4 uu = up[k4];
+            v = fmaf(gs[k4].x, uu.x, v), v = fmaf(gs[k4].y, uu.y, v), v = fmaf(gs[k4].z, uu.z, v), v = fmaf(gs[k4].w, uu.w, v);
+          }
+          if (!a.attn_only) {
+            const float4* zp = reinterpret_cast<const float4*>(s_gzn + (c * kPT + p) * kHP);
+            float z = 0.f;
 #pragma unroll
             for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
-              const float4 uu = up[k4];
-              v = fmaf(gs[k4].x, uu.x, v), v = fmaf(gs[k4].y, uu.y, v), v = fmaf(gs[k4].z, uu.z, v), v = fmaf(gs[k4].w, uu.w, v);
+              const float4 zz = zp[k4];
+              z = fmaf(at[k4].x, zz.x, z), z = fmaf(at[k4].y, zz.y, z), z = fmaf(at[k4].z, zz.z, z), z = fmaf(at[k4].w, zz.w, z);
             }
-            if (!a.attn_only) {
-              const float4* zp = reinterpret_cast<const float4*>(s_gzn + (c * kPT + p) * kHP);
-              float z = 0.f;
-#pragma unroll
-              for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
-                const float4 zz = zp[k4];
-                z = fmaf(at[k4].x, zz.x, z), z = fmaf(at[k4].y, zz.y, z), z = fmaf(at[k4].z, zz.z, z), z = fmaf(at[k4].w, zz.w, z);
-              }
-              v = fmaf(__ldg(a.gamma + c), z, v);
-            }
-            Elem<T>::store(gt + static_cast<size_t>(c) * a.hw, r * (v - m1 - fmaf(xv[u], r, -m) * m2));
+            v = fmaf(__ldg(a.gamma + c), z, v);
           }
+          Elem<T>::store(gt + static_cast<size_t>(c) * a.hw, r * (v - m1 - fmaf(xv[u], r, -m) * m2));
         }
-      }
+      });
     }
   }
 }
