@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 4
+C2S_ABI_VERSION = 5
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -23,6 +23,7 @@ EXPORTS = (
     "c2s_abi_version", "c2s_last_error", "c2s_launch_count", "c2s_reset_launch_count", "c2s_last_kernel",
     "c2s_last_ltae_kernel",
     "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_agg_backward_workspace_bytes", "c2s_agg_backward",
+    "c2s_agg_skipconv_workspace_bytes", "c2s_agg_skipconv_forward",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
     "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward",
 )
@@ -30,6 +31,11 @@ EXPORTS = (
 
 class AggDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "C", "H", "W", "n_heads", "ha", "wa", "mode", "dtype")]
+
+
+class SkipConvParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("conv_weight", "conv_bias", "bn_weight", "bn_bias", "bn_running_mean",
+                                               "bn_running_var")] + [("bn_eps", ctypes.c_float)]
 
 
 class LtaeDesc(ctypes.Structure):
@@ -100,6 +106,11 @@ def load() -> ctypes.CDLL:
         lib.c2s_agg_workspace_bytes.argtypes = [ctypes.POINTER(AggDesc)]
         lib.c2s_agg_forward.restype = i32
         lib.c2s_agg_forward.argtypes = [ctypes.POINTER(AggDesc), vp, vp, vp, vp, vp, sz, vp]
+        lib.c2s_agg_skipconv_workspace_bytes.restype = sz
+        lib.c2s_agg_skipconv_workspace_bytes.argtypes = [ctypes.POINTER(AggDesc)]
+        lib.c2s_agg_skipconv_forward.restype = i32
+        lib.c2s_agg_skipconv_forward.argtypes = [ctypes.POINTER(AggDesc), vp, vp, vp, ctypes.POINTER(SkipConvParams), vp,
+                                                 vp, sz, vp]
         lib.c2s_agg_backward_workspace_bytes.restype = sz
         lib.c2s_agg_backward_workspace_bytes.argtypes = [ctypes.POINTER(AggDesc)]
         lib.c2s_agg_backward.restype = i32

@@ -319,3 +319,23 @@ class TemporalAggregator(nn.Module):
         if self.mode not in ("att_group", "att_mean", "mean"):
             return None  # the reference falls through its if/elif chain and returns None
         return ops.temporal_aggregate(x, pad_mask=pad_mask, attn_mask=attn_mask, mode=self.mode)
+
+    def forward_skip_conv(self, x, pad_mask, attn_mask, skip_conv):
+        """``skip_conv(self(x, pad_mask, attn_mask))`` in one kernel, for the decoder's ``UpConvBlock.skip_conv`` =
+        ``Sequential(Conv2d(d, d, 1), BatchNorm2d(d), ReLU())`` (conv.py:378-382).
+
+        Inference only (``skip_conv`` in eval mode: running statistics); ``att_group``, bf16 features with 64 channels.
+        A maintainer replaces ``self.up_blocks[i](out, skip)`` by the block's own forward with the already-convolved
+        skip (INTEGRATION.md, "Fused skip convolution").
+        """
+        if self.mode != "att_group":
+            raise NotImplementedError("forward_skip_conv: only the att_group mode has a fused kernel")
+        conv, bn = skip_conv[0], skip_conv[1]
+        if not (isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d) and isinstance(skip_conv[2], nn.ReLU)):
+            raise TypeError("forward_skip_conv expects Sequential(Conv2d(d, d, 1), BatchNorm2d(d), ReLU())")
+        if conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.groups != 1:
+            raise NotImplementedError("forward_skip_conv: the skip convolution must be a plain 1x1 convolution")
+        if bn.training or bn.running_mean is None:
+            raise RuntimeError("forward_skip_conv is an inference path: put skip_conv in eval mode (running statistics)")
+        return ops.temporal_aggregate_skip_conv(x, pad_mask, attn_mask, conv.weight, conv.bias, bn.weight, bn.bias,
+                                                bn.running_mean, bn.running_var, bn.eps)

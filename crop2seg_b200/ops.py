@@ -104,6 +104,46 @@ def temporal_aggregate_forward(x: torch.Tensor, pad_mask: Optional[torch.Tensor]
     return out
 
 
+def temporal_aggregate_skip_conv(x: torch.Tensor, pad_mask: Optional[torch.Tensor], attn_mask: torch.Tensor,
+                                 conv_weight: torch.Tensor, conv_bias: Optional[torch.Tensor],
+                                 bn_weight: Optional[torch.Tensor], bn_bias: Optional[torch.Tensor],
+                                 bn_running_mean: torch.Tensor, bn_running_var: torch.Tensor, bn_eps: float = 1e-5
+                                 ) -> torch.Tensor:
+    """``relu(BatchNorm2d_eval(Conv2d_1x1(TemporalAggregator('att_group')(x, pad_mask, attn_mask))))`` in one kernel:
+    the aggregation of utae.py:225-227 followed by ``UpConvBlock.skip_conv`` (conv.py:378-382, 408), the skip map never
+    leaving the chip (``c2s_agg_skipconv_forward``).  Inference only; bf16 x[B,T,64,H,W], 16 heads, x2/x4/x8
+    up-sampling, H*W % 128 == 0 -- other shapes raise (use the two modules separately)."""
+    if x.dim() != 5:
+        raise RuntimeError(f"crop2seg_b200: x must be [B,T,C,H,W], got {tuple(x.shape)}")
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    b, t, c, h, w = x.shape
+    if attn_mask is None or attn_mask.dim() != 5 or attn_mask.shape[1] != b or attn_mask.shape[2] != t:
+        raise RuntimeError(f"crop2seg_b200: attn_mask must be [h,{b},{t},ha,wa]")
+    if tuple(conv_weight.shape[:2]) != (c, c) or conv_weight.numel() != c * c:
+        raise RuntimeError(f"crop2seg_b200: skip convolution must be 1x1 {c}->{c}, got {tuple(conv_weight.shape)}")
+    attn = attn_mask.to(device=x.device, dtype=torch.float32).contiguous()
+    desc = _lib.AggDesc(B=b, T=t, C=c, H=h, W=w, n_heads=attn.shape[0], ha=attn.shape[3], wa=attn.shape[4],
+                        mode=_AGG_MODES["att_group"], dtype=_dtype_code(x, "x"))
+    pad = _mask_u8(pad_mask, b, t, x.device)
+    keep = []
+    params = _lib.SkipConvParams(
+        conv_weight=_f32(conv_weight, x.device, keep), conv_bias=_f32(conv_bias, x.device, keep),
+        bn_weight=_f32(bn_weight, x.device, keep), bn_bias=_f32(bn_bias, x.device, keep),
+        bn_running_mean=_f32(bn_running_mean, x.device, keep), bn_running_var=_f32(bn_running_var, x.device, keep),
+        bn_eps=float(bn_eps))
+    out = torch.empty((b, c, h, w), dtype=x.dtype, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.c2s_agg_skipconv_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        status = lib.c2s_agg_skipconv_forward(ctypes.byref(desc), x.data_ptr(), attn.data_ptr(), _ptr(pad),
+                                              ctypes.byref(params), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                              _stream(x.device))
+    _lib.check(status, "c2s_agg_skipconv_forward")
+    return out
+
+
 def temporal_aggregate_backward(x: torch.Tensor, pad_mask: Optional[torch.Tensor], attn_mask: Optional[torch.Tensor],
                                 grad_out: torch.Tensor, mode: str, need_x: bool = True, need_attn: bool = True
                                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 4
+#define C2S_ABI_VERSION 5
 
 enum c2s_status {
   C2S_OK = 0,
@@ -80,6 +80,26 @@ size_t c2s_agg_workspace_bytes(const c2s_agg_desc* desc);
 int c2s_agg_forward(const c2s_agg_desc* desc, const void* x, const float* attn,
                     const uint8_t* pad_mask, void* out, void* workspace, size_t workspace_bytes,
                     void* stream);
+
+/* TemporalAggregator(att_group) fused with the decoder's skip convolution:
+ *   out[B,C,H,W] = relu( BatchNorm2d_eval( Conv2d_1x1( aggregate(x, attn, pad) ) ) )
+ * = UpConvBlock.skip_conv (conv.py:378-382, applied at conv.py:408) on the skip map of utae.py:225-229, without the
+ * skip map being written to and re-read from HBM.  Inference only (running statistics).  Serves what the shipped
+ * models use: att_group, bfloat16, C = 64, 16 heads, x2/x4/x8 up-sampling, H*W % 128 == 0; anything else returns
+ * C2S_ERR_UNSUPPORTED (run c2s_agg_forward and the convolution separately). */
+typedef struct c2s_skipconv_params {
+  const float* conv_weight;      /* skip_conv.0.weight [C,C,1,1]                               */
+  const float* conv_bias;        /* skip_conv.0.bias   [C] or NULL                             */
+  const float* bn_weight;        /* skip_conv.1.weight [C] or NULL (affine=False)              */
+  const float* bn_bias;          /* skip_conv.1.bias   [C] or NULL                             */
+  const float* bn_running_mean;  /* skip_conv.1.running_mean [C]                               */
+  const float* bn_running_var;   /* skip_conv.1.running_var  [C]                               */
+  float bn_eps;                  /* 1e-5 (nn.BatchNorm2d default)                              */
+} c2s_skipconv_params;
+size_t c2s_agg_skipconv_workspace_bytes(const c2s_agg_desc* desc);
+int c2s_agg_skipconv_forward(const c2s_agg_desc* desc, const void* x, const float* attn, const uint8_t* pad_mask,
+                             const c2s_skipconv_params* params, void* out, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* Backward of TemporalAggregator.forward (what autograd derives from temporal_aggregator.py:14-77):
  *   grad_x[b,t,c]        = resize(attn)[c // (C/n_heads), b, t] * (pad ? 0 : 1) * grad_out[b,c]      (x's dtype)

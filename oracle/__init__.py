@@ -28,3 +28,4 @@ from .aggregator_oracle import (  # noqa: F401
     bilinear_upsample,
     temporal_aggregator,
 )
+from .skipconv_oracle import aggregate_skip_conv, skip_conv  # noqa: F401
