@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <cuda.h>
+
 #include "c2s_common.cuh"
 
 namespace c2s {
@@ -522,8 +524,9 @@ size_t attn_elems(const c2s_agg_desc* d, int heads, int h, int w) {
 //   y[b,o,p] = relu( scale[o] * sum_c W[o,c] * skip[b,c,p] + shift[o] ),   skip = TemporalAggregator(att_group)
 // which is UpConvBlock.skip_conv = Conv2d(d,d,1) -> BatchNorm2d (eval) -> ReLU (conv.py:378-382) applied to the
 // aggregator's output (utae.py:225-229) without the skip map ever visiting HBM.  One CTA = one sample x ALL 64
-// channels x 128 pixels: the producer warp issues 64 bulk copies of 256 bytes per valid frame (one channel row
-// each, 16 KB per stage), the consumers accumulate 4 channels x 8 pixels each exactly like agg_pipe_kernel, then the
+// channels x 128 pixels: the producer issues ONE 3-D tensor-map copy per valid frame (box = 128 pixels x 64 channels
+// x 1 frame, 16 KB per stage; 64 separate 256-byte bulk copies per frame were issue-bound at a third of the HBM
+// rate), the consumers accumulate 4 channels x 8 pixels each exactly like agg_pipe_kernel, then the
 // [64 x 128] skip tile goes to shared memory as bf16 (the value the unfused bf16 path would have stored) and the
 // 1x1 convolution runs as mma.sync m16n8k16 with W split into bf16 hi + lo (two products, fp32 accumulation).
 // ---------------------------------------------------------------------------------------------------
@@ -542,7 +545,19 @@ struct SkipConvArgs {
 };
 
 // W[o][c] fp32 -> mma.sync A fragments (row-major 16x16 tiles), bf16 hi and the bf16 residual
-__global__ void skipconv_wfrag_kernel(const float* __restrict__ w, uint4* __restrict__ frag) {
+// plus (third block) the scale / shift of conv bias + eval BatchNorm
+__global__ void skipconv_prep_kernel(const float* __restrict__ w, uint4* __restrict__ frag, const float* conv_bias,
+                                     const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,
+                                     float eps, float* scale, float* shift) {
+  if (blockIdx.x == 2) {
+    const int o = threadIdx.x;
+    if (o < kScC) {
+      const float sc = (bn_w ? bn_w[o] : 1.f) / sqrtf(bn_var[o] + eps);
+      scale[o] = sc;
+      shift[o] = ((conv_bias ? conv_bias[o] : 0.f) - bn_mean[o]) * sc + (bn_b ? bn_b[o] : 0.f);
+    }
+    return;
+  }
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (mt, ks, lane)
   if (idx >= 4 * 4 * 32) return;
   const int lane = idx & 31, ks = (idx >> 5) & 3, mt = idx >> 7;
@@ -560,18 +575,16 @@ __global__ void skipconv_wfrag_kernel(const float* __restrict__ w, uint4* __rest
   frag[4 * 4 * 32 + idx] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// scale/shift of conv bias + eval BatchNorm
-__global__ void skipconv_affine_kernel(const float* conv_bias, const float* bn_w, const float* bn_b, const float* bn_mean,
-                                       const float* bn_var, float eps, float* scale, float* shift) {
-  const int o = threadIdx.x;
-  if (o >= kScC) return;
-  const float sc = (bn_w ? bn_w[o] : 1.f) / sqrtf(bn_var[o] + eps);
-  scale[o] = sc;
-  shift[o] = ((conv_bias ? conv_bias[o] : 0.f) - bn_mean[o]) * sc + (bn_b ? bn_b[o] : 0.f);
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
 template <int S>
-__global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(const SkipConvArgs k) {
+__global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                             const SkipConvArgs k) {
   using T = __nv_bfloat16;
   constexpr int VEC = 8;
   constexpr int NCOL = Window<VEC, S>::kCols;
@@ -606,22 +619,16 @@ __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(cons
   }
   __syncthreads();
   const int n_frames = n_frames_s;
-  const size_t frame_stride = static_cast<size_t>(a.C) * a.hw;
   const uint32_t stage0 = smem_addr(pipe_smem);
 
-  if (warp == n_cwarps) {  // ---- producer warp: 64 channel rows of 256 bytes per frame, two per lane -------------------
-    const T* src = static_cast<const T*>(a.x) + static_cast<size_t>(b) * a.T * frame_stride + static_cast<size_t>(pblk) * kScPB;
-    for (int i = 0; i < n_frames; ++i) {
-      const int s = i % n_stages, round = i / n_stages;
-      if (round > 0) mbar_wait(smem_addr(&bars[16 + s]), (round - 1) & 1);
-      const uint32_t full = smem_addr(&bars[s]);
-      if (lane == 0) mbar_expect_tx(full, kScStageBytes);
-      __syncwarp();
-      const T* fp = src + static_cast<size_t>(frames[i]) * frame_stride;
-#pragma unroll
-      for (int r = 0; r < kScC / 32; ++r) {
-        const int c = lane + 32 * r;
-        bulk_g2s(stage0 + s * kScStageBytes + c * (kScPB * 2), fp + static_cast<size_t>(c) * a.hw, kScPB * 2, full);
+  if (warp == n_cwarps) {  // ---- producer: one box {128 pixels, 64 channels, 1 frame} per valid frame ------------------
+    if (lane == 0) {
+      for (int i = 0; i < n_frames; ++i) {
+        const int s = i % n_stages, round = i / n_stages;
+        if (round > 0) mbar_wait(smem_addr(&bars[16 + s]), (round - 1) & 1);
+        const uint32_t full = smem_addr(&bars[s]);
+        mbar_expect_tx(full, kScStageBytes);
+        tma_load_3d(stage0 + s * kScStageBytes, &map_x, pblk * kScPB, 0, b * a.T + frames[i], full);
       }
     }
     return;
@@ -763,12 +770,27 @@ __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(cons
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn agg_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 template <int S>
-int launch_skipconv(const SkipConvArgs& k, cudaStream_t stream, const char* name) {
+int launch_skipconv(const CUtensorMap& map_x, const SkipConvArgs& k, cudaStream_t stream, const char* name) {
   const size_t smem = static_cast<size_t>(k.n_stages) * kScStageBytes + kScC * kScTileStride;
   C2S_CUDA(cudaFuncSetAttribute(agg_skipconv_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(k.a.hw / kScPB, k.a.B);
-  agg_skipconv_kernel<S><<<grid, kScConsumers + 32, smem, stream>>>(k);
+  agg_skipconv_kernel<S><<<grid, kScConsumers + 32, smem, stream>>>(map_x, k);
   C2S_LAUNCH_CHECK(name);
   return C2S_OK;
 }
@@ -937,17 +959,31 @@ int c2s_agg_skipconv_forward(const c2s_agg_desc* d, const void* x, const float* 
   uint4* wfrag = static_cast<uint4*>(workspace);
   float* scale = reinterpret_cast<float*>(wfrag + 2 * 4 * 4 * 32);
   float* shift = scale + kScC;
-  skipconv_wfrag_kernel<<<2, 256, 0, stream>>>(p->conv_weight, wfrag);
-  C2S_LAUNCH_CHECK("skipconv_wfrag");
-  skipconv_affine_kernel<<<1, kScC, 0, stream>>>(p->conv_bias, p->bn_weight, p->bn_bias, p->bn_running_mean,
-                                                 p->bn_running_var, p->bn_eps, scale, shift);
-  C2S_LAUNCH_CHECK("skipconv_affine");
+  skipconv_prep_kernel<<<3, 256, 0, stream>>>(p->conv_weight, wfrag, p->conv_bias, p->bn_weight, p->bn_bias,
+                                              p->bn_running_mean, p->bn_running_var, p->bn_eps, scale, shift);
+  C2S_LAUNCH_CHECK("skipconv_prep");
   k.wfrag = wfrag, k.scale = scale, k.shift = shift;
   k.n_stages = 4;
+  EncodeTiledFn fn = agg_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return C2S_ERR_CUDA;
+  }
+  CUtensorMap map_x;  // x as [B*T][C][H*W] bf16; box = 128 pixels x 64 channels x 1 frame, dense in shared memory
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(hw), static_cast<cuuint64_t>(kScC), static_cast<cuuint64_t>(d->B) * d->T};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(hw) * 2, static_cast<cuuint64_t>(kScC) * hw * 2};
+  const cuuint32_t box[3] = {kScPB, kScC, 1}, estr[3] = {1, 1, 1};
+  const CUresult r = fn(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (skip features) failed with CUresult %d", static_cast<int>(r));
+    return C2S_ERR_CUDA;
+  }
   switch (scale_class) {
-    case 2: return launch_skipconv<2>(k, stream, "agg_skipconv<x2>");
-    case 4: return launch_skipconv<4>(k, stream, "agg_skipconv<x4>");
-    default: return launch_skipconv<8>(k, stream, "agg_skipconv<x8>");
+    case 2: return launch_skipconv<2>(map_x, k, stream, "agg_skipconv<x2>");
+    case 4: return launch_skipconv<4>(map_x, k, stream, "agg_skipconv<x4>");
+    default: return launch_skipconv<8>(map_x, k, stream, "agg_skipconv<x8>");
   }
 }
 
