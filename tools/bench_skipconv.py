@@ -43,9 +43,10 @@ for c, r in LEVELS:
         t_agg = timeit(lambda: agg(x, pad_mask=pad, attn_mask=attn))
         t_unfused = timeit(lambda: conv_bf16(agg(x, pad_mask=pad, attn_mask=attn)))
         t_fused = timeit(lambda: agg.forward_skip_conv(x, pad, attn, conv))
-        a = agg.forward_skip_conv(x, pad, attn, conv).float(); b_ = conv(agg(x, pad_mask=pad, attn_mask=attn).float())
+        a = agg.forward_skip_conv(x, pad, attn, conv).float(); kname = _lib.last_kernel()
+        b_ = conv(agg(x, pad_mask=pad, attn_mask=attn).float())
     err = float((a - b_).abs().max() / b_.abs().max())
     nbytes = 2 * sum(lengths) * c * r * r + 2 * B * c * r * r + 4 * 16 * sum(lengths) * 256  # x (valid frames) + out + attention
     print(json.dumps({"level": f"{c}x{r}x{r}", "batch": B, "agg_only_ms": round(t_agg, 4), "agg_then_torch_skip_conv_ms": round(t_unfused, 4),
                       "fused_ms": round(t_fused, 4), "fused_gbs": round(nbytes / t_fused / 1e6, 1), "fused_frac_of_hbm_peak": round(nbytes / t_fused / 1e6 / peak, 3),
-                      "rel_err_vs_unfused_fp32_conv": err, "kernel": _lib.last_kernel()}))
+                      "rel_err_vs_unfused_fp32_conv": err, "kernel": kname}))
