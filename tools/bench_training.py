@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the whole step (forward, backward, Adam) in one CUDA graph and replay it (1 GPU)")
     args = ap.parse_args()
     rank, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -67,7 +69,7 @@ def main():
     enc.assume_zero_padded = True
     model = torch.nn.parallel.DistributedDataParallel(enc, device_ids=[local_rank]) if world > 1 else enc
     agg = c2s.TemporalAggregator(mode="att_group")
-    opt = torch.optim.Adam(enc.parameters(), lr=1e-3)  # train.py: Adam, lr 1e-3
+    opt = torch.optim.Adam(enc.parameters(), lr=1e-3, capturable=args.graph)  # train.py: Adam, lr 1e-3
     projs = [torch.randn((B, 128, LTAE_RES, LTAE_RES), device=dev, generator=gen).to(torch.bfloat16)] + \
             [torch.randn((B, c, r, r), device=dev, generator=gen).to(torch.bfloat16) for c, r in LEVELS]
 
@@ -88,6 +90,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    launches_per_step = None
+    if args.graph:
+        if world > 1:
+            raise SystemExit("--graph is a single-GPU option (DDP's bucket hooks are not captured here)")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # torch's capture recipe: warm up on a side stream first
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        _lib.reset_launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = step()
+        launches_per_step = _lib.launch_count()
+        eager_step = step
+
+        def step():  # noqa: F811
+            graph.replay()
+            return static_loss
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -98,7 +122,7 @@ def main():
         loss = step()
     e.record()
     barrier()
-    launches = _lib.launch_count()
+    launches = _lib.launch_count() if launches_per_step is None else launches_per_step * args.steps
     t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -116,7 +140,8 @@ def main():
             "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "scaling": "weak", "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "BASELINE configs[3] hot path: LTAE(train) + 3x TemporalAggregator forward+backward, "
-                                   "Adam step, DDP gradient all-reduce", "batch_per_gpu": B,
+                                   "Adam step, DDP gradient all-reduce" + (", whole step replayed as one CUDA graph" if args.graph else ""),
+                       "batch_per_gpu": B,
                        "mean_valid_frames": float(np.mean(lengths))},
             "roofline": {"bound": "hbm", "algorithmic_bytes": fwd + bwd, "achieved": (fwd + bwd) / (ms * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": (fwd + bwd) / (ms * 1e-3) / 1e9 / peak},
