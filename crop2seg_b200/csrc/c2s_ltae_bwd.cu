@@ -452,99 +452,118 @@ __global__ void __launch_bounds__(kBwdThreads) ltae_backward_kernel(const BwdArg
 
   // ---- phase 7: per (c, p): grad_U[c,h] += sum_t gs[h,t] xh[t,c];  zr[h,c] = sum_t at[h,t] xh[t,c] -> zn rows,
   //               direct gamma / beta terms ---------------------------------------------------------------------
-  for (int it0 = 0; it0 < a.C * kPT; it0 += kBwdThreads) {  // uniform trip count: every lane joins the shuffles
+  // One thread = one pixel x TWO channels (c and c + C/2): every gs / at row read from shared memory feeds 64 FMAs.
+  const int c_half = (a.C + 1) >> 1;
+  for (int it0 = 0; it0 < c_half * kPT; it0 += kBwdThreads) {  // uniform trip count: every lane joins the shuffles
     const int item = it0 + tid;
-    const bool valid = item < a.C * kPT;
-    const int c = valid ? item / kPT : 0, p = valid ? item - c * kPT : kPT;
-    const int g = c / a.cpg;
-    float au[kMaxHeads], az[kMaxHeads];
+    const bool valid = item < c_half * kPT;
+    const int cA = valid ? item / kPT : 0, p = valid ? item - cA * kPT : kPT;
+    const int cc[2] = {cA, cA + c_half};
+    const bool on[2] = {p < n_pix, p < n_pix && cc[1] < a.C};
+    const int gq[2] = {cc[0] / a.cpg, on[1] ? cc[1] / a.cpg : 0};
+    float au[2][kMaxHeads], az[2][kMaxHeads];
 #pragma unroll
-    for (int k = 0; k < kMaxHeads; ++k) au[k] = 0.f, az[k] = 0.f;
-    if (p < n_pix) {
-      const float r = s_rstd[g * kPT + p], m = s_mu[g * kPT + p];
-      const T* xc = xb + static_cast<size_t>(c) * a.hw + p;
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int k = 0; k < kMaxHeads; ++k) au[j][k] = 0.f, az[j][k] = 0.f;
+    if (on[0]) {
+      float r[2], m[2];
+      const T* xc[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        r[j] = s_rstd[gq[j] * kPT + p], m[j] = s_mu[gq[j] * kPT + p];
+        xc[j] = xb + static_cast<size_t>(on[j] ? cc[j] : cc[0]) * a.hw + p;
+      }
       constexpr int kF = 4;  // frames per batch; the next batch's loads are in flight while this one is consumed
-      float cur[kF], nxt[kF];
-      auto fetch = [&](float* dst, int t0) {
+      float cur[2][kF], nxt[2][kF];
+      auto fetch = [&](float (*dst)[kF], int t0) {
 #pragma unroll
-        for (int u = 0; u < kF; ++u)
-          dst[u] = (t0 + u < a.T && (s_flag[t0 + u] & 2)) ? Elem<T>::load(xc + static_cast<size_t>(t0 + u) * frame_stride) : 0.f;
+        for (int u = 0; u < kF; ++u) {
+          const bool rd = t0 + u < a.T && (s_flag[t0 + u] & 2);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            dst[j][u] = (rd && on[j]) ? Elem<T>::load(xc[j] + static_cast<size_t>(t0 + u) * frame_stride) : 0.f;
+        }
       };
       fetch(cur, 0);
       for (int t0 = 0; t0 < a.T; t0 += kF) {
         if (t0 + kF < a.T) fetch(nxt, t0 + kF);
 #pragma unroll
         for (int u = 0; u < kF; ++u) {
-        const int t = t0 + u;
-        if (t >= a.T) break;
-        const float xn = fmaf(cur[u], r, -m);
-        const float4* gp = reinterpret_cast<const float4*>(s_ga + (t * kPT + p) * kHP);
-        const float4* ap = reinterpret_cast<const float4*>(s_sc + (t * kPT + p) * kHP);
+          const int t = t0 + u;
+          if (t >= a.T) break;
+          const float xn0 = fmaf(cur[0][u], r[0], -m[0]), xn1 = on[1] ? fmaf(cur[1][u], r[1], -m[1]) : 0.f;
+          const float4* gp = reinterpret_cast<const float4*>(s_ga + (t * kPT + p) * kHP);
+          const float4* ap = reinterpret_cast<const float4*>(s_sc + (t * kPT + p) * kHP);
 #pragma unroll
-        for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
-          const float4 w = gp[k4];
-          au[4 * k4] = fmaf(w.x, xn, au[4 * k4]);
-          au[4 * k4 + 1] = fmaf(w.y, xn, au[4 * k4 + 1]);
-          au[4 * k4 + 2] = fmaf(w.z, xn, au[4 * k4 + 2]);
-          au[4 * k4 + 3] = fmaf(w.w, xn, au[4 * k4 + 3]);
-          if (!a.attn_only) {
-            const float4 v = ap[k4];
-            az[4 * k4] = fmaf(v.x, xn, az[4 * k4]);
-            az[4 * k4 + 1] = fmaf(v.y, xn, az[4 * k4 + 1]);
-            az[4 * k4 + 2] = fmaf(v.z, xn, az[4 * k4 + 2]);
-            az[4 * k4 + 3] = fmaf(v.w, xn, az[4 * k4 + 3]);
+          for (int k4 = 0; k4 < kMaxHeads / 4; ++k4) {
+            const float4 w = gp[k4];
+            au[0][4 * k4] = fmaf(w.x, xn0, au[0][4 * k4]), au[1][4 * k4] = fmaf(w.x, xn1, au[1][4 * k4]);
+            au[0][4 * k4 + 1] = fmaf(w.y, xn0, au[0][4 * k4 + 1]), au[1][4 * k4 + 1] = fmaf(w.y, xn1, au[1][4 * k4 + 1]);
+            au[0][4 * k4 + 2] = fmaf(w.z, xn0, au[0][4 * k4 + 2]), au[1][4 * k4 + 2] = fmaf(w.z, xn1, au[1][4 * k4 + 2]);
+            au[0][4 * k4 + 3] = fmaf(w.w, xn0, au[0][4 * k4 + 3]), au[1][4 * k4 + 3] = fmaf(w.w, xn1, au[1][4 * k4 + 3]);
+            if (!a.attn_only) {
+              const float4 v = ap[k4];
+              az[0][4 * k4] = fmaf(v.x, xn0, az[0][4 * k4]), az[1][4 * k4] = fmaf(v.x, xn1, az[1][4 * k4]);
+              az[0][4 * k4 + 1] = fmaf(v.y, xn0, az[0][4 * k4 + 1]), az[1][4 * k4 + 1] = fmaf(v.y, xn1, az[1][4 * k4 + 1]);
+              az[0][4 * k4 + 2] = fmaf(v.z, xn0, az[0][4 * k4 + 2]), az[1][4 * k4 + 2] = fmaf(v.z, xn1, az[1][4 * k4 + 2]);
+              az[0][4 * k4 + 3] = fmaf(v.w, xn0, az[0][4 * k4 + 3]), az[1][4 * k4 + 3] = fmaf(v.w, xn1, az[1][4 * k4 + 3]);
+            }
           }
         }
-        }
 #pragma unroll
-        for (int u = 0; u < kF; ++u) cur[u] = nxt[u];
+        for (int u = 0; u < kF; ++u) cur[0][u] = nxt[0][u], cur[1][u] = nxt[1][u];
       }
     }
-    // GroupNorm-backward means without forming g_xh:  sum_t g_xh[t,c] = U[c,:] . sum_t gs + gamma_c gzn[c,:] . sa  and
-    // sum_t g_xh[t,c] xh[t,c] = U[c,:] . au + gamma_c gzn[c,:] . az  (au, az are this pixel's sums, not yet reduced)
-    float q1 = 0.f, q2 = 0.f;
-    if (p < n_pix) {
 #pragma unroll
-      for (int k = 0; k < kMaxHeads; ++k) {
-        const float uk = s_u[c * kMaxHeads + k];
-        q1 = fmaf(uk, s_gsa[p * kHP + k], q1);
-        q2 = fmaf(uk, au[k], q2);
-      }
-    }
-    float gg = 0.f, gb = 0.f;
-    if (!a.attn_only && p < n_pix) {
-      const float gm = __ldg(a.gamma + c), bt = __ldg(a.beta + c);
+    for (int j = 0; j < 2; ++j) {
+      const int c = cc[j], g = gq[j];
+      // GroupNorm-backward means without forming g_xh:  sum_t g_xh[t,c] = U[c,:] . sum_t gs + gamma_c gzn[c,:] . sa  and
+      // sum_t g_xh[t,c] xh[t,c] = U[c,:] . au + gamma_c gzn[c,:] . az  (au, az are this pixel's sums, not yet reduced)
+      float q1 = 0.f, q2 = 0.f;
+      if (on[j]) {
 #pragma unroll
-      for (int k = 0; k < kMaxHeads; ++k) {
-        if (k < a.n_head) {
-          const float gz = s_gzn[(c * kPT + p) * kHP + k], sa = s_sa[p * kHP + k];
-          gg = fmaf(gz, az[k], gg);
-          gb = fmaf(gz, sa, gb);
-          a.zn_rows[((row0 + p) * a.n_head + k) * a.C + c] = fmaf(gm, az[k], bt * sa);
+        for (int k = 0; k < kMaxHeads; ++k) {
+          const float uk = s_u[c * kMaxHeads + k];
+          q1 = fmaf(uk, s_gsa[p * kHP + k], q1);
+          q2 = fmaf(uk, au[j][k], q2);
         }
       }
-      q1 = fmaf(gm, gb, q1);
-      q2 = fmaf(gm, gg, q2);
-    }
-    if (p < n_pix) {
-      atomicAdd(s_m1 + g * kPT + p, q1);
-      atomicAdd(s_m2 + g * kPT + p, q2);
-    }
-    // the 8 lanes of a channel: sum over the pixels, one atomic per (channel, head)
+      float gg = 0.f, gb = 0.f;
+      if (!a.attn_only && on[j]) {
+        const float gm = __ldg(a.gamma + c), bt = __ldg(a.beta + c);
 #pragma unroll
-    for (int o = 1; o < kPT; o <<= 1) {
-      gg += __shfl_xor_sync(0xffffffffu, gg, o);
-      gb += __shfl_xor_sync(0xffffffffu, gb, o);
+        for (int k = 0; k < kMaxHeads; ++k) {
+          if (k < a.n_head) {
+            const float gz = s_gzn[(c * kPT + p) * kHP + k], sa = s_sa[p * kHP + k];
+            gg = fmaf(gz, az[j][k], gg);
+            gb = fmaf(gz, sa, gb);
+            a.zn_rows[((row0 + p) * a.n_head + k) * a.C + c] = fmaf(gm, az[j][k], bt * sa);
+          }
+        }
+        q1 = fmaf(gm, gb, q1);
+        q2 = fmaf(gm, gg, q2);
+      }
+      if (on[j]) {
+        atomicAdd(s_m1 + g * kPT + p, q1);
+        atomicAdd(s_m2 + g * kPT + p, q2);
+      }
+      // the 8 lanes of a channel: sum over the pixels, one atomic per (channel, head)
 #pragma unroll
-      for (int k = 0; k < kMaxHeads; ++k) au[k] += __shfl_xor_sync(0xffffffffu, au[k], o);
-    }
-    if (valid && p == 0) {
+      for (int o = 1; o < kPT; o <<= 1) {
+        gg += __shfl_xor_sync(0xffffffffu, gg, o);
+        gb += __shfl_xor_sync(0xffffffffu, gb, o);
 #pragma unroll
-      for (int k = 0; k < kMaxHeads; ++k)
-        if (k < a.n_head) atomicAdd(a.g_u + c * kMaxHeads + k, au[k]);
-      if (!a.attn_only) {
-        atomicAdd(a.g_gamma + c, gg);
-        atomicAdd(a.g_beta + c, gb);
+        for (int k = 0; k < kMaxHeads; ++k) au[j][k] += __shfl_xor_sync(0xffffffffu, au[j][k], o);
+      }
+      if (valid && p == 0 && c < a.C) {
+#pragma unroll
+        for (int k = 0; k < kMaxHeads; ++k)
+          if (k < a.n_head) atomicAdd(a.g_u + c * kMaxHeads + k, au[j][k]);
+        if (!a.attn_only) {
+          atomicAdd(a.g_gamma + c, gg);
+          atomicAdd(a.g_beta + c, gb);
+        }
       }
     }
   }
