@@ -16,5 +16,6 @@ from .install import install, uninstall  # noqa: F401
 from .sharding import gather_shards, shard_bounds, shard_patches  # noqa: F401
 from .staging import copy_valid_frames_, valid_lengths  # noqa: F401
 from . import ops  # noqa: F401
+from .ops import pad_mask_from_input  # noqa: F401
 
-__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "ops"]
+__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "pad_mask_from_input", "ops"]

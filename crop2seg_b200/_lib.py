@@ -23,7 +23,7 @@ EXPORTS = (
     "c2s_abi_version", "c2s_last_error", "c2s_launch_count", "c2s_reset_launch_count", "c2s_last_kernel",
     "c2s_last_ltae_kernel",
     "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_agg_backward_workspace_bytes", "c2s_agg_backward",
-    "c2s_agg_skipconv_workspace_bytes", "c2s_agg_skipconv_forward",
+    "c2s_agg_skipconv_workspace_bytes", "c2s_agg_skipconv_forward", "c2s_pad_mask",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
     "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward",
 )
@@ -111,6 +111,8 @@ def load() -> ctypes.CDLL:
         lib.c2s_agg_skipconv_forward.restype = i32
         lib.c2s_agg_skipconv_forward.argtypes = [ctypes.POINTER(AggDesc), vp, vp, vp, ctypes.POINTER(SkipConvParams), vp,
                                                  vp, sz, vp]
+        lib.c2s_pad_mask.restype = i32
+        lib.c2s_pad_mask.argtypes = [vp, i32, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, vp, vp]
         lib.c2s_agg_backward_workspace_bytes.restype = sz
         lib.c2s_agg_backward_workspace_bytes.argtypes = [ctypes.POINTER(AggDesc)]
         lib.c2s_agg_backward.restype = i32

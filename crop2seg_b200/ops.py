@@ -49,6 +49,24 @@ def _mask_u8(pad_mask: Optional[torch.Tensor], b: int, t: int, device) -> Option
     return m.contiguous().view(torch.uint8)
 
 
+def pad_mask_from_input(x: torch.Tensor, pad_value: float = 0.0) -> torch.Tensor:
+    """``(x == pad_value).all(dim=-1).all(dim=-1).all(dim=-1)`` for x[B,T,C,H,W] (utae.py:201-203, wtae.py:221-223,
+    timeunet.py:170-172): bool [B,T].  One kernel; a valid frame is left at its first non-pad value, only padded
+    frames are read to the end (the reference compares and reduces the whole input three times)."""
+    if x.dim() != 5:
+        raise RuntimeError(f"crop2seg_b200: x must be [B,T,C,H,W], got {tuple(x.shape)}")
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    b, t = x.shape[:2]
+    mask = torch.empty((b, t), dtype=torch.uint8, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        status = lib.c2s_pad_mask(x.data_ptr(), _dtype_code(x, "x"), b * t, x[0, 0].numel(), float(pad_value),
+                                  mask.data_ptr(), _stream(x.device))
+    _lib.check(status, "c2s_pad_mask")
+    return mask.view(torch.bool)
+
+
 def temporal_aggregate(x: torch.Tensor, pad_mask: Optional[torch.Tensor] = None,
                        attn_mask: Optional[torch.Tensor] = None, mode: str = "mean") -> torch.Tensor:
     """``TemporalAggregator(mode).forward(x, pad_mask, attn_mask)`` (temporal_aggregator.py:14-77), differentiable

@@ -113,6 +113,12 @@ int c2s_agg_backward(const c2s_agg_desc* desc, const void* x, const float* attn,
                      const void* grad_out, void* grad_x, float* grad_attn, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* pad_mask[b,t] = (input[b,t,:,:,:] == pad_value).all()   utae.py:201-203, wtae.py:221-223, timeunet.py:170-172
+ * (SURVEY.md section 8a row a9).  x: n_frames contiguous frames of frame_elems elements; mask: uint8 [n_frames],
+ * 1 = padded.  A frame is left at the first value that differs, so only padded frames are read to the end. */
+int c2s_pad_mask(const void* x, int32_t dtype, int64_t n_frames, int64_t frame_elems, float pad_value,
+                 uint8_t* mask, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * LTAE / LTAE4WTAE                                             tae.py:349-635
  * ---------------------------------------------------------------------------------------- */

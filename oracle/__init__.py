@@ -26,6 +26,7 @@ from .ltae_oracle import (  # noqa: F401
 from .aggregator_oracle import (  # noqa: F401
     avg_pool2d,
     bilinear_upsample,
+    pad_mask_from_input,
     temporal_aggregator,
 )
 from .skipconv_oracle import aggregate_skip_conv, skip_conv  # noqa: F401

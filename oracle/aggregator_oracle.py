@@ -93,3 +93,9 @@ def temporal_aggregator(x: np.ndarray, pad_mask: Optional[np.ndarray] = None,
             return (s / keep.sum(axis=1, dtype=np.float64)[:, None, None, None]).astype(F32)
         return x.mean(axis=1, dtype=np.float64).astype(F32)  # :77
     raise ValueError(f"unknown aggregation mode {mode!r}")
+
+
+def pad_mask_from_input(x: np.ndarray, pad_value: float = 0.0) -> np.ndarray:
+    """``(input == pad_value).all(dim=-1).all(dim=-1).all(dim=-1)`` -- utae.py:201-203, wtae.py:221-223,
+    timeunet.py:170-172: bool [B,T], True where every element of the frame equals ``pad_value`` (NaN never does)."""
+    return (x == x.dtype.type(pad_value)).all(axis=(-1, -2, -3))

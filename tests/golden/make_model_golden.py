@@ -97,7 +97,8 @@ def main():
            "ltae_kwargs": {"in_channels": 128, "n_head": 16, "d_k": 4, "mlp": [256, 128], "d_model": 256},
            "agg_mode": "att_group"}
     arrays = {"cfg": np.array(json.dumps(cfg)), "enc_x": seen["enc_x"].numpy(), "positions": seen["enc_pos"].numpy(),
-              "pad_mask": seen["enc_pad"].numpy()}
+              "pad_mask": seen["enc_pad"].numpy(),  # what utae.py:201-203 derived from the raw input below
+              "raw_input": x}
     for i, a in enumerate(seen["agg_in"]):
         arrays[f"skip_x{i}"] = a.numpy()
     for k, v in model.temporal_encoder.state_dict().items():
