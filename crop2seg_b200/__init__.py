@@ -14,8 +14,8 @@ The arithmetic lives in ``lib/libcrop2seg_b200.so`` (``include/crop2seg_b200.h``
 from .modules import LTAE, LTAE4WTAE, TemporalAggregator  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from .sharding import gather_shards, shard_bounds, shard_patches  # noqa: F401
-from .staging import copy_valid_frames_, valid_lengths  # noqa: F401
+from .staging import copy_valid_frames_, smart_forward, valid_lengths  # noqa: F401
 from . import ops  # noqa: F401
 from .ops import pad_mask_from_input  # noqa: F401
 
-__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "pad_mask_from_input", "ops"]
+__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "smart_forward", "pad_mask_from_input", "ops"]

@@ -55,3 +55,35 @@ def copy_valid_frames_(dst: torch.Tensor, src: torch.Tensor, lengths: Sequence[i
             dst[b, L:].zero_()
         b += 1
     return copied
+
+
+def smart_forward(forward, x: torch.Tensor, pad_value=None, pad_mask: torch.Tensor = None) -> torch.Tensor:
+    """``TemporallySharedBlock.smart_forward`` (temp_shared_block.py:18-47) without its waste: apply ``forward`` (a block
+    shared across the sequence, [N, C, H, W] -> [N, C', H', W']) to the non-padded frames of x[B, T, C, H, W] and
+    return [B, T, C', H', W'] with ``pad_value`` on the padded frames.
+
+    Differences from the reference, results being identical: the pad mask comes from the early-exit scan kernel
+    (``pad_mask_from_input``) or from the caller (``pad_mask`` [B, T], e.g. the one the model already derived from the
+    raw input: padded frames stay exactly ``pad_value`` through the encoder, temp_shared_block.py:30-40) instead of
+    comparing the whole tensor again; the output shape is taken from the real forward instead of an extra forward of
+    an all-zero dummy batch; the valid frames are gathered once by index."""
+    if x.dim() == 4:
+        return forward(x)
+    b, t, c, h, w = x.shape
+    flat = x.contiguous().view(b * t, c, h, w)
+    if pad_value is None:
+        out = forward(flat)
+        return out.view(b, t, *out.shape[1:])
+    if pad_mask is None:
+        from .ops import pad_mask_from_input
+        pad_mask = pad_mask_from_input(x, pad_value)
+    valid = (~pad_mask.reshape(-1)).nonzero(as_tuple=True)[0]  # the one host synchronisation (the reference has two)
+    if valid.numel() == b * t:
+        out = forward(flat)
+        return out.view(b, t, *out.shape[1:])
+    if valid.numel() == 0:
+        raise RuntimeError("smart_forward: every frame is padded (the reference fails on the empty batch too)")
+    part = forward(flat.index_select(0, valid))
+    out = torch.full((b * t, *part.shape[1:]), float(pad_value), dtype=part.dtype, device=part.device)
+    out.index_copy_(0, valid, part)
+    return out.view(b, t, *out.shape[1:])

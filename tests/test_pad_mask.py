@@ -51,3 +51,26 @@ def test_cuda_matches_oracle(shape, pad_value, dtype):
         flat[1:] = xt.reshape(-1)
         shifted = flat[1:].view(shape)
         assert np.array_equal(c2s.pad_mask_from_input(shifted, pad_value).cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_smart_forward_matches_the_reference_block():
+    """temp_shared_block.py:18-47 on a padded batch (fixture from the reference class), with our scan kernel, with a
+    caller-supplied mask, and on a batch without padding."""
+    import crop2seg_b200 as c2s
+    cfg, inp, params, outs = load("smart_forward")
+    conv = torch.nn.Conv2d(3, 5, kernel_size=4, stride=2, padding=1)
+    conv.load_state_dict({k[len("conv."):]: torch.from_numpy(v) for k, v in params.items()})
+    conv = conv.cuda().eval()
+    fwd = lambda z: torch.relu(conv(z))  # noqa: E731
+    x = torch.from_numpy(inp["x"]).cuda()
+    with torch.no_grad():
+        out = c2s.smart_forward(fwd, x, pad_value=cfg["pad_value"])
+        out2 = c2s.smart_forward(fwd, x, pad_value=cfg["pad_value"], pad_mask=c2s.pad_mask_from_input(x))
+        full = c2s.smart_forward(fwd, x + 1.0, pad_value=cfg["pad_value"])
+    assert tuple(out.shape) == outs["out"].shape
+    assert np.abs(out.cpu().numpy() - outs["out"]).max() < 1e-5
+    assert torch.equal(out, out2)
+    assert tuple(full.shape) == outs["out"].shape
+    pad = pad_mask_from_input(inp["x"], 0.0)
+    assert np.all(out.cpu().numpy()[pad] == 0.0)
