@@ -25,7 +25,7 @@ EXPORTS = (
     "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_agg_backward_workspace_bytes", "c2s_agg_backward",
     "c2s_agg_skipconv_workspace_bytes", "c2s_agg_skipconv_forward", "c2s_pad_mask",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
-    "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward",
+    "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward", "c2s_ltae_inconv_grad",
 )
 
 
@@ -111,6 +111,8 @@ def load() -> ctypes.CDLL:
         lib.c2s_agg_skipconv_forward.restype = i32
         lib.c2s_agg_skipconv_forward.argtypes = [ctypes.POINTER(AggDesc), vp, vp, vp, ctypes.POINTER(SkipConvParams), vp,
                                                  vp, sz, vp]
+        lib.c2s_ltae_inconv_grad.restype = i32
+        lib.c2s_ltae_inconv_grad.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64, i32, i32, i32, vp]
         lib.c2s_pad_mask.restype = i32
         lib.c2s_pad_mask.argtypes = [vp, i32, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, vp, vp]
         lib.c2s_agg_backward_workspace_bytes.restype = sz

@@ -229,11 +229,13 @@ def _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params
             if need["in_norm_bias"]:
                 grads["in_norm_bias"] = wc.t() @ g_wb + (0 if attn_only else res["grad_beta"])
             if not attn_only:
-                go3 = g_o.view(n, h, dh)
-                if need["inconv_weight"]:
-                    g_wc += torch.einsum("nhi,nhc->hic", go3, res["zn_rows"]).reshape(D, c)
-                if need["inconv_bias"]:
-                    g_wb = g_wb + torch.einsum("nhi,nh->hi", go3, res["sa_rows"][:, :h]).reshape(D)
+                if need["inconv_weight"]:  # direct terms: one kernel over the rows (c2s_ltae_inconv_grad)
+                    g_wc = g_wc.contiguous()
+                    g_wb = g_wb.contiguous().clone() if need["inconv_bias"] else g_wb
+                    ops.ltae_inconv_grad(g_o.contiguous(), res["zn_rows"].contiguous(), res["sa_rows"].contiguous(), g_wc,
+                                         g_wb if need["inconv_bias"] else None, h)
+                elif need["inconv_bias"]:
+                    g_wb = g_wb + torch.einsum("nhi,nh->hi", g_o.view(n, h, dh), res["sa_rows"][:, :h]).reshape(D)
             if need["inconv_weight"]:
                 grads["inconv_weight"] = g_wc
             if need["inconv_bias"]:

@@ -21,30 +21,44 @@ __global__ void __launch_bounds__(kGemmThreads)
 sgemm_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbk,
              long long sbn, float* __restrict__ Cm, long long ldc, const float* __restrict__ bias, int M, int N, int K,
              int k_per_split, int accumulate) {
-  __shared__ float sA[kTK][kTM + 4];
-  __shared__ float sB[kTK][kTN + 4];
+  __shared__ __align__(16) float sA[kTK][kTM + 4];
+  __shared__ __align__(16) float sB[kTK][kTN + 4];
   const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
   const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // 16 x 16 threads, 4 x 4 outputs each
   float acc[4][4] = {};
-  for (int k0 = k_begin; k0 < k_end; k0 += kTK) {
-    for (int i = threadIdx.x; i < kTK * kTM; i += kGemmThreads) {
+  // the next K slice travels from global memory into registers while the current one is multiplied
+  constexpr int kPer = kTK * kTM / kGemmThreads;
+  float ra[kPer], rb[kPer];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int i = threadIdx.x + u * kGemmThreads;
       // the faster index follows the contiguous dimension of the operand
-      const int kk = (sak == 1) ? i % kTK : i / kTM, mm = (sak == 1) ? i / kTK : i % kTM;
-      const int m = m0 + mm, k = k0 + kk;
-      sA[kk][mm] = (m < M && k < k_end) ? A[m * sam + k * sak] : 0.f;
+      const int ka = (sak == 1) ? i % kTK : i / kTM, mm = (sak == 1) ? i / kTK : i % kTM;
+      const int kb = (sbk == 1) ? i % kTK : i / kTN, nn = (sbk == 1) ? i / kTK : i % kTN;
+      const int m = m0 + mm, n = n0 + nn;
+      ra[u] = (m < M && k0 + ka < k_end) ? A[m * sam + (k0 + ka) * sak] : 0.f;
+      rb[u] = (n < N && k0 + kb < k_end) ? B[(k0 + kb) * sbk + n * sbn] : 0.f;
     }
-    for (int i = threadIdx.x; i < kTK * kTN; i += kGemmThreads) {
-      const int kk = (sbk == 1) ? i % kTK : i / kTN, nn = (sbk == 1) ? i / kTK : i % kTN;
-      const int n = n0 + nn, k = k0 + kk;
-      sB[kk][nn] = (n < N && k < k_end) ? B[k * sbk + n * sbn] : 0.f;
+  };
+  if (k_begin < k_end) fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += kTK) {
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int i = threadIdx.x + u * kGemmThreads;
+      const int ka = (sak == 1) ? i % kTK : i / kTM, mm = (sak == 1) ? i / kTK : i % kTM;
+      const int kb = (sbk == 1) ? i % kTK : i / kTN, nn = (sbk == 1) ? i / kTK : i % kTN;
+      sA[ka][mm] = ra[u];
+      sB[kb][nn] = rb[u];
     }
     __syncthreads();
+    if (k0 + kTK < k_end) fetch(k0 + kTK);
 #pragma unroll
     for (int kk = 0; kk < kTK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i], b[i] = sB[kk][tx * 4 + i];
+      const float4 av = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);  // rows are 272 bytes: 16-byte aligned
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -199,6 +213,64 @@ __global__ void bn_batch_backward_kernel(float* __restrict__ g, const float* __r
   }
 }
 
+// Direct term of the in-projection gradient (stage F of DESIGN.md section 4.6):
+//   grad_Wc[h*dh + i][c] += sum_rows grad_o[row][h*dh + i] * zn[row][h][c],   grad_bc[h*dh + i] += sum_rows grad_o[..] * sa[row][h]
+// One CTA = one head x one slice of rows; thread = (channel, half of the dh outputs of the head).
+constexpr int kHoThreads = 256, kHoRows = 64, kHoMaxDh = 32;
+__global__ void __launch_bounds__(kHoThreads)
+head_outer_kernel(const float* __restrict__ g_o, const float* __restrict__ zn, const float* __restrict__ sa, float* __restrict__ g_wc,
+                  float* __restrict__ g_bc, int n_rows, int n_head, int dh, int C, int rows_per_cta) {
+  __shared__ float s_g[kHoRows][kHoMaxDh];
+  __shared__ float s_sa[kHoRows];
+  const int h = blockIdx.x, D = n_head * dh;
+  const int r_begin = blockIdx.y * rows_per_cta, r_end = min(n_rows, r_begin + rows_per_cta);
+  // thread = (channel slot, part of the head's dh outputs); a slot owns channels c and c + n_c
+  const int n_c = (C + 1) / 2;
+  const int parts = min(dh, kHoThreads / n_c), per = (dh + parts - 1) / parts;
+  const int part = threadIdx.x / n_c, c = threadIdx.x - part * n_c;
+  const bool busy = part < parts;
+  const int i0 = part * per, i1 = min(dh, i0 + per);
+  float acc0[kHoMaxDh / 2] = {}, acc1[kHoMaxDh / 2] = {};
+  float accb = 0.f;
+  const int c0 = c, c1 = c + n_c;
+  for (int r0 = r_begin; r0 < r_end; r0 += kHoRows) {
+    const int nr = min(kHoRows, r_end - r0);
+    for (int i = threadIdx.x; i < nr * dh; i += kHoThreads) {
+      const int r = i / dh, j = i - r * dh;
+      s_g[r][j] = g_o[static_cast<size_t>(r0 + r) * D + h * dh + j];
+    }
+    for (int r = threadIdx.x; r < nr; r += kHoThreads) s_sa[r] = sa ? sa[static_cast<size_t>(r0 + r) * 16 + h] : 0.f;
+    __syncthreads();
+    if (busy) {
+      for (int r = 0; r < nr; ++r) {
+        const float* zr = zn + (static_cast<size_t>(r0 + r) * n_head + h) * C;
+        const float z0 = c0 < C ? zr[c0] : 0.f, z1 = c1 < C ? zr[c1] : 0.f;
+#pragma unroll
+        for (int j = 0; j < kHoMaxDh / 2; ++j) {
+          if (i0 + j < i1) {
+            const float gv = s_g[r][i0 + j];
+            acc0[j] = fmaf(gv, z0, acc0[j]);
+            acc1[j] = fmaf(gv, z1, acc1[j]);
+          }
+        }
+      }
+    }
+    if (g_bc != nullptr && threadIdx.x < dh)
+      for (int r = 0; r < nr; ++r) accb = fmaf(s_g[r][threadIdx.x], s_sa[r], accb);
+    __syncthreads();
+  }
+  if (busy) {
+#pragma unroll
+    for (int j = 0; j < kHoMaxDh / 2; ++j) {
+      if (i0 + j < i1) {
+        if (c0 < C) atomicAdd(g_wc + static_cast<size_t>(h * dh + i0 + j) * C + c0, acc0[j]);
+        if (c1 < C) atomicAdd(g_wc + static_cast<size_t>(h * dh + i0 + j) * C + c1, acc1[j]);
+      }
+    }
+  }
+  if (g_bc != nullptr && threadIdx.x < dh) atomicAdd(g_bc + h * dh + threadIdx.x, accb);
+}
+
 int launch_gemm(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* Cm,
                 long long ldc, const float* bias, int M, int N, int K, int splits, bool accumulate, cudaStream_t stream,
                 const char* name) {
@@ -280,8 +352,29 @@ int c2s_ltae_mlp_backward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, co
   status = launch_gemm(g, co, 1, p.mlp_weight, D, 1, io.grad_o, D, nullptr, n_rows, D, co, 1, false, stream,
                        "ltae_mlp_backward<grad_o>");
   if (status != C2S_OK) return status;
-  return launch_gemm(g, 1, co, io.o_rows, D, 1, io.grad_mlp_weight, D, nullptr, co, D, n_rows, ceil_div(n_rows, 512), true,
+  return launch_gemm(g, 1, co, io.o_rows, D, 1, io.grad_mlp_weight, D, nullptr, co, D, n_rows, ceil_div(n_rows, 128), true,
                      stream, "ltae_mlp_backward<grad_weight>");
+}
+
+
+int c2s_ltae_inconv_grad(const float* grad_o, const float* zn_rows, const float* sa_rows, float* grad_inconv_weight,
+                         float* grad_inconv_bias, int64_t n_rows, int32_t n_head, int32_t d_model, int32_t C, void* stream_ptr) {
+  using namespace c2s;
+  C2S_CHECK_ARG(grad_o && zn_rows && grad_inconv_weight, "c2s_ltae_inconv_grad: grad_o / zn_rows / grad_inconv_weight is NULL");
+  C2S_CHECK_ARG(grad_inconv_bias == nullptr || sa_rows != nullptr, "c2s_ltae_inconv_grad: the bias gradient needs sa_rows");
+  C2S_CHECK_ARG(n_rows > 0 && n_head > 0 && n_head <= 16 && d_model % n_head == 0 && C > 0, "c2s_ltae_inconv_grad: bad shape");
+  const int dh = d_model / n_head;
+  if (dh > kHoMaxDh || C > 2 * (kHoThreads / 2))
+    C2S_UNSUPPORTED("c2s_ltae_inconv_grad: d_model / n_head = %d (max %d) or C = %d (max %d) not supported", dh, kHoMaxDh, C,
+                    kHoThreads);
+  int status = check_device();
+  if (status != C2S_OK) return status;
+  const int rows_per_cta = 256;
+  dim3 grid(n_head, ceil_div(static_cast<int>(n_rows), rows_per_cta));
+  head_outer_kernel<<<grid, kHoThreads, 0, static_cast<cudaStream_t>(stream_ptr)>>>(
+      grad_o, zn_rows, sa_rows, grad_inconv_weight, grad_inconv_bias, static_cast<int>(n_rows), n_head, dh, C, rows_per_cta);
+  C2S_LAUNCH_CHECK("ltae_inconv_grad");
+  return C2S_OK;
 }
 
 }  // extern "C"

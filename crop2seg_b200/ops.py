@@ -423,3 +423,22 @@ def ltae_mlp_backward(o_rows: torch.Tensor, grad_out: torch.Tensor, params: Dict
                                            ws_bytes, _stream(dev))
     _lib.check(status, "c2s_ltae_mlp_backward")
     return res
+
+
+def ltae_inconv_grad(grad_o: torch.Tensor, zn_rows: torch.Tensor, sa_rows: Optional[torch.Tensor],
+                     grad_weight: torch.Tensor, grad_bias: Optional[torch.Tensor], n_head: int) -> None:
+    """``c2s_ltae_inconv_grad``: add the direct term of the in-projection gradient to ``grad_weight`` [d_model, C]
+    (and ``grad_bias`` [d_model]) from ``grad_o`` [N, d_model], ``zn_rows`` [N, n_head, C], ``sa_rows`` [N, 16]."""
+    dev = grad_o.device
+    n, d_model = grad_o.shape
+    c = zn_rows.shape[-1]
+    for name, t in (("grad_o", grad_o), ("zn_rows", zn_rows), ("grad_weight", grad_weight)):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+            raise RuntimeError(f"crop2seg_b200: {name} must be a contiguous float32 tensor on {dev}")
+    if grad_bias is not None and (sa_rows is None or not sa_rows.is_contiguous() or not grad_bias.is_contiguous()):
+        raise RuntimeError("crop2seg_b200: the bias gradient needs contiguous sa_rows / grad_bias")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        status = lib.c2s_ltae_inconv_grad(grad_o.data_ptr(), zn_rows.data_ptr(), _ptr(sa_rows), grad_weight.data_ptr(),
+                                          _ptr(grad_bias), n, n_head, d_model, c, _stream(dev))
+    _lib.check(status, "c2s_ltae_inconv_grad")

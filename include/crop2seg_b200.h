@@ -233,6 +233,13 @@ size_t c2s_ltae_mlp_backward_workspace_bytes(const c2s_ltae_desc* desc);
 int c2s_ltae_mlp_backward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const c2s_ltae_mlp_bwd_io* io,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Direct term of the in-projection gradient from the two stages above (what autograd derives from tae.py:478-480):
+ *   grad_inconv_weight[h*dh+i][c] += sum_rows grad_o[row][h*dh+i] * zn_rows[row][h][c]      (acc [d_model][C])
+ *   grad_inconv_bias[h*dh+i]      += sum_rows grad_o[row][h*dh+i] * sa_rows[row][h]         (acc [d_model] or NULL)
+ * grad_o from c2s_ltae_mlp_backward, zn_rows / sa_rows from c2s_ltae_backward. */
+int c2s_ltae_inconv_grad(const float* grad_o, const float* zn_rows, const float* sa_rows, float* grad_inconv_weight,
+                         float* grad_inconv_bias, int64_t n_rows, int32_t n_head, int32_t d_model, int32_t C, void* stream);
+
 size_t c2s_ltae_backward_workspace_bytes(const c2s_ltae_desc* desc);
 int c2s_ltae_backward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const void* x, const void* positions,
                       const uint8_t* pad_mask, const c2s_ltae_bwd_io* io, void* workspace, size_t workspace_bytes,

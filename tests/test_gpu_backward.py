@@ -134,7 +134,7 @@ def test_ltae_backward_matches_autograd_of_the_oracle(variant):
     out, attn = m(xd, batch_positions=to_dev(pos), pad_mask=to_dev(pad))
     assert "ltae_forward" in _lib.last_kernel()
     ((out * to_dev(wo)).sum() + (attn * to_dev(wa)).sum()).backward()
-    assert _lib.last_kernel() == "ltae_backward<general>"  # the feature-sized part of the backward is the CUDA kernel
+    assert _lib.last_kernel() in ("ltae_backward<general>", "ltae_inconv_grad")  # the backward ran on the CUDA kernels
     assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-3
     gmax = max(float(P[name].grad.abs().max()) for name, _ in m.named_parameters())
     for name, p in m.named_parameters():
@@ -220,7 +220,7 @@ def test_ltae_cuda_backward_matches_the_torch_restatement(case):
     wo, wa = _loss_weights(rng, (b, C, h, w), (16, b, t, h, w))
     gx_t, gp_t, _ = _grads(m, kind, x, pos, pad, wo, wa, dtype, True, 5)
     gx_c, gp_c, kernel = _grads(m, kind, x, pos, pad, wo, wa, dtype, False, 5)
-    assert kernel == "ltae_backward<general>"
+    assert kernel in ("ltae_backward<general>", "ltae_inconv_grad")
     tol = 1e-2 if dtype == torch.bfloat16 else 1e-3
     assert rel_err(gx_c, gx_t) < tol
     gmax = max(float(np.abs(v).max()) for v in gp_t.values())
