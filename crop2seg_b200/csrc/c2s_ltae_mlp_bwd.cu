@@ -216,42 +216,62 @@ __global__ void bn_batch_backward_kernel(float* __restrict__ g, const float* __r
 // Direct term of the in-projection gradient (stage F of DESIGN.md section 4.6):
 //   grad_Wc[h*dh + i][c] += sum_rows grad_o[row][h*dh + i] * zn[row][h][c],   grad_bc[h*dh + i] += sum_rows grad_o[..] * sa[row][h]
 // One CTA = one head x one slice of rows; thread = (channel, half of the dh outputs of the head).
-constexpr int kHoThreads = 256, kHoRows = 64, kHoMaxDh = 32;
+constexpr int kHoThreads = 256, kHoRows = 32, kHoMaxDh = 32, kHoMaxC = 256;
+template <int PER>  // outputs of the head per thread (dh / parts, rounded up)
 __global__ void __launch_bounds__(kHoThreads)
 head_outer_kernel(const float* __restrict__ g_o, const float* __restrict__ zn, const float* __restrict__ sa, float* __restrict__ g_wc,
                   float* __restrict__ g_bc, int n_rows, int n_head, int dh, int C, int rows_per_cta) {
   __shared__ float s_g[kHoRows][kHoMaxDh];
   __shared__ float s_sa[kHoRows];
+  __shared__ __align__(16) float s_z[kHoRows][kHoMaxC];  // this head's zn rows of the chunk (coalesced loads, reused by every part)
   const int h = blockIdx.x, D = n_head * dh;
   const int r_begin = blockIdx.y * rows_per_cta, r_end = min(n_rows, r_begin + rows_per_cta);
   // thread = (channel slot, part of the head's dh outputs); a slot owns channels c and c + n_c
   const int n_c = (C + 1) / 2;
-  const int parts = min(dh, kHoThreads / n_c), per = (dh + parts - 1) / parts;
+  const int parts = (dh + PER - 1) / PER, per = PER;
   const int part = threadIdx.x / n_c, c = threadIdx.x - part * n_c;
   const bool busy = part < parts;
   const int i0 = part * per, i1 = min(dh, i0 + per);
-  float acc0[kHoMaxDh / 2] = {}, acc1[kHoMaxDh / 2] = {};
+  float acc0[PER] = {}, acc1[PER] = {};
   float accb = 0.f;
   const int c0 = c, c1 = c + n_c;
   for (int r0 = r_begin; r0 < r_end; r0 += kHoRows) {
     const int nr = min(kHoRows, r_end - r0);
-    for (int i = threadIdx.x; i < nr * dh; i += kHoThreads) {
-      const int r = i / dh, j = i - r * dh;
-      s_g[r][j] = g_o[static_cast<size_t>(r0 + r) * D + h * dh + j];
+    for (int i = threadIdx.x; i < nr * kHoMaxDh; i += kHoThreads) {
+      const int r = i / kHoMaxDh, j = i - r * kHoMaxDh;
+      s_g[r][j] = j < dh ? g_o[static_cast<size_t>(r0 + r) * D + h * dh + j] : 0.f;
     }
     for (int r = threadIdx.x; r < nr; r += kHoThreads) s_sa[r] = sa ? sa[static_cast<size_t>(r0 + r) * 16 + h] : 0.f;
+    if ((C & 3) == 0) {  // 16-byte loads, four in flight per thread
+      const int c4 = C >> 2, n4 = nr * c4;
+      for (int base = 0; base < n4; base += 4 * kHoThreads) {
+        float4 v[4];
+        int rr[4], cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = base + u * kHoThreads + threadIdx.x;
+          rr[u] = i / c4, cc[u] = i - rr[u] * c4;
+          if (i < n4) v[u] = __ldg(reinterpret_cast<const float4*>(zn + (static_cast<size_t>(r0 + rr[u]) * n_head + h) * C) + cc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (base + u * kHoThreads + threadIdx.x < n4) *reinterpret_cast<float4*>(&s_z[rr[u]][cc[u] * 4]) = v[u];
+      }
+    } else {
+      for (int i = threadIdx.x; i < nr * C; i += kHoThreads) {
+        const int r = i / C, cc = i - r * C;
+        s_z[r][cc] = zn[(static_cast<size_t>(r0 + r) * n_head + h) * C + cc];
+      }
+    }
     __syncthreads();
     if (busy) {
       for (int r = 0; r < nr; ++r) {
-        const float* zr = zn + (static_cast<size_t>(r0 + r) * n_head + h) * C;
-        const float z0 = c0 < C ? zr[c0] : 0.f, z1 = c1 < C ? zr[c1] : 0.f;
+        const float z0 = c0 < C ? s_z[r][c0] : 0.f, z1 = c1 < C ? s_z[r][c1] : 0.f;
 #pragma unroll
-        for (int j = 0; j < kHoMaxDh / 2; ++j) {
-          if (i0 + j < i1) {
-            const float gv = s_g[r][i0 + j];
-            acc0[j] = fmaf(gv, z0, acc0[j]);
-            acc1[j] = fmaf(gv, z1, acc1[j]);
-          }
+        for (int j = 0; j < PER; ++j) {
+          const float gv = s_g[r][i0 + j];  // rows are kHoMaxDh wide and zero beyond dh
+          acc0[j] = fmaf(gv, z0, acc0[j]);
+          acc1[j] = fmaf(gv, z1, acc1[j]);
         }
       }
     }
@@ -261,7 +281,7 @@ head_outer_kernel(const float* __restrict__ g_o, const float* __restrict__ zn, c
   }
   if (busy) {
 #pragma unroll
-    for (int j = 0; j < kHoMaxDh / 2; ++j) {
+    for (int j = 0; j < PER; ++j) {
       if (i0 + j < i1) {
         if (c0 < C) atomicAdd(g_wc + static_cast<size_t>(h * dh + i0 + j) * C + c0, acc0[j]);
         if (c1 < C) atomicAdd(g_wc + static_cast<size_t>(h * dh + i0 + j) * C + c1, acc1[j]);
@@ -364,15 +384,27 @@ int c2s_ltae_inconv_grad(const float* grad_o, const float* zn_rows, const float*
   C2S_CHECK_ARG(grad_inconv_bias == nullptr || sa_rows != nullptr, "c2s_ltae_inconv_grad: the bias gradient needs sa_rows");
   C2S_CHECK_ARG(n_rows > 0 && n_head > 0 && n_head <= 16 && d_model % n_head == 0 && C > 0, "c2s_ltae_inconv_grad: bad shape");
   const int dh = d_model / n_head;
-  if (dh > kHoMaxDh || C > 2 * (kHoThreads / 2))
+  if (dh > kHoMaxDh || C > kHoMaxC)
     C2S_UNSUPPORTED("c2s_ltae_inconv_grad: d_model / n_head = %d (max %d) or C = %d (max %d) not supported", dh, kHoMaxDh, C,
                     kHoThreads);
   int status = check_device();
   if (status != C2S_OK) return status;
-  const int rows_per_cta = 256;
+  const int rows_per_cta = 128;
   dim3 grid(n_head, ceil_div(static_cast<int>(n_rows), rows_per_cta));
-  head_outer_kernel<<<grid, kHoThreads, 0, static_cast<cudaStream_t>(stream_ptr)>>>(
-      grad_o, zn_rows, sa_rows, grad_inconv_weight, grad_inconv_bias, static_cast<int>(n_rows), n_head, dh, C, rows_per_cta);
+  // threads = channel slots (C / 2) x parts of the head's dh outputs: the fewest outputs per thread that fit 256 threads
+  const int n_c = (C + 1) / 2;
+  const int max_parts = kHoThreads / n_c > 0 ? kHoThreads / n_c : 1;
+  const int per = ceil_div(dh, max_parts);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_ptr);
+  const int rows = static_cast<int>(n_rows);
+#define C2S_HO(PER) head_outer_kernel<PER><<<grid, kHoThreads, 0, stream>>>(grad_o, zn_rows, sa_rows, grad_inconv_weight, \
+                                                                            grad_inconv_bias, rows, n_head, dh, C, rows_per_cta)
+  if (per <= 2) C2S_HO(2);
+  else if (per <= 4) C2S_HO(4);
+  else if (per <= 8) C2S_HO(8);
+  else if (per <= 16) C2S_HO(16);
+  else C2S_HO(32);
+#undef C2S_HO
   C2S_LAUNCH_CHECK("ltae_inconv_grad");
   return C2S_OK;
 }
