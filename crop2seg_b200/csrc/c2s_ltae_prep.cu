@@ -131,7 +131,7 @@ __global__ void pos_table_kernel(const P* __restrict__ pos, int pos_stride, cons
   float* row = base + dh;
   const size_t bt = blockIdx.x;
   const size_t pi = bt * pos_stride;
-  if (pe_mode == C2S_PE_SINUSOID_LINEAR) {
+  if (pe_mode == C2S_PE_SINUSOID_LINEAR || pe_mode == C2S_PE_SINUSOID) {  // the table has dh distinct columns, tiled h times
     const float p = pos_as_float(pos, pi);
     for (int i = threadIdx.x; i < dh; i += blockDim.x) {
       const float a = p / denom[i];
@@ -143,8 +143,7 @@ __global__ void pos_table_kernel(const P* __restrict__ pos, int pos_stride, cons
     const int i = d % dh;
     float v = 0.f;
     if (pe_mode == C2S_PE_SINUSOID) {
-      const float a = pos_as_float(pos, pi) / denom[i];
-      v = (i & 1) ? cosf(a) : sinf(a);
+      v = base[i];
     } else if (pe_mode == C2S_PE_SINUSOID_LINEAR) {
       v = fc_b[d];
       for (int k = 0; k < D; ++k) v = fmaf(fc_w[static_cast<size_t>(d) * D + k], base[k % dh], v);
