@@ -13,7 +13,7 @@ for r in (32, 64, 128):
     go = torch.randn((B, 64, r, r), device=dev).to(torch.bfloat16)
     nbytes = 2 * int(lengths.sum()) * 64 * r * r + 2 * B * T_FRAMES * 64 * r * r + 2 * B * 64 * r * r
     for rep in range(2):
-        for ch in ("reg", "pipe3", "pipe4", "pipe6"):
+        for ch in ("pipe2", "pipe3", "pipe4", "pipe6"):
             os.environ.pop('C2S_AGG_NO_PIPE', None); os.environ.pop('C2S_AGG_BWD_STAGES', None)
             if ch == "reg": os.environ['C2S_AGG_NO_PIPE'] = '1'
             else: os.environ['C2S_AGG_BWD_STAGES'] = ch[4:]
