@@ -317,9 +317,14 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   return r;
 }
 
-template <typename T, int S>
+// TAPS: the attention rows a pixel block needs (a contiguous slice of the low-resolution map, at most a few hundred
+// floats) ride along with every frame as one more bulk copy into the stage, and the consumers read their bilinear taps
+// from shared memory.  Without it every consumer thread issues 2 * NCOL global loads per frame for them -- measured as
+// the largest cost after the feature bytes themselves (x2 / x4 / x8: 0.103 / 0.304 / 0.928 ms with, 0.078 / 0.228 /
+// 0.857 ms without any tap loads).  TAPS needs 16-byte aligned attention rows (wa % 4 == 0).
+template <typename T, int S, bool TAPS>
 __global__ void __launch_bounds__(kPipeMaxConsumers + 32, (S == 8 && sizeof(T) == 2) ? 3 : 2) agg_pipe_kernel(const AggArgs a, int n_stages,
-                                                                            int n_consumers, int pblocks) {
+                                                                            int n_consumers, int pblocks, int tap_floats) {
   constexpr int VEC = Elem<T>::kVec;
   constexpr int NCOL = Window<VEC, S>::kCols;
   extern __shared__ __align__(128) unsigned char pipe_smem[];
@@ -334,8 +339,19 @@ __global__ void __launch_bounds__(kPipeMaxConsumers + 32, (S == 8 && sizeof(T) =
   const int pb = n_consumers * VEC;                 // pixels per block
   const uint32_t row_bytes = pb * sizeof(T);        // one channel row of the block
   const uint32_t stage_bytes = kPipeCPT * row_bytes;
+  const uint32_t stage_stride = stage_bytes + (TAPS ? tap_floats * 4 : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cwarps = n_consumers >> 5;
+  // attention rows [r_lo, r_hi] feed this pixel block (the rows of its first and last pixel, clamped like source_index)
+  int r_lo = 0, n_rows_att = 0;
+  if (TAPS) {
+    int i0, i1;
+    float l1;
+    source_index(a.sy, (pblk * pb) / a.W, a.ha, i0, i1, l1);
+    r_lo = i0;
+    source_index(a.sy, (pblk * pb + pb - 1) / a.W, a.ha, i0, i1, l1);
+    n_rows_att = i1 - r_lo + 1;
+  }
 
   if (threadIdx.x < 32) {
     int count = 0;
@@ -364,15 +380,19 @@ __global__ void __launch_bounds__(kPipeMaxConsumers + 32, (S == 8 && sizeof(T) =
     if (lane == 0) {
       const T* src = static_cast<const T*>(a.x) + static_cast<size_t>(b) * a.T * frame_stride +
                      static_cast<size_t>(c0) * a.hw + static_cast<size_t>(pblk) * pb;
+      const int amap_p = a.ha * a.wa;
+      const float* att_src = TAPS ? a.attn + (static_cast<size_t>(c0 / a.cpg) * a.B + b) * a.T * amap_p + r_lo * a.wa : nullptr;
+      const uint32_t tap_bytes = TAPS ? static_cast<uint32_t>(n_rows_att * a.wa) * 4u : 0u;
       for (int i = 0; i < n_frames; ++i) {
         const int s = i % n_stages, round = i / n_stages;
         if (round > 0) mbar_wait(smem_addr(&bars[16 + s]), (round - 1) & 1);
         const uint32_t full = smem_addr(&bars[s]);
-        mbar_expect_tx(full, stage_bytes);
+        mbar_expect_tx(full, stage_bytes + tap_bytes);
         const T* fp = src + static_cast<size_t>(frames[i]) * frame_stride;
 #pragma unroll
         for (int k = 0; k < kPipeCPT; ++k)
-          bulk_g2s(stage0 + s * stage_bytes + k * row_bytes, fp + static_cast<size_t>(k) * a.hw, row_bytes, full);
+          bulk_g2s(stage0 + s * stage_stride + k * row_bytes, fp + static_cast<size_t>(k) * a.hw, row_bytes, full);
+        if (TAPS) bulk_g2s(stage0 + s * stage_stride + stage_bytes, att_src + static_cast<size_t>(frames[i]) * amap_p, tap_bytes, full);
       }
     }
     return;
@@ -414,27 +434,35 @@ __global__ void __launch_bounds__(kPipeMaxConsumers + 32, (S == 8 && sizeof(T) =
     for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
 
   float top_n[NCOL], bot_n[NCOL];
-  if (n_frames > 0) {
+  if (!TAPS && n_frames > 0) {
     const float* ap = ab + static_cast<size_t>(frames[0]) * amap;
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) top_n[j] = __ldg(ap + row0 + col[j]), bot_n[j] = __ldg(ap + row1 + col[j]);
   }
+  const int trow0 = (iy0 - r_lo) * a.wa, trow1 = (iy1 - r_lo) * a.wa;  // TAPS: rows inside the staged slice
   const uint32_t my_off = threadIdx.x * 16;
   for (int i = 0; i < n_frames; ++i) {
     float r[NCOL];
+    if (!TAPS) {
 #pragma unroll
-    for (int j = 0; j < NCOL; ++j) r[j] = fmaf(ly1, bot_n[j], ly0 * top_n[j]);
-    if (i + 1 < n_frames) {  // attention taps of the next frame travel while this one is consumed
-      const float* ap = ab + static_cast<size_t>(frames[i + 1]) * amap;
+      for (int j = 0; j < NCOL; ++j) r[j] = fmaf(ly1, bot_n[j], ly0 * top_n[j]);
+      if (i + 1 < n_frames) {  // attention taps of the next frame travel while this one is consumed
+        const float* ap = ab + static_cast<size_t>(frames[i + 1]) * amap;
 #pragma unroll
-      for (int j = 0; j < NCOL; ++j) top_n[j] = __ldg(ap + row0 + col[j]), bot_n[j] = __ldg(ap + row1 + col[j]);
+        for (int j = 0; j < NCOL; ++j) top_n[j] = __ldg(ap + row0 + col[j]), bot_n[j] = __ldg(ap + row1 + col[j]);
+      }
     }
     const int s = i % n_stages;
     mbar_wait(smem_addr(&bars[s]), (i / n_stages) & 1);
     uint4 xv[kPipeCPT];
-    const uint32_t base = stage0 + s * stage_bytes + my_off;
+    const uint32_t base = stage0 + s * stage_stride + my_off;
 #pragma unroll
     for (int k = 0; k < kPipeCPT; ++k) xv[k] = lds_v4(base + k * row_bytes);
+    if (TAPS) {
+      const float* tp = reinterpret_cast<const float*>(pipe_smem + s * stage_stride + stage_bytes);
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) r[j] = fmaf(ly1, tp[trow1 + col[j]], ly0 * tp[trow0 + col[j]]);
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_addr(&bars[16 + s]));  // the stage's data now lives in registers
 
@@ -457,20 +485,34 @@ __global__ void __launch_bounds__(kPipeMaxConsumers + 32, (S == 8 && sizeof(T) =
   for (int k = 0; k < kPipeCPT; ++k) PixelVec<T, VEC>::store(op + static_cast<size_t>(k) * a.hw, acc[k]);
 }
 
-template <typename T, int S>
-int launch_pipe_s(const AggArgs& a, int n_consumers, int n_stages, cudaStream_t stream, const char* name) {
+template <typename T, int S, bool TAPS>
+int launch_pipe_st(const AggArgs& a, int n_consumers, int n_stages, int tap_floats, cudaStream_t stream, const char* name) {
   constexpr int VEC = Elem<T>::kVec;
   const int pblocks = a.hw / (n_consumers * VEC);
-  const size_t smem = static_cast<size_t>(n_stages) * kPipeCPT * n_consumers * 16;
+  const size_t smem = static_cast<size_t>(n_stages) * (static_cast<size_t>(kPipeCPT) * n_consumers * 16 + (TAPS ? tap_floats * 4 : 0));
   static bool attr_done = false;  // per instantiation; the value is the same on every call
   if (!attr_done) {
-    C2S_CUDA(cudaFuncSetAttribute(agg_pipe_kernel<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 16384));
+    C2S_CUDA(cudaFuncSetAttribute(agg_pipe_kernel<T, S, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 13 * 16384));
     attr_done = true;
   }
   dim3 grid((a.C / kPipeCPT) * pblocks, a.B);
-  agg_pipe_kernel<T, S><<<grid, n_consumers + 32, smem, stream>>>(a, n_stages, n_consumers, pblocks);
+  agg_pipe_kernel<T, S, TAPS><<<grid, n_consumers + 32, smem, stream>>>(a, n_stages, n_consumers, pblocks, tap_floats);
   C2S_LAUNCH_CHECK(name);
   return C2S_OK;
+}
+
+template <typename T, int S>
+int launch_pipe_s(const AggArgs& a, int n_consumers, int n_stages, cudaStream_t stream, const char* name) {
+  constexpr int VEC = Elem<T>::kVec;
+  // staged attention rows: 16-byte aligned slices of the map, small enough to ride in the stage
+  const int rows_out = (n_consumers * VEC + a.W - 1) / a.W + 1;  // output rows a pixel block can touch
+  int rows_att = rows_out / S + 3;
+  rows_att = rows_att > a.ha ? a.ha : rows_att;
+  const int tap_floats = ((rows_att * a.wa + 3) / 4) * 4;
+  const bool taps = getenv("C2S_AGG_GLOBAL_TAPS") == nullptr && a.wa % 4 == 0 && reinterpret_cast<uintptr_t>(a.attn) % 16 == 0 &&
+                    tap_floats <= 1024;
+  return taps ? launch_pipe_st<T, S, true>(a, n_consumers, n_stages, tap_floats, stream, name)
+              : launch_pipe_st<T, S, false>(a, n_consumers, n_stages, 0, stream, name);
 }
 
 template <typename T>
