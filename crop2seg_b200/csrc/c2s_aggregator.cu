@@ -584,6 +584,7 @@ struct SkipConvArgs {
   const float* scale;  // [64]  gamma / sqrt(var + eps)
   const float* shift;  // [64]  (conv_bias - mean) * scale + beta
   int n_stages;
+  int tap_floats;      // per head and stage: staged attention rows of the pixel block (0: taps from global memory)
 };
 
 // W[o][c] fp32 -> mma.sync A fragments (row-major 16x16 tiles), bf16 hi and the bf16 residual
@@ -640,6 +641,17 @@ __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int n_cwarps = kScConsumers / 32;
   const int n_stages = k.n_stages;
+  const bool taps = k.tap_floats > 0;
+  const uint32_t stage_stride = kScStageBytes + 16u * k.tap_floats * 4u;
+  int r_lo = 0, n_rows_att = 0;  // attention rows [r_lo, r_lo + n_rows_att) feed this pixel block (as in agg_pipe_kernel)
+  if (taps) {
+    int i0, i1;
+    float l1;
+    source_index(a.sy, (pblk * kScPB) / a.W, a.ha, i0, i1, l1);
+    r_lo = i0;
+    source_index(a.sy, (pblk * kScPB + kScPB - 1) / a.W, a.ha, i0, i1, l1);
+    n_rows_att = i1 - r_lo + 1;
+  }
 
   if (threadIdx.x < 32) {
     int count = 0;
@@ -663,15 +675,23 @@ __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(cons
   const int n_frames = n_frames_s;
   const uint32_t stage0 = smem_addr(pipe_smem);
 
-  if (warp == n_cwarps) {  // ---- producer: one box {128 pixels, 64 channels, 1 frame} per valid frame ------------------
-    if (lane == 0) {
-      for (int i = 0; i < n_frames; ++i) {
-        const int s = i % n_stages, round = i / n_stages;
-        if (round > 0) mbar_wait(smem_addr(&bars[16 + s]), (round - 1) & 1);
-        const uint32_t full = smem_addr(&bars[s]);
-        mbar_expect_tx(full, kScStageBytes);
-        tma_load_3d(stage0 + s * kScStageBytes, &map_x, pblk * kScPB, 0, b * a.T + frames[i], full);
+  if (warp == n_cwarps) {  // ---- producer warp: one box {128 pixels, 64 channels, 1 frame} per valid frame (lane 0) and,
+    // with staged taps, the attention rows of the block for the 16 heads (one small bulk copy per lane 0..15)
+    const int amap_p = a.ha * a.wa;
+    const uint32_t tap_bytes = taps ? static_cast<uint32_t>(n_rows_att * a.wa) * 4u : 0u;
+    const float* att_src = taps && lane < 16 ? a.attn + (static_cast<size_t>(lane) * a.B + b) * a.T * amap_p + r_lo * a.wa : nullptr;
+    for (int i = 0; i < n_frames; ++i) {
+      const int s = i % n_stages, round = i / n_stages;
+      if (round > 0) mbar_wait(smem_addr(&bars[16 + s]), (round - 1) & 1);
+      const uint32_t full = smem_addr(&bars[s]);
+      if (lane == 0) {
+        mbar_expect_tx(full, kScStageBytes + 16u * tap_bytes);
+        tma_load_3d(stage0 + s * stage_stride, &map_x, pblk * kScPB, 0, b * a.T + frames[i], full);
       }
+      __syncwarp();
+      if (taps && lane < 16)
+        bulk_g2s(stage0 + s * stage_stride + kScStageBytes + lane * k.tap_floats * 4, att_src + static_cast<size_t>(frames[i]) * amap_p,
+                 tap_bytes, full);
     }
     return;
   }
@@ -713,7 +733,8 @@ __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(cons
     for (int j = 0; j < VEC; ++j) acc[c][j] = 0.f;
 
   float top_n[NCOL], bot_n[NCOL];
-  if (n_frames > 0) {
+  const int trow0 = (iy0 - r_lo) * a.wa, trow1 = (iy1 - r_lo) * a.wa;  // staged taps: rows inside the slice
+  if (!taps && n_frames > 0) {
     const float* ap = ab + static_cast<size_t>(frames[0]) * amap;
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) top_n[j] = __ldg(ap + row0 + col[j]), bot_n[j] = __ldg(ap + row1 + col[j]);
@@ -721,19 +742,26 @@ __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(cons
   const uint32_t my_off = (head * 4) * (kScPB * 2) + pv * 16;
   for (int i = 0; i < n_frames; ++i) {
     float r[NCOL];
+    if (!taps) {
 #pragma unroll
-    for (int j = 0; j < NCOL; ++j) r[j] = fmaf(ly1, bot_n[j], ly0 * top_n[j]);
-    if (i + 1 < n_frames) {
-      const float* ap = ab + static_cast<size_t>(frames[i + 1]) * amap;
+      for (int j = 0; j < NCOL; ++j) r[j] = fmaf(ly1, bot_n[j], ly0 * top_n[j]);
+      if (i + 1 < n_frames) {
+        const float* ap = ab + static_cast<size_t>(frames[i + 1]) * amap;
 #pragma unroll
-      for (int j = 0; j < NCOL; ++j) top_n[j] = __ldg(ap + row0 + col[j]), bot_n[j] = __ldg(ap + row1 + col[j]);
+        for (int j = 0; j < NCOL; ++j) top_n[j] = __ldg(ap + row0 + col[j]), bot_n[j] = __ldg(ap + row1 + col[j]);
+      }
     }
     const int s = i % n_stages;
     mbar_wait(smem_addr(&bars[s]), (i / n_stages) & 1);
     uint4 xv[4];
-    const uint32_t base = stage0 + s * kScStageBytes + my_off;
+    const uint32_t base = stage0 + s * stage_stride + my_off;
 #pragma unroll
     for (int c = 0; c < 4; ++c) xv[c] = lds_v4(base + c * (kScPB * 2));
+    if (taps) {
+      const float* tp = reinterpret_cast<const float*>(pipe_smem + s * stage_stride + kScStageBytes) + head * k.tap_floats;
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) r[j] = fmaf(ly1, tp[trow1 + col[j]], ly0 * tp[trow0 + col[j]]);
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_addr(&bars[16 + s]));
 
@@ -753,7 +781,7 @@ __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(cons
   }
 
   // ---- epilogue: skip tile [64 channels][128 pixels] bf16 -> shared memory, 1x1 convolution on the tensor cores -------
-  const uint32_t tile = stage0 + n_stages * kScStageBytes;
+  const uint32_t tile = stage0 + n_stages * stage_stride;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const uint4 v = Elem<T>::pack(acc[c]);
@@ -829,7 +857,7 @@ EncodeTiledFn agg_encode_fn() {
 
 template <int S>
 int launch_skipconv(const CUtensorMap& map_x, const SkipConvArgs& k, cudaStream_t stream, const char* name) {
-  const size_t smem = static_cast<size_t>(k.n_stages) * kScStageBytes + kScC * kScTileStride;
+  const size_t smem = static_cast<size_t>(k.n_stages) * (kScStageBytes + 16 * k.tap_floats * 4) + kScC * kScTileStride;
   C2S_CUDA(cudaFuncSetAttribute(agg_skipconv_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(k.a.hw / kScPB, k.a.B);
   agg_skipconv_kernel<S><<<grid, kScConsumers + 32, smem, stream>>>(map_x, k);
@@ -1006,6 +1034,15 @@ int c2s_agg_skipconv_forward(const c2s_agg_desc* d, const void* x, const float* 
   C2S_LAUNCH_CHECK("skipconv_prep");
   k.wfrag = wfrag, k.scale = scale, k.shift = shift;
   k.n_stages = 4;
+  {  // staged attention rows: the rows a 128-pixel block can touch, per head (16-byte aligned slices of the map)
+    const int rows_out = (kScPB + d->W - 1) / d->W + 1;
+    int rows_att = rows_out / scale_class + 3;
+    rows_att = rows_att > d->ha ? d->ha : rows_att;
+    const int tap_floats = ((rows_att * d->wa + 3) / 4) * 4;
+    const bool taps = getenv("C2S_AGG_GLOBAL_TAPS") == nullptr && d->wa % 4 == 0 && reinterpret_cast<uintptr_t>(attn) % 16 == 0 &&
+                      tap_floats <= 256;
+    k.tap_floats = taps ? tap_floats : 0;
+  }
   EncodeTiledFn fn = agg_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");

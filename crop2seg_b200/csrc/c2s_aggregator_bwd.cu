@@ -300,9 +300,11 @@ __device__ __forceinline__ uint4 blds_v4(uint32_t addr) {
   return r;
 }
 
-template <typename T, int S>
+// TAPS: as in the forward (c2s_aggregator.cu), the attention rows of the pixel block ride in the stage as one more bulk
+// copy and the consumers read their taps from shared memory instead of 2 * NCOL global loads per thread and frame.
+template <typename T, int S, bool TAPS>
 __global__ void __launch_bounds__(kBwdPipeMaxConsumers + 32, 2)
-agg_backward_pipe_kernel(const AggBwdArgs a, int n_stages, int n_consumers, int pblocks) {
+agg_backward_pipe_kernel(const AggBwdArgs a, int n_stages, int n_consumers, int pblocks, int tap_floats) {
   constexpr int VEC = Elem<T>::kVec;
   constexpr int CPT = kBwdPipeCPT;
   constexpr int M = VEC / S;   // attention cells per thread
@@ -319,8 +321,19 @@ agg_backward_pipe_kernel(const AggBwdArgs a, int n_stages, int n_consumers, int 
   const int c0 = cchunk * CPT;
   const uint32_t row_bytes = n_consumers * 16;
   const uint32_t stage_bytes = CPT * row_bytes;
+  const uint32_t stage_stride = stage_bytes + (TAPS ? tap_floats * 4 : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cwarps = n_consumers >> 5;
+  int r_lo = 0, n_rows_att = 0;  // attention rows [r_lo, r_lo + n_rows_att) feed this pixel block
+  if (TAPS) {
+    const int pb = n_consumers * VEC;
+    int i0, i1;
+    float l1;
+    bwd_source_index(a.sy, (pblk * pb) / a.W, a.ha, i0, i1, l1);
+    r_lo = i0;
+    bwd_source_index(a.sy, (pblk * pb + pb - 1) / a.W, a.ha, i0, i1, l1);
+    n_rows_att = i1 - r_lo + 1;
+  }
 
   for (int t = threadIdx.x; t < a.T; t += blockDim.x) s_pad[t] = a.pad != nullptr && a.pad[b * a.T + t] != 0;
   if (threadIdx.x == 0) {
@@ -338,17 +351,21 @@ agg_backward_pipe_kernel(const AggBwdArgs a, int n_stages, int n_consumers, int 
   if (warp == n_cwarps) {  // ---- producer: the valid frames of the chunk, in order ------------------------
     if (lane == 0) {
       const T* src = static_cast<const T*>(a.x) + static_cast<size_t>(b) * a.T * frame_stride + plane0;
+      const int amap_p = a.ha * a.wa;
+      const float* att_src = TAPS ? a.attn + (static_cast<size_t>(c0 / a.cpg) * a.B + b) * a.T * amap_p + r_lo * a.wa : nullptr;
+      const uint32_t tap_bytes = TAPS ? static_cast<uint32_t>(n_rows_att * a.wa) * 4u : 0u;
       int i = 0;
       for (int t = t_begin; t < t_end; ++t) {
         if (s_pad[t]) continue;
         const int s = i % n_stages, round = i / n_stages;
         if (round > 0) bmbar_wait(bsmem_addr(&bars[16 + s]), (round - 1) & 1);
         const uint32_t full = bsmem_addr(&bars[s]);
-        bmbar_expect_tx(full, stage_bytes);
+        bmbar_expect_tx(full, stage_bytes + tap_bytes);
         const T* fp = src + static_cast<size_t>(t) * frame_stride;
 #pragma unroll
         for (int k = 0; k < CPT; ++k)
-          bbulk_g2s(stage0 + s * stage_bytes + k * row_bytes, fp + static_cast<size_t>(k) * a.hw, row_bytes, full);
+          bbulk_g2s(stage0 + s * stage_stride + k * row_bytes, fp + static_cast<size_t>(k) * a.hw, row_bytes, full);
+        if (TAPS) bbulk_g2s(stage0 + s * stage_stride + stage_bytes, att_src + static_cast<size_t>(t) * amap_p, tap_bytes, full);
         ++i;
       }
     }
@@ -399,19 +416,30 @@ agg_backward_pipe_kernel(const AggBwdArgs a, int n_stages, int n_consumers, int 
       continue;
     }
     // forward weights (identical arithmetic to agg_forward_kernel); the taps travel while the stage is awaited
-    const float* ap = a.attn + abase + static_cast<size_t>(t) * amap;
     float r[NCOL];
+    if (!TAPS) {
+      const float* ap = a.attn + abase + static_cast<size_t>(t) * amap;
 #pragma unroll
-    for (int jj = 0; jj < NCOL; ++jj) {
-      const int cj = clampc(cmin + jj);
-      r[jj] = fmaf(ly1, __ldg(ap + row1 + cj), ly0 * __ldg(ap + row0 + cj));
+      for (int jj = 0; jj < NCOL; ++jj) {
+        const int cj = clampc(cmin + jj);
+        r[jj] = fmaf(ly1, __ldg(ap + row1 + cj), ly0 * __ldg(ap + row0 + cj));
+      }
     }
     const int s = i % n_stages;
     bmbar_wait(bsmem_addr(&bars[s]), (i / n_stages) & 1);
     uint4 xv[CPT];
-    const uint32_t base = stage0 + s * stage_bytes + my_off;
+    const uint32_t base = stage0 + s * stage_stride + my_off;
 #pragma unroll
     for (int k = 0; k < CPT; ++k) xv[k] = blds_v4(base + k * row_bytes);
+    if (TAPS) {
+      const float* tp = reinterpret_cast<const float*>(bpipe_smem + s * stage_stride + stage_bytes);
+      const int trow0 = row0 - r_lo * a.wa, trow1 = row1 - r_lo * a.wa;
+#pragma unroll
+      for (int jj = 0; jj < NCOL; ++jj) {
+        const int cj = clampc(cmin + jj);
+        r[jj] = fmaf(ly1, tp[trow1 + cj], ly0 * tp[trow0 + cj]);
+      }
+    }
     __syncwarp();
     if (lane == 0) bmbar_arrive(bsmem_addr(&bars[16 + s]));  // the stage's data now lives in registers
     ++i;
@@ -469,6 +497,21 @@ agg_backward_pipe_kernel(const AggBwdArgs a, int n_stages, int n_consumers, int 
   }
 }
 
+template <typename T, int S, bool TAPS>
+int launch_bwd_pipe_st(const AggBwdArgs& b, int n_consumers, int n_stages, int pblocks, int tap_floats, cudaStream_t stream,
+                       const char* name) {
+  const size_t smem = static_cast<size_t>(n_stages) * (static_cast<size_t>(kBwdPipeCPT) * n_consumers * 16 + (TAPS ? tap_floats * 4 : 0));
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    C2S_CUDA(cudaFuncSetAttribute(agg_backward_pipe_kernel<T, S, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 13 * 16384));
+    attr_done = true;
+  }
+  dim3 grid((b.C / kBwdPipeCPT) * pblocks, b.B * b.t_chunks);
+  agg_backward_pipe_kernel<T, S, TAPS><<<grid, n_consumers + 32, smem, stream>>>(b, n_stages, n_consumers, pblocks, tap_floats);
+  C2S_LAUNCH_CHECK(name);
+  return C2S_OK;
+}
+
 template <typename T, int S>
 int launch_bwd_pipe_s(const AggBwdArgs& a, int n_consumers, int n_stages, cudaStream_t stream, const char* name) {
   constexpr int VEC = Elem<T>::kVec;
@@ -479,17 +522,15 @@ int launch_bwd_pipe_s(const AggBwdArgs& a, int n_consumers, int n_stages, cudaSt
   while (ctas * chunks < 8 * 148 && ceil_div(a.T, chunks * 2) >= 8 && static_cast<long long>(a.B) * chunks * 2 <= 65535) chunks *= 2;
   b.t_per_chunk = ceil_div(a.T, chunks);
   b.t_chunks = ceil_div(a.T, b.t_per_chunk);
-  const size_t smem = static_cast<size_t>(n_stages) * kBwdPipeCPT * n_consumers * 16;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    C2S_CUDA(cudaFuncSetAttribute(agg_backward_pipe_kernel<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 16384));
-    attr_done = true;
-  }
-  dim3 grid((a.C / kBwdPipeCPT) * pblocks, a.B * b.t_chunks);
-  agg_backward_pipe_kernel<T, S><<<grid, n_consumers + 32, smem, stream>>>(b, n_stages, n_consumers, pblocks);
-  C2S_LAUNCH_CHECK(name);
-  (void)VEC;
-  return C2S_OK;
+  // staged attention rows (see agg_pipe_kernel): 16-byte aligned slices of the map
+  const int rows_out = (n_consumers * VEC + a.W - 1) / a.W + 1;
+  int rows_att = rows_out / S + 3;
+  rows_att = rows_att > a.ha ? a.ha : rows_att;
+  const int tap_floats = ((rows_att * a.wa + 3) / 4) * 4;
+  const bool taps = getenv("C2S_AGG_GLOBAL_TAPS") == nullptr && a.wa % 4 == 0 && reinterpret_cast<uintptr_t>(a.attn) % 16 == 0 &&
+                    tap_floats <= 1024;
+  return taps ? launch_bwd_pipe_st<T, S, true>(b, n_consumers, n_stages, pblocks, tap_floats, stream, name)
+              : launch_bwd_pipe_st<T, S, false>(b, n_consumers, n_stages, pblocks, 0, stream, name);
 }
 
 // att_mean: every head receives grad(mean) / n_heads                       (temporal_aggregator.py:48)
