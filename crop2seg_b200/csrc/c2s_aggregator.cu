@@ -625,8 +625,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-template <int S>
+template <int S, bool TAPS>
 __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                             const __grid_constant__ CUtensorMap map_att,
                                                                              const SkipConvArgs k) {
   using T = __nv_bfloat16;
   constexpr int VEC = 8;
@@ -641,7 +642,7 @@ __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int n_cwarps = kScConsumers / 32;
   const int n_stages = k.n_stages;
-  const bool taps = k.tap_floats > 0;
+  constexpr bool taps = TAPS;
   const uint32_t stage_stride = kScStageBytes + 16u * k.tap_floats * 4u;
   int r_lo = 0, n_rows_att = 0;  // attention rows [r_lo, r_lo + n_rows_att) feed this pixel block (as in agg_pipe_kernel)
   if (taps) {
@@ -675,23 +676,19 @@ __global__ void __launch_bounds__(kScConsumers + 32, 2) agg_skipconv_kernel(cons
   const int n_frames = n_frames_s;
   const uint32_t stage0 = smem_addr(pipe_smem);
 
-  if (warp == n_cwarps) {  // ---- producer warp: one box {128 pixels, 64 channels, 1 frame} per valid frame (lane 0) and,
-    // with staged taps, the attention rows of the block for the 16 heads (one small bulk copy per lane 0..15)
-    const int amap_p = a.ha * a.wa;
-    const uint32_t tap_bytes = taps ? static_cast<uint32_t>(n_rows_att * a.wa) * 4u : 0u;
-    const float* att_src = taps && lane < 16 ? a.attn + (static_cast<size_t>(lane) * a.B + b) * a.T * amap_p + r_lo * a.wa : nullptr;
-    for (int i = 0; i < n_frames; ++i) {
-      const int s = i % n_stages, round = i / n_stages;
-      if (round > 0) mbar_wait(smem_addr(&bars[16 + s]), (round - 1) & 1);
-      const uint32_t full = smem_addr(&bars[s]);
-      if (lane == 0) {
-        mbar_expect_tx(full, kScStageBytes + 16u * tap_bytes);
+  if (warp == n_cwarps) {  // ---- producer: one box {128 pixels, 64 channels, 1 frame} per valid frame and, with staged
+    // taps, one box {tap_floats of the map from row r_lo, 1 frame, 16 heads} of the attention (16 separate bulk copies
+    // of 128-256 bytes per frame were measured: issue-bound, slower than the global-memory taps)
+    if (lane == 0) {
+      const uint32_t tap_bytes = taps ? 16u * k.tap_floats * 4u : 0u;
+      for (int i = 0; i < n_frames; ++i) {
+        const int s = i % n_stages, round = i / n_stages;
+        if (round > 0) mbar_wait(smem_addr(&bars[16 + s]), (round - 1) & 1);
+        const uint32_t full = smem_addr(&bars[s]);
+        mbar_expect_tx(full, kScStageBytes + tap_bytes);
         tma_load_3d(stage0 + s * stage_stride, &map_x, pblk * kScPB, 0, b * a.T + frames[i], full);
+        if (taps) tma_load_3d(stage0 + s * stage_stride + kScStageBytes, &map_att, r_lo * a.wa, b * a.T + frames[i], 0, full);
       }
-      __syncwarp();
-      if (taps && lane < 16)
-        bulk_g2s(stage0 + s * stage_stride + kScStageBytes + lane * k.tap_floats * 4, att_src + static_cast<size_t>(frames[i]) * amap_p,
-                 tap_bytes, full);
     }
     return;
   }
@@ -855,14 +852,20 @@ EncodeTiledFn agg_encode_fn() {
   return fn;
 }
 
-template <int S>
-int launch_skipconv(const CUtensorMap& map_x, const SkipConvArgs& k, cudaStream_t stream, const char* name) {
+template <int S, bool TAPS>
+int launch_skipconv_t(const CUtensorMap& map_x, const CUtensorMap& map_att, const SkipConvArgs& k, cudaStream_t stream, const char* name) {
   const size_t smem = static_cast<size_t>(k.n_stages) * (kScStageBytes + 16 * k.tap_floats * 4) + kScC * kScTileStride;
-  C2S_CUDA(cudaFuncSetAttribute(agg_skipconv_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  C2S_CUDA(cudaFuncSetAttribute(agg_skipconv_kernel<S, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(k.a.hw / kScPB, k.a.B);
-  agg_skipconv_kernel<S><<<grid, kScConsumers + 32, smem, stream>>>(map_x, k);
+  agg_skipconv_kernel<S, TAPS><<<grid, kScConsumers + 32, smem, stream>>>(map_x, map_att, k);
   C2S_LAUNCH_CHECK(name);
   return C2S_OK;
+}
+
+template <int S>
+int launch_skipconv(const CUtensorMap& map_x, const CUtensorMap& map_att, const SkipConvArgs& k, cudaStream_t stream, const char* name) {
+  return k.tap_floats > 0 ? launch_skipconv_t<S, true>(map_x, map_att, k, stream, name)
+                          : launch_skipconv_t<S, false>(map_x, map_att, k, stream, name);
 }
 
 bool uses_pool(const c2s_agg_desc* d) { return d->mode == C2S_AGG_ATT_GROUP && !(d->H > d->wa); }
@@ -1039,8 +1042,9 @@ int c2s_agg_skipconv_forward(const c2s_agg_desc* d, const void* x, const float* 
     int rows_att = rows_out / scale_class + 3;
     rows_att = rows_att > d->ha ? d->ha : rows_att;
     const int tap_floats = ((rows_att * d->wa + 3) / 4) * 4;
+    // x2: measured slower with staged taps here (0.151 vs 0.109 ms at 32 x 32), so that level keeps the global-memory taps
     const bool taps = getenv("C2S_AGG_GLOBAL_TAPS") == nullptr && d->wa % 4 == 0 && reinterpret_cast<uintptr_t>(attn) % 16 == 0 &&
-                      tap_floats <= 256;
+                      tap_floats <= 256 && scale_class >= 4;
     k.tap_floats = taps ? tap_floats : 0;
   }
   EncodeTiledFn fn = agg_encode_fn();
@@ -1059,10 +1063,24 @@ int c2s_agg_skipconv_forward(const c2s_agg_desc* d, const void* x, const float* 
     set_error("cuTensorMapEncodeTiled (skip features) failed with CUresult %d", static_cast<int>(r));
     return C2S_ERR_CUDA;
   }
+  CUtensorMap map_att = map_x;  // attention as [16 heads][B*T][ha*wa] fp32; box = tap_floats of one map x 1 frame x 16 heads
+  if (k.tap_floats > 0) {
+    const cuuint64_t amap = static_cast<cuuint64_t>(d->ha) * d->wa;
+    const cuuint64_t adims[3] = {amap, static_cast<cuuint64_t>(d->B) * d->T, 16};
+    const cuuint64_t astrides[2] = {amap * 4, static_cast<cuuint64_t>(d->B) * d->T * amap * 4};
+    const cuuint32_t abox[3] = {static_cast<cuuint32_t>(k.tap_floats), 1, 16};
+    const CUresult ra = fn(&map_att, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(attn), adims, astrides, abox, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (ra != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (attention) failed with CUresult %d", static_cast<int>(ra));
+      return C2S_ERR_CUDA;
+    }
+  }
   switch (scale_class) {
-    case 2: return launch_skipconv<2>(map_x, k, stream, "agg_skipconv<x2>");
-    case 4: return launch_skipconv<4>(map_x, k, stream, "agg_skipconv<x4>");
-    default: return launch_skipconv<8>(map_x, k, stream, "agg_skipconv<x8>");
+    case 2: return launch_skipconv<2>(map_x, map_att, k, stream, "agg_skipconv<x2>");
+    case 4: return launch_skipconv<4>(map_x, map_att, k, stream, "agg_skipconv<x4>");
+    default: return launch_skipconv<8>(map_x, map_att, k, stream, "agg_skipconv<x8>");
   }
 }
 
