@@ -350,8 +350,8 @@ def run_b200(args):
         "achieved": a128, "peak": peak, "unit": "GB/s", "frac": a128 / peak, "traffic": traffic,
         "algorithmic_bytes": agg128_bytes(lengths, elem),
         "peak_source": peak_src, "kernel_ms": per[3],
-        "peak_note": "the measured peak is a COPY bandwidth (half reads, half writes); this kernel is 98 % reads, so a "
-                     "fraction above 1 is possible (%.2f of the 7.7 TB/s HBM3e figure of the hardware guide)" % (a128 / 7700.0),
+        "peak_note": "the measured peak is a COPY bandwidth (half reads, half writes); this kernel is 98 percent reads, so "
+                     f"a fraction above 1 is possible ({a128 / 7700.0:.2f} of the 7.7 TB/s HBM3e figure of the hardware guide)",
         "step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9,
                  "frac": step_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9 / peak,
                  "kernel_ms": {"ltae": per[0], "agg32": per[1], "agg64": per[2], "agg128": per[3]}},
