@@ -529,6 +529,9 @@ int launch_bwd_pipe_s(const AggBwdArgs& a, int n_consumers, int n_stages, cudaSt
   const int tap_floats = ((rows_att * a.wa + 3) / 4) * 4;
   const bool taps = getenv("C2S_AGG_GLOBAL_TAPS") == nullptr && a.wa % 4 == 0 && reinterpret_cast<uintptr_t>(a.attn) % 16 == 0 &&
                     tap_floats <= 1024;
+  if (taps)  // the tuning hook may ask for more stages than fit once the rows ride along
+    while (n_stages > 2 && static_cast<size_t>(n_stages) * (static_cast<size_t>(kBwdPipeCPT) * n_consumers * 16 + tap_floats * 4) > 13 * 16384)
+      --n_stages;
   return taps ? launch_bwd_pipe_st<T, S, true>(b, n_consumers, n_stages, pblocks, tap_floats, stream, name)
               : launch_bwd_pipe_st<T, S, false>(b, n_consumers, n_stages, pblocks, 0, stream, name);
 }

@@ -207,6 +207,28 @@ def test_pipelined_aggregator_matches_oracle(name, dtype):
     assert torch.equal(outs[False], outs[True])
 
 
+@pytest.mark.parametrize("name", sorted(AGG_CASES))
+def test_staged_attention_rows_equal_global_taps(name):
+    """The attention rows that ride in the stage (default) give the same bits as per-thread global loads of the taps
+    (C2S_AGG_GLOBAL_TAPS hook): forward, both gradients' kernels, bf16."""
+    from crop2seg_b200 import ops
+    heads, (b, t, c, h, w), (ha, wa), lengths = AGG_CASES[name]
+    rng = np.random.RandomState(6000 + len(name))
+    x, _, pad = synth_inputs(rng, b, t, c, h, w, lengths)
+    attn = random_attention(rng, heads, pad, ha, wa)
+    go = rng.standard_normal((b, c, h, w)).astype(np.float32)
+    xd, pd, ad, gd = to_dev(x, dtype=torch.bfloat16), to_dev(pad), to_dev(attn), to_dev(go, dtype=torch.bfloat16)
+    res = {}
+    for global_taps in (False, True):
+        with env("C2S_AGG_GLOBAL_TAPS", global_taps):
+            out = ops.temporal_aggregate_forward(xd, pd, ad, "att_group")
+            gx, ga = ops.temporal_aggregate_backward(xd, pd, ad, gd, "att_group")
+        res[global_taps] = (out, gx, ga)
+    assert torch.equal(res[False][0], res[True][0])
+    assert torch.equal(res[False][1], res[True][1])
+    assert rel_err(res[False][2].cpu().numpy(), res[True][2].cpu().numpy()) < 1e-5  # float atomics reorder
+
+
 def test_folded_weights_are_reused_until_a_parameter_changes():
     kind, kw, (b, t, h, w), lengths, _ = LTAE_CASES["utae"]
     m, rng = _build(kind, kw, 31)
