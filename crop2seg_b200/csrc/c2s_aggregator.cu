@@ -323,7 +323,7 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 // the largest cost after the feature bytes themselves (x2 / x4 / x8: 0.103 / 0.304 / 0.928 ms with, 0.078 / 0.228 /
 // 0.857 ms without any tap loads).  TAPS needs 16-byte aligned attention rows (wa % 4 == 0).
 template <typename T, int S, bool TAPS>
-__global__ void __launch_bounds__(kPipeMaxConsumers + 32, (S == 8 && sizeof(T) == 2) ? 3 : 2) agg_pipe_kernel(const AggArgs a, int n_stages,
+__global__ void __launch_bounds__(kPipeMaxConsumers + 32, (S >= 4 && sizeof(T) == 2 && TAPS) || (S == 8 && sizeof(T) == 2) ? 3 : 2) agg_pipe_kernel(const AggArgs a, int n_stages,
                                                                             int n_consumers, int pblocks, int tap_floats) {
   constexpr int VEC = Elem<T>::kVec;
   constexpr int NCOL = Window<VEC, S>::kCols;
