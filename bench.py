@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of one step's outputs")
     ap.add_argument("--cpu-patches", type=int, default=2, help="patches in the CPU-baseline sample")
     return ap.parse_args()
 
@@ -221,7 +222,7 @@ def run_reference(args):
     total = time.perf_counter() - t0
     value = args.cpu_patches * args.steps / sum(times)
     sample = (f"{args.cpu_patches} patches/step (U-TAE placement fp32, T=61, one full series + series of length 27), "
-              f"torch-CPU port of the reference modules (oracle/torch_port.py: same ATen calls; the reference itself cannot travel to the GPU box)")
+              f"torch-CPU port of the reference modules (oracle/torch_port.py: the reference's ATen calls and materialising copies, pinned on the reference's outputs; the reference itself cannot travel to the GPU box)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
@@ -357,6 +358,22 @@ def run_b200(args):
                  "kernel_ms": {"ltae": per[0], "agg32": per[1], "agg64": per[2], "agg128": per[3]}},
     }
 
+    # ---- parity of one step at the benchmarked shapes (outside every timed region): first, middle and LAST sample
+    #      of the batch against the oracle on the host (offsets beyond 2^32 elements are exercised by the last one) ----
+    parity = None
+    if not args.no_parity:
+        from c2s_testlib import hot_path_parity
+        out_p, att_p = None, None
+        with torch.no_grad():
+            out_p, att_p = enc(x4, batch_positions=pos, pad_mask=pad)
+            skips_p = [agg(x, pad_mask=pad, attn_mask=att_p) for x in xs]
+        torch.cuda.synchronize()
+        parity = hot_path_parity(enc, x4, xs, pos, pad, out_p, att_p, skips_p, samples=sorted({0, B // 2, B - 1}))
+        parity["tolerance"] = 1e-2 if args.dtype == "bf16" else 1e-4
+        parity["ok"] = bool(parity["attn"] < parity["tolerance"] and parity["out"] < parity["tolerance"]
+                            and max(parity["skips"]) < parity["tolerance"] and parity["pad_attention_exactly_zero"])
+        del out_p, att_p, skips_p
+
     # ---- end to end through the modules with host buffers -------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -435,7 +452,7 @@ def run_b200(args):
                                    "[B,61,64,{32,64,128}^2], irregular T 27..61 with pad masks",
                        "batch_per_gpu": B, "mean_valid_frames": float(np.mean(lengths)),
                        "l2": "inputs (11 GB/step) exceed L2; no flush", "sharding": f"{world} x independent patch shards"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

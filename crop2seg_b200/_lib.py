@@ -11,17 +11,20 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 5
+C2S_ABI_VERSION = 6
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
 AGG_ATT_GROUP, AGG_ATT_MEAN, AGG_MEAN = 0, 1, 2
 PE_NONE, PE_SINUSOID, PE_SINUSOID_LINEAR, PE_DOY_TABLE = 0, 1, 2, 3
 LTAE_ATTN_ONLY, LTAE_SKIP_ATTN_STORE, LTAE_ZERO_PADDED, LTAE_BN_BATCH_STATS, LTAE_REUSE_FOLDED = 1, 2, 4, 8, 16
+# enum c2s_option / c2s_ltae_kernel (kernel-selection switches for parity tests and A/B measurements)
+OPT_LTAE_KERNEL, OPT_AGG_KERNEL, OPT_AGG_TAPS = 0, 1, 2
+LTAE_KERNEL_AUTO, LTAE_KERNEL_GENERAL, LTAE_KERNEL_SLAB, LTAE_KERNEL_STREAM = 0, 1, 2, 3
 
 EXPORTS = (
     "c2s_abi_version", "c2s_last_error", "c2s_launch_count", "c2s_reset_launch_count", "c2s_last_kernel",
-    "c2s_last_ltae_kernel",
+    "c2s_last_ltae_kernel", "c2s_set_option", "c2s_get_option",
     "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_agg_backward_workspace_bytes", "c2s_agg_backward",
     "c2s_agg_skipconv_workspace_bytes", "c2s_agg_skipconv_forward", "c2s_pad_mask",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
@@ -102,6 +105,10 @@ def load() -> ctypes.CDLL:
         lib.c2s_last_ltae_kernel.restype = ctypes.c_char_p
         lib.c2s_launch_count.restype = ctypes.c_int64
         lib.c2s_reset_launch_count.restype = None
+        lib.c2s_set_option.restype = i32
+        lib.c2s_set_option.argtypes = [i32, i32]
+        lib.c2s_get_option.restype = i32
+        lib.c2s_get_option.argtypes = [i32]
         lib.c2s_agg_workspace_bytes.restype = sz
         lib.c2s_agg_workspace_bytes.argtypes = [ctypes.POINTER(AggDesc)]
         lib.c2s_agg_forward.restype = i32
@@ -162,3 +169,21 @@ def last_kernel() -> str:
 def last_ltae_kernel() -> str:
     """The L-TAE attention kernel that served the last ``c2s_ltae_forward`` call."""
     return load().c2s_last_ltae_kernel().decode("utf-8", "replace")
+
+
+class option:
+    """``with _lib.option(_lib.OPT_LTAE_KERNEL, _lib.LTAE_KERNEL_GENERAL): ...`` -- process-wide kernel-selection
+    switch of the library (``c2s_set_option``), restored on exit.  For parity tests and A/B measurements; production
+    leaves every option at 0."""
+
+    def __init__(self, which: int, value: int):
+        self.which, self.value = which, int(value)
+
+    def __enter__(self):
+        lib = load()
+        self.old = lib.c2s_get_option(self.which)
+        check(lib.c2s_set_option(self.which, self.value), "c2s_set_option")
+        return self
+
+    def __exit__(self, *exc):
+        load().c2s_set_option(self.which, self.old)

@@ -4,22 +4,20 @@
   the aggregations move 97.7 % of the hot path's bytes.
 * ``LtaeFunction``: the forward is the fused CUDA kernel (train-mode BatchNorm statistics and injected dropout masks
   included).  The backward has three stages:
-    M  the rows after the attention (MLP Linear, BatchNorm, ReLU, dropout mask, output GroupNorm on [N, 256] /
-       [N, c_out] rows, N = B*H*W) are differentiated with torch autograd -- library GEMMs on a few MB;
+    M  ``c2s_ltae_mlp_backward`` (CUDA, ``csrc/c2s_ltae_mlp_bwd.cu``): the rows after the attention (MLP Linear,
+       BatchNorm, ReLU, dropout mask, output GroupNorm on [N, 256] / [N, c_out] rows, N = B*H*W);
     A  ``c2s_ltae_backward`` (CUDA, ``csrc/c2s_ltae_bwd.cu``) does everything that touches the [N, T, C] features:
        it recomputes the attention, back-propagates through the value sums, the softmax, the scores and the input
        GroupNorm, writes grad_x and reduces the gradients of the folded score weights U[C,16] and cpos[B,T,16];
     F  the chain from (grad_U, grad_cpos, grad_pe) to the state_dict tensors (Q, fc1_k, inconv, in_norm,
-       positional tables) runs through a differentiable torch restatement of the weight folding on [16, 256]-sized
-       tensors.
-  No [N, T, D] activation is ever materialised.  Encoders without ``inconv`` (d_model=None) keep the older
-  torch-recompute backward (``ltae_torch``), which is also what the gradient tests compare against.
+       positional tables): the adjoint of the weight folding of ``csrc/c2s_ltae_prep.cu`` on [16, 256]-sized
+       tensors, plus ``c2s_ltae_inconv_grad`` for the direct in-projection terms.
+  No [N, T, D] activation is ever materialised.  There is no torch fallback: encoders without ``inconv``
+  (d_model=None) and output GroupNorm groups wider than 16 channels raise in training (forward-only support).
 """
 from __future__ import annotations
 
 from typing import Dict, Optional
-
-import os
 
 import torch
 import torch.nn.functional as F
@@ -48,7 +46,7 @@ class AggregateFunction(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# differentiable restatement of the encoder used ONLY by LtaeFunction.backward (interim, see module docstring)
+# positional table [B,T,D] on the device: stage F needs it (and its autograd graph for learnable tables)
 # ------------------------------------------------------------------------------------------------------------
 def _positional(cfg: Dict, P: Dict[str, torch.Tensor], positions: torch.Tensor, n_rows_per_sample: int):
     """[B,T,D] positional table (identical for every pixel of a sample; positional_encoding.py:25-73)."""
@@ -71,47 +69,6 @@ def _positional(cfg: Dict, P: Dict[str, torch.Tensor], positions: torch.Tensor, 
     if cfg["pe_abs"]:
         return primary(positions[..., 0]) + doy(positions[..., 1], P["pe_abs_fc_weight"], P["pe_abs_fc_bias"])
     return primary(positions)
-
-
-def ltae_torch(x, positions, pad_mask, P: Dict[str, Optional[torch.Tensor]], cfg: Dict, attn_keep=None, mlp_keep=None):
-    """Differentiable evaluation of LTAE / LTAE4WTAE with device tensors (fp32 math).  Returns (out | None, attn)."""
-    b, t, c, hh, ww = x.shape
-    h, dk, D = cfg["n_head"], cfg["d_k"], cfg["d_model"]
-    n = b * hh * ww
-    rows = x.float().permute(0, 3, 4, 1, 2).reshape(n, t, c)
-    e = F.group_norm(rows.permute(0, 2, 1), h, P["in_norm_weight"], P["in_norm_bias"], cfg["gn_eps"]).permute(0, 2, 1)
-    if cfg["has_inconv"]:  # 1x1 Conv1d == per-row Linear; F.linear stays in fp32 (cuDNN convolutions may use TF32)
-        e = F.linear(e, P["inconv_weight"].reshape(D, c), P["inconv_bias"])  # [N,T,D]
-    if cfg["pe_mode"] != _lib.PE_NONE:
-        pe = _positional(cfg, P, positions, hh * ww)  # [B,T,D]
-        e = (e.view(b, hh * ww, t, D) + pe[:, None]).view(n, t, D)
-    k = F.linear(e, P["key_weight"], P["key_bias"]).view(n, t, h, dk)
-    s = torch.einsum("hk,nthk->hnt", P["query"].reshape(h, dk), k) / (dk ** 0.5)
-    if pad_mask is not None:
-        pr = pad_mask.bool()[:, None, :].expand(b, hh * ww, t).reshape(n, t)
-        s = s.masked_fill(pr[None], -1e6)
-    a = torch.softmax(s, dim=2)  # [h,N,T]
-    if attn_keep is not None:
-        keep = attn_keep.view(h, b, t, hh * ww).permute(0, 1, 3, 2).reshape(h, n, t)
-        a = a * keep.to(a.dtype) * cfg["attn_keep_scale"]
-    attn = a.view(h, b, hh, ww, t).permute(0, 1, 4, 2, 3)
-    if cfg["attn_only"]:
-        return None, attn
-    v = e.view(n, t, h, D // h)
-    o = torch.einsum("hnt,nthd->nhd", a, v).reshape(n, D)
-    y = F.linear(o, P["mlp_weight"], P["mlp_bias"])
-    if cfg["bn_batch_stats"]:
-        y = F.batch_norm(y, None, None, P["bn_weight"], P["bn_bias"], True, 0.0, cfg["bn_eps"])
-    else:
-        y = F.batch_norm(y, P["bn_running_mean"], P["bn_running_var"], P["bn_weight"], P["bn_bias"], False, 0.0,
-                         cfg["bn_eps"])
-    y = F.relu(y)
-    if mlp_keep is not None:
-        mk = mlp_keep.view(b, -1, hh * ww).permute(0, 2, 1).reshape(n, -1)
-        y = y * mk.to(y.dtype) * cfg["mlp_keep_scale"]
-    y = F.group_norm(y[:, :, None], h, P["out_norm_weight"], P["out_norm_bias"], cfg["gn_eps"])[:, :, 0]
-    out = y.view(b, hh, ww, -1).permute(0, 3, 1, 2)
-    return out, attn
 
 
 _GRAD_PARAM_ORDER = tuple(_lib.LTAE_PARAM_FIELDS)
@@ -148,7 +105,10 @@ def _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params
     if not attn_only:
         if g_out is None:
             g_o = torch.zeros((n, D), dtype=torch.float32, device=x.device)
-        elif cfg["c_out"] // h <= 16 and os.environ.get("C2S_LTAE_TORCH_MLP_BACKWARD") is None:
+        else:
+            if cfg["c_out"] // h > 16:
+                raise _lib.C2SError(f"crop2seg_b200: L-TAE backward supports out_norm groups of at most 16 channels "
+                                    f"(mlp[-1]={cfg['c_out']}, n_head={h}); there is no torch fallback")
             if cfg["bn_batch_stats"]:
                 mean, var = ctx.bn_stats
             else:
@@ -161,31 +121,12 @@ def _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params
             for k in ("mlp_weight", "mlp_bias", "bn_weight", "bn_bias", "out_norm_weight", "out_norm_bias"):
                 if need[k]:
                     grads[k] = m_res[k]
-        else:  # more than 16 channels per out_norm group: torch autograd on the small rows
-            with torch.enable_grad():
-                o = ctx.o_rows.detach().requires_grad_(True)
-                names = ("mlp_weight", "mlp_bias", "bn_weight", "bn_bias", "out_norm_weight", "out_norm_bias")
-                L = {k: raw[k].detach().float().requires_grad_(bool(need[k])) for k in names}
-                y = F.linear(o, L["mlp_weight"], L["mlp_bias"])
-                if cfg["bn_batch_stats"]:
-                    y = F.batch_norm(y, None, None, L["bn_weight"], L["bn_bias"], True, 0.0, cfg["bn_eps"])
-                else:
-                    y = F.batch_norm(y, raw["bn_running_mean"].float(), raw["bn_running_var"].float(), L["bn_weight"],
-                                     L["bn_bias"], False, 0.0, cfg["bn_eps"])
-                y = F.relu(y)
-                if mlp_keep is not None:
-                    mk = mlp_keep.view(b, -1, hh * ww).permute(0, 2, 1).reshape(n, -1)
-                    y = y * mk.to(y.dtype) * cfg["mlp_keep_scale"]
-                y = F.group_norm(y[:, :, None], h, L["out_norm_weight"], L["out_norm_bias"], cfg["gn_eps"])[:, :, 0]
-                out = y.view(b, hh, ww, -1).permute(0, 3, 1, 2)
-                wanted = [o] + [L[k] for k in names if need[k]]
-                got = list(torch.autograd.grad(out, wanted, g_out.to(out.dtype), allow_unused=True))
-            g_o = got.pop(0)
-            for k in names:
-                if need[k]:
-                    grads[k] = got.pop(0)
 
     # ---- stage A: the CUDA kernel over the features ------------------------------------------------------------
+    if attn_only and g_attn is None:  # LTAE4WTAE whose attention received no gradient: everything upstream is zero
+        gx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
+        gparams = [torch.zeros_like(p) if (p is not None and need[k]) else None for k, p in zip(_GRAD_PARAM_ORDER, params)]
+        return (gx, None, None, None, None, None, *gparams)
     pe_learnable = any(need.get(k) for k in ("pe_fc_weight", "pe_fc_bias", "pe_abs_fc_weight", "pe_abs_fc_bias"))
     res = ops.ltae_backward(
         x, positions, pad_mask, raw, g_o, g_attn, n_head=h, d_k=cfg["d_k"], d_model=D, has_inconv=True,
@@ -272,7 +213,9 @@ class LtaeFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, positions, pad_mask, attn_keep, mlp_keep, cfg, *params):
         P = dict(zip(_GRAD_PARAM_ORDER, params))
-        ctx.cuda_backward = bool(cfg["has_inconv"]) and os.environ.get("C2S_LTAE_TORCH_BACKWARD") is None
+        # d_model=None (tae.py:398-403: no inconv) is served in the forward only; the reference's shipped models always
+        # build the in-projection (utae.py:179-189, wtae.py:196-207, timeunet.py:155-164).  backward() raises for it.
+        ctx.cuda_backward = bool(cfg["has_inconv"])
         res = ops.ltae_forward(
             x, positions, pad_mask, P, n_head=cfg["n_head"], d_k=cfg["d_k"], d_model=cfg["d_model"],
             has_inconv=cfg["has_inconv"], c_out=cfg["c_out"], pe_mode=cfg["pe_mode"], pe_abs=cfg["pe_abs"],
@@ -305,38 +248,7 @@ class LtaeFunction(torch.autograd.Function):
         positions, pad_mask, attn_keep, mlp_keep = ctx.opt
         params = [rest.pop(0) if present else None for present in ctx.present]
         g_out, g_attn = grads[0], grads[1]
-        if ctx.cuda_backward:
-            return _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params, g_out, g_attn)
-        with torch.enable_grad():
-            xr = x.detach().requires_grad_(ctx.needs_input_grad[0])
-            leaves, P = [], {}
-            for name, p, need in zip(_GRAD_PARAM_ORDER, params, ctx.needs_input_grad[6:]):
-                if p is None:
-                    P[name] = None
-                    continue
-                q = p.detach().float()
-                if need and q.is_floating_point():
-                    q.requires_grad_(True)
-                P[name] = q
-                leaves.append((name, q, need))
-            out, attn = ltae_torch(xr, positions, pad_mask, P, cfg, attn_keep, mlp_keep)
-            outs, gouts = [], []
-            if g_out is not None and out is not None:
-                outs.append(out)
-                gouts.append(g_out.to(out.dtype))
-            if g_attn is not None:
-                outs.append(attn)
-                gouts.append(g_attn.to(attn.dtype))
-            wanted = ([xr] if ctx.needs_input_grad[0] else []) + [q for _, q, need in leaves if need and q.requires_grad]
-            got = torch.autograd.grad(outs, wanted, gouts, allow_unused=True) if outs and wanted else ()
-        got = list(got)
-        gx = got.pop(0).to(x.dtype) if ctx.needs_input_grad[0] and got else None
-        gparams = []
-        lookup = {}
-        for name, q, need in leaves:
-            if need and q.requires_grad:
-                lookup[name] = got.pop(0) if got else None
-        for name, p in zip(_GRAD_PARAM_ORDER, params):
-            g = lookup.get(name)
-            gparams.append(None if g is None or p is None else g.to(p.dtype).reshape(p.shape))
-        return (gx, None, None, None, None, None, *gparams)
+        if not ctx.cuda_backward:
+            raise _lib.C2SError("crop2seg_b200: the L-TAE backward needs the in-projection (d_model is not None); "
+                                "there is no torch fallback for encoders without inconv")
+        return _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params, g_out, g_attn)

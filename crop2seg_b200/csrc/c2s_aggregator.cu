@@ -490,11 +490,7 @@ int launch_pipe_st(const AggArgs& a, int n_consumers, int n_stages, int tap_floa
   constexpr int VEC = Elem<T>::kVec;
   const int pblocks = a.hw / (n_consumers * VEC);
   const size_t smem = static_cast<size_t>(n_stages) * (static_cast<size_t>(kPipeCPT) * n_consumers * 16 + (TAPS ? tap_floats * 4 : 0));
-  static bool attr_done = false;  // per instantiation; the value is the same on every call
-  if (!attr_done) {
-    C2S_CUDA(cudaFuncSetAttribute(agg_pipe_kernel<T, S, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 13 * 16384));
-    attr_done = true;
-  }
+  C2S_SMEM_ATTR((agg_pipe_kernel<T, S, TAPS>), 13 * 16384);  // once per instantiation and device
   dim3 grid((a.C / kPipeCPT) * pblocks, a.B);
   agg_pipe_kernel<T, S, TAPS><<<grid, n_consumers + 32, smem, stream>>>(a, n_stages, n_consumers, pblocks, tap_floats);
   C2S_LAUNCH_CHECK(name);
@@ -509,9 +505,9 @@ int launch_pipe_s(const AggArgs& a, int n_consumers, int n_stages, cudaStream_t 
   int rows_att = rows_out / S + 3;
   rows_att = rows_att > a.ha ? a.ha : rows_att;
   const int tap_floats = ((rows_att * a.wa + 3) / 4) * 4;
-  const bool taps = getenv("C2S_AGG_GLOBAL_TAPS") == nullptr && a.wa % 4 == 0 && reinterpret_cast<uintptr_t>(a.attn) % 16 == 0 &&
+  const bool taps = option(C2S_OPT_AGG_TAPS) == 0 && a.wa % 4 == 0 && reinterpret_cast<uintptr_t>(a.attn) % 16 == 0 &&
                     tap_floats <= 1024;
-  if (taps)  // the tuning hook may ask for more stages than fit once the rows ride along
+  if (taps)  // fewer stages if they do not fit once the rows ride along
     while (n_stages > 2 && static_cast<size_t>(n_stages) * (static_cast<size_t>(kPipeCPT) * n_consumers * 16 + tap_floats * 4) > 13 * 16384)
       --n_stages;
   return taps ? launch_pipe_st<T, S, true>(a, n_consumers, n_stages, tap_floats, stream, name)
@@ -858,7 +854,7 @@ EncodeTiledFn agg_encode_fn() {
 template <int S, bool TAPS>
 int launch_skipconv_t(const CUtensorMap& map_x, const CUtensorMap& map_att, const SkipConvArgs& k, cudaStream_t stream, const char* name) {
   const size_t smem = static_cast<size_t>(k.n_stages) * (kScStageBytes + 16 * k.tap_floats * 4) + kScC * kScTileStride;
-  C2S_CUDA(cudaFuncSetAttribute(agg_skipconv_kernel<S, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  C2S_SMEM_ATTR((agg_skipconv_kernel<S, TAPS>), 227 * 1024);  // once per instantiation and device (smem varies per call)
   dim3 grid(k.a.hw / kScPB, k.a.B);
   agg_skipconv_kernel<S, TAPS><<<grid, kScConsumers + 32, smem, stream>>>(map_x, map_att, k);
   C2S_LAUNCH_CHECK(name);
@@ -970,16 +966,12 @@ int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, con
   if (vec == 1 && scale_class > 0) scale_class = 0;
 
   // pipelined (bulk-copy) variant: power-of-two up-sampling, 4-channel head groups, whole 16-byte vectors
-  const bool no_pipe = getenv("C2S_AGG_NO_PIPE") != nullptr;  // test hook: A/B against the register kernel
-  const int env_stages = getenv("C2S_AGG_STAGES") ? atoi(getenv("C2S_AGG_STAGES")) : 0;
+  const bool no_pipe = option(C2S_OPT_AGG_KERNEL) == 1;  // parity tests: A/B against the register kernel
   if (!no_pipe && scale_class > 0 && vec == vec_full && a.cpg % kPipeCPT == 0) {
     const int vecs = a.hw / vec;
-    const int env_cons = getenv("C2S_AGG_CONSUMERS") ? atoi(getenv("C2S_AGG_CONSUMERS")) : 0;  // tuning hook
-    const int max_cons = (env_cons >= 64 && env_cons <= kPipeMaxConsumers && a.hw <= 4096) ? env_cons : kPipeMaxConsumers;
-    int n_consumers = vecs < max_cons ? vecs : max_cons;
+    int n_consumers = vecs < kPipeMaxConsumers ? vecs : kPipeMaxConsumers;
     if (n_consumers >= 64 && n_consumers % 32 == 0 && vecs % n_consumers == 0) {
-      int n_stages = env_stages > 0 ? env_stages : (bf16 ? 3 : 4);  // 16 KB stages; bf16: 3 (x8: three CTAs per SM = 144 KB, the rest stays L1 for the attention taps: 0.927 vs 0.967 ms with 4)
-      n_stages = n_stages > 16 ? 16 : (n_stages < 2 ? 2 : n_stages);
+      int n_stages = bf16 ? 3 : 4;  // 16 KB stages; bf16: 3 (x8: three CTAs per SM = 144 KB, the rest stays L1 for the attention taps: 0.927 vs 0.967 ms with 4)
       while (static_cast<size_t>(n_stages) * kPipeCPT * n_consumers * 16 > 12 * 16384) --n_stages;
       return bf16 ? launch_pipe<__nv_bfloat16>(a, scale_class, n_consumers, n_stages, stream)
                   : launch_pipe<float>(a, scale_class, n_consumers, n_stages, stream);
@@ -1046,7 +1038,7 @@ int c2s_agg_skipconv_forward(const c2s_agg_desc* d, const void* x, const float* 
     rows_att = rows_att > d->ha ? d->ha : rows_att;
     const int tap_floats = ((rows_att * d->wa + 3) / 4) * 4;
     // x2: measured slower with staged taps here (0.151 vs 0.109 ms at 32 x 32), so that level keeps the global-memory taps
-    const bool taps = getenv("C2S_AGG_GLOBAL_TAPS") == nullptr && d->wa % 4 == 0 && reinterpret_cast<uintptr_t>(attn) % 16 == 0 &&
+    const bool taps = option(C2S_OPT_AGG_TAPS) == 0 && d->wa % 4 == 0 && reinterpret_cast<uintptr_t>(attn) % 16 == 0 &&
                       tap_floats <= 256 && scale_class >= 4;
     k.tap_floats = taps ? tap_floats : 0;
   }

@@ -501,11 +501,7 @@ template <typename T, int S, bool TAPS>
 int launch_bwd_pipe_st(const AggBwdArgs& b, int n_consumers, int n_stages, int pblocks, int tap_floats, cudaStream_t stream,
                        const char* name) {
   const size_t smem = static_cast<size_t>(n_stages) * (static_cast<size_t>(kBwdPipeCPT) * n_consumers * 16 + (TAPS ? tap_floats * 4 : 0));
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    C2S_CUDA(cudaFuncSetAttribute(agg_backward_pipe_kernel<T, S, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 13 * 16384));
-    attr_done = true;
-  }
+  C2S_SMEM_ATTR((agg_backward_pipe_kernel<T, S, TAPS>), 13 * 16384);  // once per instantiation and device
   dim3 grid((b.C / kBwdPipeCPT) * pblocks, b.B * b.t_chunks);
   agg_backward_pipe_kernel<T, S, TAPS><<<grid, n_consumers + 32, smem, stream>>>(b, n_stages, n_consumers, pblocks, tap_floats);
   C2S_LAUNCH_CHECK(name);
@@ -527,9 +523,9 @@ int launch_bwd_pipe_s(const AggBwdArgs& a, int n_consumers, int n_stages, cudaSt
   int rows_att = rows_out / S + 3;
   rows_att = rows_att > a.ha ? a.ha : rows_att;
   const int tap_floats = ((rows_att * a.wa + 3) / 4) * 4;
-  const bool taps = getenv("C2S_AGG_GLOBAL_TAPS") == nullptr && a.wa % 4 == 0 && reinterpret_cast<uintptr_t>(a.attn) % 16 == 0 &&
+  const bool taps = option(C2S_OPT_AGG_TAPS) == 0 && a.wa % 4 == 0 && reinterpret_cast<uintptr_t>(a.attn) % 16 == 0 &&
                     tap_floats <= 1024;
-  if (taps)  // the tuning hook may ask for more stages than fit once the rows ride along
+  if (taps)  // fewer stages if they do not fit once the rows ride along
     while (n_stages > 2 && static_cast<size_t>(n_stages) * (static_cast<size_t>(kBwdPipeCPT) * n_consumers * 16 + tap_floats * 4) > 13 * 16384)
       --n_stages;
   return taps ? launch_bwd_pipe_st<T, S, true>(b, n_consumers, n_stages, pblocks, tap_floats, stream, name)
@@ -557,7 +553,6 @@ int launch_bwd(const AggBwdArgs& a, cudaStream_t stream, const char* name) {
   const long long ctas = static_cast<long long>(ceil_div(a.vecs_per_plane, kBwdThreads)) * (a.C / CPT) * a.B;
   int chunks = 1;  // enough CTAs for ~8 per SM, at least 8 frames per CTA (the prologue loads grad_out once per CTA)
   while (ctas * chunks < 8 * 148 && ceil_div(a.T, chunks * 2) >= 8 && static_cast<long long>(a.B) * chunks * 2 <= 65535) chunks *= 2;
-  if (getenv("C2S_AGG_BWD_CHUNKS") != nullptr) chunks = atoi(getenv("C2S_AGG_BWD_CHUNKS")) > 0 ? atoi(getenv("C2S_AGG_BWD_CHUNKS")) : 1;  // tuning hook
   b.t_per_chunk = ceil_div(a.T, chunks);
   b.t_chunks = ceil_div(a.T, b.t_per_chunk);
   dim3 grid(ceil_div(a.vecs_per_plane, kBwdThreads), a.C / CPT, a.B * b.t_chunks);
@@ -668,14 +663,13 @@ int c2s_agg_backward(const c2s_agg_desc* d, const void* x, const float* attn, co
   if (scale_class > 0 && (vec == 1 || vec < scale_class)) scale_class = 0;  // whole attention cells per thread only
 
   // pipelined variant: both gradients wanted, power-of-two up-sampling with whole attention cells per thread
-  const bool no_pipe = getenv("C2S_AGG_NO_PIPE") != nullptr;  // test hook: A/B against the register kernel
+  const bool no_pipe = option(C2S_OPT_AGG_KERNEL) == 1;  // parity tests: A/B against the register kernel
   if (!no_pipe && scale_class > 0 && vec == vec_full && vec >= scale_class && a.cpg % kBwdPipeCPT == 0 && a.gx != nullptr &&
       a.gattn != nullptr && x != nullptr && a.W % vec == 0) {
     const int vecs = a.vecs_per_plane;
     int n_consumers = vecs < kBwdPipeMaxConsumers ? vecs : kBwdPipeMaxConsumers;
     if (n_consumers >= 64 && n_consumers % 32 == 0 && vecs % n_consumers == 0) {
-      int n_stages = getenv("C2S_AGG_BWD_STAGES") ? atoi(getenv("C2S_AGG_BWD_STAGES")) : 4;
-      n_stages = n_stages > 16 ? 16 : (n_stages < 2 ? 2 : n_stages);
+      int n_stages = 4;
       while (static_cast<size_t>(n_stages) * kBwdPipeCPT * n_consumers * 16 > 12 * 16384) --n_stages;
       auto go = [&](auto tag) {
         using TT = decltype(tag);

@@ -12,7 +12,21 @@ thread_local char g_error[512] = "";
 char g_kernel[128] = "";
 char g_ltae_kernel[128] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_options[3] = {{0}, {0}, {0}};
 }  // namespace
+
+int option(int which) { return (which >= 0 && which < 3) ? g_options[which].load(std::memory_order_relaxed) : 0; }
+
+// cudaFuncSetAttribute is a per-device setting: `done` holds one flag per device ordinal for one kernel.
+int set_max_dynamic_smem(const void* func, int bytes, std::atomic<unsigned long long>* done) {
+  int dev = 0;
+  C2S_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done->load(std::memory_order_acquire) & bit) return C2S_OK;
+  C2S_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done->fetch_or(bit, std::memory_order_release);
+  return C2S_OK;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -68,6 +82,18 @@ const char* c2s_last_error(void) { return c2s::g_error; }
 int64_t c2s_launch_count(void) { return c2s::g_launches.load(); }
 
 void c2s_reset_launch_count(void) { c2s::g_launches.store(0); }
+
+int c2s_set_option(int option, int value) {
+  const int max_value[3] = {C2S_LTAE_KERNEL_STREAM, 1, 1};
+  if (option < 0 || option >= 3 || value < 0 || value > max_value[option]) {
+    c2s::set_error("c2s_set_option: unknown option %d / value %d", option, value);
+    return C2S_ERR_BAD_ARGUMENT;
+  }
+  c2s::g_options[option].store(value);
+  return C2S_OK;
+}
+
+int c2s_get_option(int option) { return (option >= 0 && option < 3) ? c2s::g_options[option].load() : -1; }
 
 const char* c2s_last_kernel(void) { return c2s::g_kernel; }
 const char* c2s_last_ltae_kernel(void) { return c2s::g_ltae_kernel; }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -19,6 +20,16 @@ void set_error(const char* fmt, ...);
 void note_launch(const char* kernel_name);
 // C2S_OK when the current device is an sm_100 part, C2S_ERR_NO_DEVICE (with message) otherwise.
 int check_device();
+// current value of a c2s_option (c2s_set_option); 0 = production behaviour
+int option(int which);
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device): `done` is a static flag word of the caller
+int set_max_dynamic_smem(const void* func, int bytes, std::atomic<unsigned long long>* done);
+#define C2S_SMEM_ATTR(kernel, bytes)                                                                \
+  do {                                                                                              \
+    static std::atomic<unsigned long long> done__{0};                                               \
+    const int st__ = ::c2s::set_max_dynamic_smem(reinterpret_cast<const void*>(kernel), static_cast<int>(bytes), &done__); \
+    if (st__ != C2S_OK) return st__;                                                                \
+  } while (0)
 
 #define C2S_CHECK_ARG(cond, ...)        \
   do {                                  \

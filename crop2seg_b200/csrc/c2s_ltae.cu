@@ -506,12 +506,10 @@ int launch_general(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void*
   const long long n_tiles = static_cast<long long>(d.B) * a.tiles_per_b;
   if (n_tiles > 0x7fffffffll) C2S_UNSUPPORTED("c2s_ltae_forward: too many pixel tiles");
   if (d.dtype == C2S_BF16) {
-    C2S_CUDA(cudaFuncSetAttribute(ltae_forward_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem_bytes)));
+    C2S_SMEM_ATTR(ltae_forward_kernel<__nv_bfloat16>, 227 * 1024);
     ltae_forward_kernel<__nv_bfloat16><<<static_cast<unsigned>(n_tiles), kLtaeThreads, smem_bytes, stream>>>(a);
   } else {
-    C2S_CUDA(cudaFuncSetAttribute(ltae_forward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem_bytes)));
+    C2S_SMEM_ATTR(ltae_forward_kernel<float>, 227 * 1024);
     ltae_forward_kernel<float><<<static_cast<unsigned>(n_tiles), kLtaeThreads, smem_bytes, stream>>>(a);
   }
   C2S_LAUNCH_CHECK("ltae_forward<general>");
@@ -607,25 +605,18 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
                 "c2s_ltae_forward: workspace of %zu bytes needed, %zu given", lay.total * sizeof(float),
                 workspace_bytes);
   float* ws = static_cast<float*>(workspace);
-  const bool force_general = getenv("C2S_LTAE_FORCE_GENERAL") != nullptr;  // test hook: compare both kernels
-  const bool use_mma = !force_general && ltae_mma_eligible(d, x, out);
-  const bool use_fa = use_mma && (!ltae_tc_enabled() || p.save_o != nullptr) && ltae_fa_eligible(d);
+  const int choice = option(C2S_OPT_LTAE_KERNEL);  // parity tests compare the kernels; 0 = automatic
+  const bool use_fa = choice != C2S_LTAE_KERNEL_GENERAL && ltae_fa_eligible(d, x, out);
   // the reuse flag is honoured only if the previous call on this very workspace went through the same (persistent) path
   const bool was_prepared = fa_prepared(workspace, /*mark=*/use_fa);  // every call updates the set: another path unmarks
   if (!(use_fa && was_prepared)) d.flags &= ~C2S_LTAE_REUSE_FOLDED;
-  status = ltae_prepare(d, p, positions, ws, lay, /*need_transposed=*/!use_mma, stream);
+  status = ltae_prepare(d, p, positions, ws, lay, /*need_transposed=*/!use_fa, stream);
   if (status != C2S_OK) return status;
 
   const int hw = d.H * d.W;
   float* ypre = train ? ws + lay.ypre : nullptr;
   if (use_fa) {
     status = ltae_fa_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.fa, stream);
-    if (status != C2S_OK) return status;
-  } else if (use_mma && ltae_tc_enabled() && ltae_tc_eligible(d) && p.save_o == nullptr) {
-    status = ltae_tc_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.tca, stream);
-    if (status != C2S_OK) return status;
-  } else if (use_mma) {
-    status = ltae_mma_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.frag, stream);
     if (status != C2S_OK) return status;
   } else {
     status = launch_general(d, p, x, pad_mask, out, attn, ws, lay, stream);

@@ -692,12 +692,10 @@ int c2s_ltae_backward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const 
   const long long n_tiles = static_cast<long long>(d.B) * a.tiles_per_b;
   if (n_tiles > 0x7fffffffll) C2S_UNSUPPORTED("c2s_ltae_backward: too many pixel tiles");
   if (d.dtype == C2S_BF16) {
-    C2S_CUDA(cudaFuncSetAttribute(ltae_backward_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem_bytes)));
+    C2S_SMEM_ATTR(ltae_backward_kernel<__nv_bfloat16>, 227 * 1024);
     ltae_backward_kernel<__nv_bfloat16><<<static_cast<unsigned>(n_tiles), kBwdThreads, smem_bytes, stream>>>(a);
   } else {
-    C2S_CUDA(cudaFuncSetAttribute(ltae_backward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem_bytes)));
+    C2S_SMEM_ATTR(ltae_backward_kernel<float>, 227 * 1024);
     ltae_backward_kernel<float><<<static_cast<unsigned>(n_tiles), kBwdThreads, smem_bytes, stream>>>(a);
   }
   C2S_LAUNCH_CHECK("ltae_backward<general>");

@@ -910,7 +910,7 @@ template <int C, int WPP>
 int fa_launch(const CUtensorMap& map16, const CUtensorMap& map4, const CUtensorMap& map1, const FaArgs& a,
               cudaStream_t stream, const char* name) {
   using S = FaSmem<C, WPP>;
-  C2S_CUDA(cudaFuncSetAttribute(ltae_fa_kernel<C, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  C2S_SMEM_ATTR((ltae_fa_kernel<C, WPP>), S::kTotal);
   const int slots = fa_sm_count() * (WPP == 1 ? 2 : 1);  // persistent CTAs: one per SM, two for the single-warp tiles
   const int grid = a.n_tiles < slots ? a.n_tiles : slots;
   ltae_fa_kernel<C, WPP><<<static_cast<unsigned>(grid), 256 * WPP, S::kTotal, stream>>>(map16, map4, map1, a);
@@ -920,9 +920,15 @@ int fa_launch(const CUtensorMap& map16, const CUtensorMap& map4, const CUtensorM
 
 }  // namespace
 
-bool ltae_fa_eligible(const c2s_ltae_desc& d) {
-  // the caller has already checked ltae_mma_eligible (bf16, 16 heads, d_model 256, C in {64, 128}, T <= 64, ...)
-  return getenv("C2S_LTAE_MMA") == nullptr && getenv("C2S_LTAE_NO_TCGEN05") == nullptr;
+bool ltae_fa_eligible(const c2s_ltae_desc& d, const void* x, const void* out) {
+  const bool attn_only = (d.flags & C2S_LTAE_ATTN_ONLY) != 0;
+  if (d.dtype != C2S_BF16 || d.n_head != kH || d.d_model != kD || !d.has_inconv) return false;
+  if (d.C != 64 && d.C != 128) return false;
+  if (d.T > kTP || (d.H * d.W) % kPix != 0) return false;
+  if (d.pe_mode == C2S_PE_SINUSOID_LINEAR) return false;  // table differs per head chunk
+  if (!attn_only && (d.c_out % 16 != 0 || d.c_out > 256)) return false;
+  if (reinterpret_cast<uintptr_t>(x) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0) return false;
+  return true;
 }
 
 size_t ltae_fa_workspace_floats(const c2s_ltae_desc& d) {
@@ -1026,8 +1032,6 @@ int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void
   int status;
   if (C == 128)
     status = fa_launch<128, 2>(map16, map4, map1, a, stream, "ltae_forward<fa,C=128>");
-  else if (getenv("C2S_LTAE_FA_PAIR") != nullptr)  // comparison hook: two warps per pixel, double-buffered slabs
-    status = fa_launch<64, 2>(map16, map4, map1, a, stream, "ltae_forward<fa,C=64,pair>");
   else
     status = fa_launch<64, 1>(map16, map4, map1, a, stream, "ltae_forward<fa,C=64>");
   if (status != C2S_OK) return status;

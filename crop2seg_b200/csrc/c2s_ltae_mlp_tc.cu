@@ -317,7 +317,7 @@ int ltae_mlp_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, float*
   const size_t ys_bytes = static_cast<size_t>(kRows) * (d.c_out + 1) * sizeof(float);
   if (ys_bytes > smem) smem = ys_bytes;
   smem += 1024;  // alignment slack for the 1024-byte swizzle atoms
-  C2S_CUDA(cudaFuncSetAttribute(ltae_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  C2S_SMEM_ATTR(ltae_mlp_tc_kernel, 227 * 1024);
   ltae_mlp_tc_kernel<<<ceil_div(rows, kRows), kTcThreads, smem, stream>>>(m_ohi, m_olo, m_whi, m_wlo, a);
   C2S_LAUNCH_CHECK("ltae_mlp<tcgen05>");
   return C2S_OK;

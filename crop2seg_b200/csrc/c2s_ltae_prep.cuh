@@ -32,17 +32,13 @@ struct LtaeWorkspace {
   size_t cpos;   // [B, T, kMaxHeads]
   size_t ypre;   // [B*H*W, c_out]   pre-BatchNorm MLP output (training mode only)
   size_t bnpart; // [2, c_out, parts] partial batch statistics (training mode only)
-  size_t frag;   // fragment-ordered weights of the tensor-core path
   size_t tc;     // tcgen05 MLP: o hi/lo rows + mlp weight hi/lo
-  size_t tca;    // tcgen05 attention: score weight tiles
-  size_t fa;     // persistent TMA kernel: score / in-projection / MLP weight fragments, scales
+  size_t fa;     // tensor-core attention kernels: score / in-projection weight fragments, scales, frame masks
   size_t total;  // floats
 };
 
 inline size_t align64(size_t n) { return (n + 63) & ~static_cast<size_t>(63); }
-size_t ltae_mma_workspace_floats(const c2s_ltae_desc& d);
 size_t ltae_mlp_tc_workspace_floats(const c2s_ltae_desc& d);
-size_t ltae_tc_workspace_floats(const c2s_ltae_desc& d);
 size_t ltae_fa_workspace_floats(const c2s_ltae_desc& d);
 
 inline LtaeWorkspace ltae_workspace(const c2s_ltae_desc& d) {
@@ -68,20 +64,11 @@ inline LtaeWorkspace ltae_workspace(const c2s_ltae_desc& d) {
   const bool train = (d.flags & C2S_LTAE_BN_BATCH_STATS) != 0 && !attn_only;
   w.ypre = take(train ? static_cast<size_t>(d.B) * d.H * d.W * co : 0);
   w.bnpart = take(train ? 2 * co * 1024 : 0);
-  w.frag = take(ltae_mma_workspace_floats(d));
   w.tc = take(ltae_mlp_tc_workspace_floats(d));
-  w.tca = take(ltae_tc_workspace_floats(d));
   w.fa = take(ltae_fa_workspace_floats(d));
   w.total = off;
   return w;
 }
-
-// Tensor-core path for the shipped shapes (c2s_ltae_mma.cu)
-bool ltae_mma_eligible(const c2s_ltae_desc& d, const void* x, const void* out);
-size_t ltae_mma_workspace_floats(const c2s_ltae_desc& d);
-int ltae_mma_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask,
-                     void* out, float* attn, float* ws, const LtaeWorkspace& lay, float* frag_ws,
-                     cudaStream_t stream);
 
 // tcgen05 row GEMM for the MLP + BatchNorm + ReLU + output GroupNorm (c2s_ltae_mlp_tc.cu)
 void ltae_mlp_tc_buffers(const c2s_ltae_desc& d, float* ws, __nv_bfloat16** o_hi, __nv_bfloat16** o_lo,
@@ -89,14 +76,8 @@ void ltae_mlp_tc_buffers(const c2s_ltae_desc& d, float* ws, __nv_bfloat16** o_hi
 int ltae_mlp_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, float* tc_ws, const float* bnf, float* ypre,
                         void* out, cudaStream_t stream);
 
-// tcgen05 attention kernel (c2s_ltae_tc.cu), opt-in with C2S_LTAE_TC while it only covers the attention-only encoder
-bool ltae_tc_enabled();
-bool ltae_tc_eligible(const c2s_ltae_desc& d);
-int ltae_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask, void* out,
-                    float* attn, float* ws, const LtaeWorkspace& lay, float* tc_ws, cudaStream_t stream);
-
-// persistent TMA-fed kernel (c2s_ltae_fa.cu): the default for the shapes ltae_mma_eligible accepts
-bool ltae_fa_eligible(const c2s_ltae_desc& d);
+// persistent TMA-fed whole-slab kernel (c2s_ltae_fa.cu): bf16, 16 heads, d_model 256, C in {64, 128}, T <= 64, ...
+bool ltae_fa_eligible(const c2s_ltae_desc& d, const void* x, const void* out);
 int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* x, const uint8_t* pad_mask, void* out,
                     float* attn, float* ws, const LtaeWorkspace& lay, float* fa_ws, cudaStream_t stream);
 

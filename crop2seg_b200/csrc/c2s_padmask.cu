@@ -88,6 +88,8 @@ extern "C" int c2s_pad_mask(const void* x, int32_t dtype, int64_t n_frames, int6
   const size_t esize = dtype == C2S_BF16 ? 2 : 4;
   // whole 16-byte vectors need every frame to start on a 16-byte boundary
   const int vectorised = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && ((static_cast<size_t>(frame_elems) * esize) % 16 == 0);
+  // torch compares a bf16 tensor with the scalar rounded to bf16 (`input == pad_value`, utae.py:201): do the same
+  if (dtype == C2S_BF16) pad_value = __bfloat162float(__float2bfloat16_rn(pad_value));
   if (dtype == C2S_BF16)
     pad_mask_kernel<__nv_bfloat16><<<static_cast<unsigned>(n_frames), kPadThreads, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x), frame_elems, pad_value, mask, vectorised);

@@ -27,6 +27,42 @@ from . import _lib, ops
 #: ScaledDotProductAttention(attn_dropout=0.1) -- tae.py:816-819; applied only in training mode
 ATTENTION_DROPOUT = 0.1
 
+_injected_masks = None
+
+
+class injected_dropout:
+    """``with injected_dropout(attn_keep, mlp_keep): module(x, ...)`` -- training-mode forwards inside the block use
+    these keep masks (uint8/bool, ``attn_keep`` [n_head,B,T,H,W], ``mlp_keep`` [B,C',H,W] or None) instead of drawing
+    them.  Parity tests replay the reference's own dropout realisation this way (tests/golden/make_train_golden.py)."""
+
+    def __init__(self, attn_keep, mlp_keep=None):
+        self.masks = (attn_keep, mlp_keep)
+
+    def __enter__(self):
+        global _injected_masks
+        self.old, _injected_masks = _injected_masks, self.masks
+        return self
+
+    def __exit__(self, *exc):
+        global _injected_masks
+        _injected_masks = self.old
+
+
+def _draw_keep(shape, p, device, which):
+    """uint8 keep mask of a dropout with rate p (None when p == 0), or the injected one."""
+    if p <= 0:
+        return None
+    if _injected_masks is not None and _injected_masks[which] is not None:
+        m = _injected_masks[which]
+        if tuple(m.shape) != tuple(shape):
+            raise RuntimeError(f"crop2seg_b200: injected dropout mask has shape {tuple(m.shape)}, expected {tuple(shape)}")
+        return m.to(device=device, dtype=torch.uint8)
+    return (torch.rand(shape, device=device) >= p).to(torch.uint8)
+
+
+#: construction-time defaults of the encoder attributes, set by ``crop2seg_b200.install(...)``
+_DEFAULTS = {"assume_zero_padded": False, "return_attention": True}
+
 
 class _Placeholder(nn.Module):
     """Parameter-free stand-in for einops' ``Rearrange`` inside ``mlp`` (keeps the indices 0..5)."""
@@ -102,9 +138,14 @@ class _LTAEBase(nn.Module):
             self.positional_encoder = None
         self.attention_head = LightweightMultiHeadAttention(n_head=n_head, d_k=d_k, d_in=self.d_model, n=num_queries)
         self.in_norm = nn.GroupNorm(num_groups=n_head, num_channels=in_channels)
-        #: set by the caller (``crop2seg_b200.install`` does) when padded frames of x are exactly zero, as
-        #: ``smart_forward`` guarantees with pad_value=0 (temp_shared_block.py:30-40); padded frames are then not read
-        self.assume_zero_padded = False
+        #: set by the caller (``crop2seg_b200.install(assume_zero_padded=True)`` does it for every encoder it builds)
+        #: when padded frames of x are exactly zero, as ``smart_forward`` guarantees with pad_value=0
+        #: (temp_shared_block.py:30-40); padded frames are then not read
+        self.assume_zero_padded = _DEFAULTS["assume_zero_padded"]
+        #: model-level ``return_att`` (utae.py:200, timeunet.py:169) is not visible to the encoder: a caller that never
+        #: consumes the attention (``TimeUNet_v1.forward`` drops it unless return_att, timeunet.py:178-205) sets this to
+        #: False and ``forward`` then skips the [n_head,B,T,H,W] store and returns ``(out, None)``
+        self.return_attention = _DEFAULTS["return_attention"]
         #: eval mode keeps the folded weights between calls while no parameter changes (``Tensor._version`` and
         #: ``data_ptr`` of every parameter / buffer); writes through ``.data`` bypass the version counters -- call
         #: ``invalidate_folded_weights()`` after those, or set this to False
@@ -201,8 +242,10 @@ class LTAE(_LTAEBase):
                  *args, **kwargs):
         super().__init__()
         widths: List[int] = copy.deepcopy(mlp)
+        # the reference never forwards its T argument to the positional encoder (tae.py:409-419): period 1000 always
         self._build_front(in_channels, n_head, d_k, d_model, positional_encoding, use_abs_rel_enc, num_queries,
-                          use_doy, add_linear, T=T)
+                          use_doy, add_linear)
+        self.T = T
         assert widths[0] == self.d_model  # tae.py:404
         self.out_norm = nn.GroupNorm(num_groups=n_head, num_channels=widths[-1])
         self.mlp = nn.Sequential(
@@ -215,15 +258,18 @@ class LTAE(_LTAEBase):
         )
         self._widths = widths
 
-    def forward(self, x, batch_positions=None, pad_mask=None, return_comp=False, return_att=True):
+    def forward(self, x, batch_positions=None, pad_mask=None, return_comp=False, return_att=None):
         """x[B,T,C,H,W] -> (out[B,C',H,W], attn[n_head,B,T,H,W]); ``return_comp`` is ignored as in tae.py:451.
 
-        ``return_att=False`` (extension) skips the attention store and returns ``(out, None)``.
+        ``return_att=False`` (extension; default: the module's ``return_attention`` attribute) skips the attention
+        store and returns ``(out, None)``.
         Training mode follows the reference: BatchNorm1d batch statistics (+ running-stat update), dropout on the
         attention before it is returned (tae.py:837) and after the MLP's ReLU (tae.py:448); the masks are drawn with
         torch's generator here and injected into the kernel.
         """
         self._check_inputs(x, batch_positions)
+        if return_att is None:
+            return_att = self.return_attention
         bn = self.mlp[2]
         train_bn = self.training or not bn.track_running_stats
         params = self._front_params(x.device)
@@ -237,8 +283,8 @@ class LTAE(_LTAEBase):
         c_out = self._widths[-1]
         attn_p = ATTENTION_DROPOUT if self.training else 0.0
         mlp_p = float(self.mlp[5].p) if self.training else 0.0
-        attn_keep = (torch.rand((self.n_head, b, t, h, w), device=x.device) >= attn_p).to(torch.uint8) if attn_p > 0 else None
-        mlp_keep = (torch.rand((b, c_out, h, w), device=x.device) >= mlp_p).to(torch.uint8) if mlp_p > 0 else None
+        attn_keep = _draw_keep((self.n_head, b, t, h, w), attn_p, x.device, 0)
+        mlp_keep = _draw_keep((b, c_out, h, w), mlp_p, x.device, 1)
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
@@ -284,7 +330,7 @@ class LTAE4WTAE(_LTAEBase):
         self._check_inputs(x, batch_positions)
         b, t, _, h, w = x.shape
         attn_p = ATTENTION_DROPOUT if self.training else 0.0
-        attn_keep = (torch.rand((self.n_head, b, t, h, w), device=x.device) >= attn_p).to(torch.uint8) if attn_p > 0 else None
+        attn_keep = _draw_keep((self.n_head, b, t, h, w), attn_p, x.device, 0)
         params = self._front_params(x.device)
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self.parameters()))

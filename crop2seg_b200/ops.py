@@ -286,7 +286,12 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
     with torch.cuda.device(dev):
         ws_bytes = lib.c2s_ltae_workspace_bytes(ctypes.byref(desc))
         ws = None
-        if folded_cache is not None and ws_bytes <= _FOLDED_CACHE_MAX_BYTES:
+        # Under CUDA-graph capture the cache is bypassed: a captured graph bakes the workspace pointer, and a cached
+        # workspace can be evicted (another shape) or go stale (weights updated) while the graph lives on.  A captured
+        # call allocates its workspace inside the capture (the graph's private pool keeps it alive) and folds the
+        # weights on every replay.
+        capturing = torch.cuda.is_current_stream_capturing()
+        if folded_cache is not None and ws_bytes <= _FOLDED_CACHE_MAX_BYTES and not capturing:
             key = (folded_key, dev, b, t, c, h, w, n_head, d_k, d_model, desc.c_out, int(has_inconv), pe_mode,
                    int(pe_abs), desc.dtype, flags, float(gn_eps), float(bn_eps))
             if folded_cache.get("key") == key and folded_cache.get("ws") is not None:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 5
+#define C2S_ABI_VERSION 6
 
 enum c2s_status {
   C2S_OK = 0,
@@ -254,6 +254,21 @@ const char* c2s_last_error(void);
  * (bench.py reports it as gpu_launches). */
 int64_t c2s_launch_count(void);
 void c2s_reset_launch_count(void);
+/* Kernel-selection switches for parity tests and A/B measurements (process-wide, value 0 = what production runs).
+ * They replace environment variables: nothing on the call path reads the environment. */
+enum c2s_option {
+  C2S_OPT_LTAE_KERNEL = 0, /* enum c2s_ltae_kernel: which kernel serves c2s_ltae_forward                       */
+  C2S_OPT_AGG_KERNEL = 1,  /* 0 = automatic, 1 = register-streaming aggregator kernels (no bulk-copy pipeline) */
+  C2S_OPT_AGG_TAPS = 2     /* 0 = automatic, 1 = bilinear taps read from global memory (no staged rows)        */
+};
+enum c2s_ltae_kernel {
+  C2S_LTAE_KERNEL_AUTO = 0,
+  C2S_LTAE_KERNEL_GENERAL = 1, /* fp32 CUDA-core kernel (c2s_ltae.cu), any shape                                   */
+  C2S_LTAE_KERNEL_SLAB = 2,    /* persistent whole-slab kernel (c2s_ltae_fa.cu) where eligible, else general       */
+  C2S_LTAE_KERNEL_STREAM = 3   /* frame-ring streaming kernel (c2s_ltae_stream.cu) where eligible, else general    */
+};
+int c2s_set_option(int option, int value); /* C2S_ERR_BAD_ARGUMENT for an unknown option / value */
+int c2s_get_option(int option);            /* current value, -1 for an unknown option            */
 /* Name of the kernel the library launched last (diagnostics). */
 const char* c2s_last_kernel(void);
 /* Name of the last L-TAE attention kernel ("ltae_forward<...>") the library launched (diagnostics: which of the

@@ -1,8 +1,9 @@
 """torch-CPU restatement of the reference L-TAE + TemporalAggregator.  TEST INFRASTRUCTURE ONLY.
 
-Second oracle and the CPU baseline of ``bench.py``: it issues the same ATen library calls the reference
+Second oracle and the CPU baseline of ``bench.py``: it issues the ATen library calls the reference
 modules make (GroupNorm, 1x1 Conv1d, Linear, matmul, softmax, bilinear Upsample -- SURVEY.md section 8c
-lists the call sites), written functionally over a ``state_dict``-keyed parameter dict, so its speed on
+lists the call sites) including the reference's materialising copies (one query per pixel row, head-major mask
+and value copies), written functionally over a ``state_dict``-keyed parameter dict, so its speed on
 the host cores is representative of the reference's own CPU path (the reference itself lives in
 ``/root/reference`` and cannot travel to the GPU box).  Like the numpy oracle it follows the as-written
 algorithm, including the [N,T,D] activations and head-major copies the fused kernels avoid.
@@ -40,10 +41,18 @@ def _doy(pos_rows, fc_w, fc_b, repeat):
     return F.linear(onehot, fc_w, fc_b).repeat(1, 1, repeat)  # :66-71
 
 
-def ltae_forward_torch(cfg, params: Dict, x, positions=None, pad_mask=None, attn_only: bool = False):
-    """Eval-mode ``LTAE.forward`` (or ``LTAE4WTAE.forward`` with ``attn_only``) on CPU tensors.
+def ltae_forward_torch(cfg, params: Dict, x, positions=None, pad_mask=None, attn_only: bool = False,
+                       training: bool = False, attn_keep=None, mlp_keep=None, attn_drop_p: float = 0.1,
+                       mlp_drop_p: float = 0.2, materialise: bool = True):
+    """``LTAE.forward`` (or ``LTAE4WTAE.forward`` with ``attn_only``) on CPU tensors, differentiable.
 
     ``cfg`` is an ``oracle.LtaeConfig``; ``params`` is keyed like the reference ``state_dict``.
+    ``training``: BatchNorm1d batch statistics (tae.py:445) and the two dropouts with INJECTED keep masks (torch's
+    generator cannot be matched by a kernel): ``attn_keep`` uint8/bool [n_head, B, T, H, W] applied to the attention
+    before it is returned (tae.py:837), ``mlp_keep`` [B, c_out, H, W] after the ReLU (tae.py:448); a missing mask means
+    no dropout.  Training mode returns ``(out, attn, (batch_mean, biased_batch_var))``.
+    ``materialise``: make the copies the reference makes (``torch.stack`` of one query per pixel row, tae.py:764;
+    ``pad_mask.repeat``, :772) so that the CPU timing is the reference's, not a cheaper one.
     """
     p = {k: _t(v) for k, v in params.items()}
     x = _t(x).float()
@@ -78,7 +87,10 @@ def ltae_forward_torch(cfg, params: Dict, x, positions=None, pad_mask=None, attn
         else:
             e = e + primary(per_pixel(pos))  # :476-479
     # LightweightMultiHeadAttention, num_queries == 1 (tae.py:760-807)
-    q = p["attention_head.Q"].reshape(h, 1, 1, dk).expand(h, n, 1, dk).reshape(h * n, 1, dk)
+    if materialise:
+        q = torch.stack([p["attention_head.Q"] for _ in range(n)], dim=1).view(-1, 1, dk)  # :764-766
+    else:
+        q = p["attention_head.Q"].reshape(h, 1, 1, dk).expand(h, n, 1, dk).reshape(h * n, 1, dk)
     k = F.linear(e, p["attention_head.fc1_k.weight"], p["attention_head.fc1_k.bias"]).view(n, t, h, dk)
     k = k.permute(2, 0, 1, 3).reshape(h * n, t, dk)
     v = torch.stack(e.split(d // h, dim=-1)).reshape(h * n, t, d // h)
@@ -86,16 +98,29 @@ def ltae_forward_torch(cfg, params: Dict, x, positions=None, pad_mask=None, attn
     if pad_rows is not None:
         s = s.masked_fill(pad_rows.repeat(h, 1).unsqueeze(1), -1e6)  # :831
     a = torch.softmax(s, dim=2)  # :836
+    if training and attn_keep is not None:  # :837 nn.Dropout(0.1): zero and rescale, BEFORE the attention is returned
+        ak = _t(attn_keep).to(torch.float32).permute(0, 1, 3, 4, 2).reshape(h * n, 1, t)
+        a = a * ak / (1.0 - attn_drop_p)
     attn = a.view(h, b, hh, ww, t).permute(0, 1, 4, 2, 3).contiguous()  # :490-493
     if attn_only:
         return attn
     o = torch.matmul(a, v).view(h, n, d // h).permute(1, 0, 2).reshape(n, d)  # :839, :796-798
     y = F.linear(o, p["mlp.0.weight"], p["mlp.0.bias"])  # :443
-    y = F.batch_norm(y, p["mlp.2.running_mean"], p["mlp.2.running_var"], p["mlp.2.weight"], p["mlp.2.bias"],
-                     False, 0.1, 1e-5)  # :445 (eval)
+    stats = None
+    if training:  # :445 batch statistics over all B*H*W rows (biased variance normalises)
+        stats = (y.mean(dim=0).detach(), y.var(dim=0, unbiased=False).detach())
+        y = F.batch_norm(y, None, None, p["mlp.2.weight"], p["mlp.2.bias"], True, 0.1, 1e-5)
+    else:
+        y = F.batch_norm(y, p["mlp.2.running_mean"], p["mlp.2.running_var"], p["mlp.2.weight"], p["mlp.2.bias"],
+                         False, 0.1, 1e-5)  # :445 (eval)
     y = F.relu(y)  # :447
+    if training and mlp_keep is not None:  # :448 nn.Dropout(0.2)
+        mk = _t(mlp_keep).to(torch.float32).permute(0, 2, 3, 1).reshape(n, -1)
+        y = y * mk / (1.0 - mlp_drop_p)
     y = F.group_norm(y[:, :, None], h, p["out_norm.weight"], p["out_norm.bias"], 1e-5)[:, :, 0]  # :488
     out = y.view(b, hh, ww, -1).permute(0, 3, 1, 2).contiguous()  # :494
+    if training:
+        return out, attn, stats
     return out, attn
 
 

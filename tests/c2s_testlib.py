@@ -95,3 +95,33 @@ def to_dev(a, device="cuda", dtype=None):
 def bf16_round(a):
     """float32 array rounded to bfloat16 and back (what a bf16 tensor of the same values holds)."""
     return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def hot_path_parity(enc, x4, xs, pos, pad, out, attn, skips, samples):
+    """Oracle check of one U-TAE-placement step at its REAL shapes, per sample: the device tensors of the samples in
+    ``samples`` are copied to the host and pushed through the numpy / torch-CPU oracles.  ``x4`` [B,T,C,h,w] and ``xs``
+    (list of [B,T,c,H,W]) are the device inputs, ``out`` / ``attn`` [heads,B,T,h,w] / ``skips`` the device outputs.
+    Returns max relative errors (max|d| / max|ref| per tensor and sample) and the pad-handling check."""
+    from oracle import ltae_forward
+    from oracle.torch_port import temporal_aggregator_torch
+    params = oracle_params(enc)
+    kw = dict(in_channels=enc.in_channels, n_head=enc.n_head, d_k=enc.d_k, mlp=list(enc._widths), d_model=enc.d_model)
+    cfg = LtaeConfig(**kw)
+    errs = {"attn": 0.0, "out": 0.0, "skips": [0.0] * len(xs), "pad_attention_exactly_zero": True, "samples": list(samples)}
+
+    def rel(a, r):
+        return float(np.abs(a - r).max() / max(np.abs(r).max(), 1e-30))
+
+    for b in samples:
+        xb = x4[b:b + 1].float().cpu().numpy()
+        pb, mb = pos[b:b + 1].cpu().numpy(), pad[b:b + 1].cpu().numpy()
+        ref_out, ref_attn = ltae_forward(cfg, params, xb, pb, mb)
+        a = attn[:, b:b + 1].float().cpu().numpy()
+        errs["attn"] = max(errs["attn"], rel(a, ref_attn))
+        errs["out"] = max(errs["out"], rel(out[b:b + 1].float().cpu().numpy(), ref_out))
+        if not mb.all():
+            errs["pad_attention_exactly_zero"] &= bool(np.all(a[:, 0, mb[0]] == 0.0))
+        for i, x in enumerate(xs):
+            ref = temporal_aggregator_torch(x[b:b + 1].float().cpu(), mb, ref_attn, "att_group").numpy()
+            errs["skips"][i] = max(errs["skips"][i], rel(skips[i][b:b + 1].float().cpu().numpy(), ref))
+    return errs

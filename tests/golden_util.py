@@ -22,6 +22,12 @@ def load(name):
     return cfg, inputs, params, outs
 
 
+def load_grads(name):
+    """``grad::*`` arrays of a training fixture (tests/golden/make_train_golden.py): reference autograd results."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    return {k[len("grad::"):]: z[k] for k in z.files if k.startswith("grad::")}
+
+
 def rel_err(a, b):
     """max|a-b| / max|b| -- the tolerance definition of SURVEY.md section 8d."""
     a = np.asarray(a, dtype=np.float64)

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(LIB_PATH)
     for sym in declared:
         assert hasattr(raw, sym), sym
-    assert lib.c2s_abi_version() == _lib.C2S_ABI_VERSION == 5
+    assert lib.c2s_abi_version() == _lib.C2S_ABI_VERSION == 6
 
 
 def test_header_compiles_as_plain_c(tmp_path):
@@ -155,6 +155,28 @@ def test_install_swaps_reference_bindings():
                 sys.modules.pop(n, None)
             else:
                 sys.modules[n] = m
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/backbones"), reason="needs the reference checkout")
+def test_install_imports_then_uninstall_restores_the_reference_classes():
+    """install() doing the importing itself must still remember the reference classes (the model files import
+    src.backbones.tae, so saving while importing would record the fused class as the original)."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r)\n"
+        "import crop2seg_b200 as c2s\n"
+        "swapped = c2s.install(assume_zero_padded=True)\n"
+        "import src.backbones.utae as u, src.backbones.tae as t, src.backbones.timeunet as tu\n"
+        "assert u.LTAE is c2s.LTAE and t.LTAE is c2s.LTAE and tu.LTAE is c2s.LTAE, swapped\n"
+        "assert c2s.LTAE().assume_zero_padded is True\n"
+        "wrapped = tu.TimeUNet_v1.forward\n"
+        "c2s.uninstall()\n"
+        "assert t.LTAE.__module__ == 'src.backbones.tae' and u.LTAE is t.LTAE and tu.LTAE is t.LTAE\n"
+        "assert u.TemporalAggregator.__module__ == 'src.backbones.temporal_aggregator'\n"
+        "assert tu.TimeUNet_v1.forward is not wrapped and c2s.LTAE().assume_zero_padded is False\n"
+        "print('ok')\n") % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
 
 
 def test_shard_bounds_partition():

@@ -94,5 +94,23 @@ def test_cuda_hot_path_inside_the_reference_model(dtype):
             mine = dec(out.float().cpu(), *[s.float().cpu() for s in skips]).numpy()
             ref = dec(torch.from_numpy(ref_out.astype(np.float32)),
                       *[torch.from_numpy(r.astype(np.float32)) for r in ref_skips]).numpy()
-        assert float((mine.argmax(axis=1) == ref.argmax(axis=1)).mean()) >= 0.99
+        agree_oracle = float((mine.argmax(axis=1) == ref.argmax(axis=1)).mean())
+        agree_reference = float((mine.argmax(axis=1) == outs["argmax"]).mean())
+        # what rounding the feature maps to bf16 does by itself (the oracle in fp32 on the rounded inputs vs the
+        # reference on the unrounded ones): the part of the disagreement no bf16 kernel can avoid
+        agree_rounding = float((ref.argmax(axis=1) == outs["argmax"]).mean())
+        record = {"bf16_vs_oracle_on_rounded_inputs": agree_oracle, "bf16_vs_reference_fp32_class_map": agree_reference,
+                  "oracle_on_rounded_inputs_vs_reference": agree_rounding, "pixels": int(outs["argmax"].size)}
+        print("model gate (bf16):", json.dumps(record))
+        try:
+            os.makedirs(os.path.join(os.path.dirname(GOLDEN_DIR), "..", "gpurun_out"), exist_ok=True)
+            with open(os.path.join(os.path.dirname(GOLDEN_DIR), "..", "gpurun_out", "model_gate_bf16.json"), "w") as f:
+                json.dump(record, f)
+        except OSError:
+            pass
+        # the kernels' own error: >= 99.9 % against the pinned oracle on identical (rounded) inputs
+        assert agree_oracle >= ARGMAX_AGREEMENT, record
+        # against the reference's fp32 class map the bf16 path may only lose what the input rounding itself loses
+        # (untrained random weights give many near-tied pixels; profiles/ holds the measured figures)
+        assert agree_reference >= agree_rounding - 0.002, record
         assert rel_err(mine, ref) < 2e-2
