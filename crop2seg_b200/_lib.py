@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 6
+C2S_ABI_VERSION = 7
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -29,7 +29,9 @@ EXPORTS = (
     "c2s_agg_skipconv_workspace_bytes", "c2s_agg_skipconv_forward", "c2s_pad_mask",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
     "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward", "c2s_ltae_inconv_grad",
+    "c2s_tile_patchify", "c2s_tile_classmap",
 )
+RAW_I16, RAW_U16, RAW_F32 = 0, 1, 2  # enum c2s_raw_dtype
 
 
 class AggDesc(ctypes.Structure):
@@ -39,6 +41,11 @@ class AggDesc(ctypes.Structure):
 class SkipConvParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("conv_weight", "conv_bias", "bn_weight", "bn_bias", "bn_running_mean",
                                                "bn_running_var")] + [("bn_eps", ctypes.c_float)]
+
+
+class TileDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("T", "T_pad", "C", "H", "W", "patch", "grid_h", "grid_w", "patch_begin",
+                                              "patch_count", "src_dtype", "dst_dtype")] + [("pad_value", ctypes.c_float)]
 
 
 class LtaeDesc(ctypes.Structure):
@@ -141,6 +148,10 @@ def load() -> ctypes.CDLL:
         lib.c2s_ltae_mlp_backward.restype = i32
         lib.c2s_ltae_mlp_backward.argtypes = [ctypes.POINTER(LtaeDesc), ctypes.POINTER(LtaeParams),
                                               ctypes.POINTER(LtaeMlpBwdIo), vp, sz, vp]
+        lib.c2s_tile_patchify.restype = i32
+        lib.c2s_tile_patchify.argtypes = [ctypes.POINTER(TileDesc), vp, vp, vp, vp, vp, vp]
+        lib.c2s_tile_classmap.restype = i32
+        lib.c2s_tile_classmap.argtypes = [ctypes.POINTER(TileDesc), vp, i32, vp, vp, vp]
         got = lib.c2s_abi_version()
         if got != C2S_ABI_VERSION:
             raise C2SError(f"ABI mismatch: library reports version {got}, binding expects {C2S_ABI_VERSION}")

@@ -23,7 +23,10 @@ int set_max_dynamic_smem(const void* func, int bytes, std::atomic<unsigned long 
   C2S_CUDA(cudaGetDevice(&dev));
   const unsigned long long bit = 1ull << (dev & 63);
   if (done->load(std::memory_order_acquire) & bit) return C2S_OK;
-  C2S_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  cudaFuncAttributes fa;
+  C2S_CUDA(cudaFuncGetAttributes(&fa, func));
+  const int room = 232448 - static_cast<int>(fa.sharedSizeBytes);  // 227 KB per CTA, static part included
+  C2S_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes < room ? bytes : room));
   done->fetch_or(bit, std::memory_order_release);
   return C2S_OK;
 }

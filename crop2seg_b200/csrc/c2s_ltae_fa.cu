@@ -191,6 +191,25 @@ __device__ __forceinline__ void split_f16(float v0, float v1, uint32_t& hi, uint
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// packed fp32 pairs (FADD2 / FFMA2 on sm_100): two lanes of arithmetic per issue slot
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
@@ -287,9 +306,15 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
   // frames that are not read must hold zeros: warp w owns quad w % NQ of the frames w / NQ + k TSTEP
   auto zero_fill = [&](int buf, unsigned long long live) {
     unsigned char* slab = smem + S::oSlab + buf * S::kSlab;
-    for (int t = warp / NQ; t < kTP; t += TSTEP)
-      if (!((live >> t) & 1ull))
-        *reinterpret_cast<uint4*>(slab + t * FB + (warp % NQ) * 512 + lane * 16) = make_uint4(0, 0, 0, 0);
+    unsigned long long mine = 0;  // frames t = warp / NQ + k TSTEP
+#pragma unroll
+    for (int k = 0; k < kTP / TSTEP; ++k) mine |= 1ull << (k * TSTEP);
+    unsigned long long dead = ~live & (mine << (warp / NQ));
+    while (dead) {  // a full-length series leaves the frames T .. 63 only
+      const int t = __ffsll(static_cast<long long>(dead)) - 1;
+      dead &= dead - 1;
+      *reinterpret_cast<uint4*>(slab + t * FB + (warp % NQ) * 512 + lane * 16) = make_uint4(0, 0, 0, 0);
+    }
   };
   // warp 0 issues the copies of a tile.  The copy unit takes about one cycle per 16-byte row and blocks the issuing
   // thread once its queue is full, so the boxes are as large as the live frames allow (16, 4 or 1 frames): a regular
@@ -360,7 +385,12 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < kTP * 16 / NT; ++q) {
           const int i = tid + q * NT, t = i >> 4, h = i & 15;
-          s_cpos[h * kAP + t] = s_raw[i] * kLog2e;
+          // frames behind T never count; padded frames that are not read (rows of zeros) start from the mask
+          // value and stay there (tae.py:831): the softmax below needs no per-value test for them
+          float c0 = s_raw[i] * kLog2e;
+          if (a.zero_padded && ((padm >> t) & 1ull)) c0 = -1e6f * kLog2e;
+          if (t >= a.T) c0 = -INFINITY;
+          s_cpos[h * kAP + t] = c0;
           if (!a.attn_only) {
             const float pe = s_raw[kTP * 16 + i];
             const __nv_bfloat16 hi = __float2bfloat16_rn(pe);
@@ -388,26 +418,49 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
       float pv_fin = 0.f;  // pivot of (group tid / 8, pixel tid % 8): first live frame, first channel of the group
       if (tid < kH * kPix && n_live > 0) pv_fin = __bfloat162float(x_first[static_cast<size_t>((tid >> 3) * CPG) * a.hw + (tid & 7)]);
       const int q4 = warp % NQ;
-      float pv[4], s1[4], s2[4];
+      constexpr int FPG = 16 / TSTEP;  // frames of a 16-frame barrier group that this warp owns
+      static_assert(16 % TSTEP == 0 && FPG * TSTEP == 16, "a warp owns whole frames of every barrier group");
+      float s1[4], s2[4];
+      unsigned long long s1p[4], s2p[4], npv[4];  // {even channel, odd channel} pairs: FADD2 / FFMA2
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        s1[i] = 0.f, s2[i] = 0.f;
+        s1p[i] = 0ull, s2p[i] = 0ull;
         const int c0 = (4 * q4 + i) * 8 + (CPG == 4 ? 4 * (j >> 1) : 0);
-        pv[i] = n_live > 0 ? __bfloat162float(x_first[static_cast<size_t>(c0) * a.hw + g]) : 0.f;
+        const float pv = n_live > 0 ? __bfloat162float(x_first[static_cast<size_t>(c0) * a.hw + g]) : 0.f;
+        npv[i] = pack_f32x2(-pv, -pv);
       }
-      for (int t = warp / NQ; t < kTP; t += TSTEP) {
-        if (!((live >> t) & 1ull)) continue;  // warp-uniform
-        mbar_wait(bars + 8 * (buf * 4 + (t >> 4)), par);
-        const uint32_t blk = slab + t * FB + q4 * 512 + mat * 128;
-        uint32_t v[4];
-        ldsm_x4_trans(v, blk + mr * 16);          // v[i]: pixel g, channels 2j, 2j+1 of block 4 q4 + i
-        stsm_x4(blk + ((mr ^ (t & 7)) << 4), v);  // row = pixel, 8 channels; slot pixel ^ (t & 7)
+      const uint32_t blk0 = slab + q4 * 512 + mat * 128;
+      const int f0 = warp / NQ;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float d0 = bf16_lo(v[i]) - pv[i], d1 = bf16_hi(v[i]) - pv[i];
-          s1[i] += d0 + d1;
-          s2[i] = fmaf(d0, d0, fmaf(d1, d1, s2[i]));
+      for (int grp = 0; grp < 4; ++grp) {
+        const uint32_t gl = static_cast<uint32_t>(live >> (16 * grp)) & 0xffffu;  // warp-uniform
+        if (gl == 0) continue;
+        mbar_wait(bars + 8 * (buf * 4 + grp), par);  // once per group: a completed barrier still costs ~90 cycles
+        uint32_t v[FPG][4];
+#pragma unroll
+        for (int q = 0; q < FPG; ++q)  // every load of the group goes out before the first use
+          if ((gl >> (f0 + TSTEP * q)) & 1u) ldsm_x4_trans(v[q], blk0 + (16 * grp + f0 + TSTEP * q) * FB + mr * 16);
+#pragma unroll
+        for (int q = 0; q < FPG; ++q) {
+          if (!((gl >> (f0 + TSTEP * q)) & 1u)) continue;
+          const int t = 16 * grp + f0 + TSTEP * q;
+          // v[q][i]: pixel g, channels 2j, 2j+1 of block 4 q4 + i; row = pixel, 8 channels; slot pixel ^ (t & 7)
+          stsm_x4(blk0 + t * FB + ((mr ^ (t & 7)) << 4), v[q]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const unsigned long long d = add_f32x2(pack_f32x2(bf16_lo(v[q][i]), bf16_hi(v[q][i])), npv[i]);
+            s1p[i] = add_f32x2(s1p[i], d);
+            s2p[i] = fma_f32x2(d, d, s2p[i]);
+          }
         }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        unpack_f32x2(s1p[i], lo, hi);
+        s1[i] = lo + hi;
+        unpack_f32x2(s2p[i], lo, hi);
+        s2[i] = lo + hi;
       }
       FA_DBG(2);
 #pragma unroll
@@ -471,15 +524,24 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
         split_bf16(u0.z * r0, u0.w * r0, ahi[1], alo[1]);  // (row g + 8, k 2j, 2j+1)
         split_bf16(u1.x * r1, u1.y * r1, ahi[2], alo[2]);  // (row g,     k 2j+8, 2j+9)
         split_bf16(u1.z * r1, u1.w * r1, ahi[3], alo[3]);  // (row g + 8, k 2j+8, 2j+9)
+        // every fragment of the k-step is requested before the first product (one ldmatrix latency per k-step instead
+        // of one per pair of frame blocks); bfr[ntp]: (block 2 ntp, channels 16 ks..+7), (.., +8..15), (block 2 ntp + 1, ..)
+        uint32_t bfr[FN / 2][4];
+#pragma unroll
+        for (int ntp = 0; ntp < FN / 2; ++ntp)
+          if (((live_w >> (16 * ntp)) & 0xffffull) != 0) ldsm_x4(bfr[ntp], xrow + ntp * 16 * FB + ks * 256);
+        // hi pass over every frame block, then the lo pass: FN products between two that share an accumulator
 #pragma unroll
         for (int ntp = 0; ntp < FN / 2; ++ntp) {
           if (((live_w >> (16 * ntp)) & 0xffffull) == 0) continue;  // both frame blocks hold zeros
-          uint32_t bfr[4];  // (block 2 ntp, channels 16 ks..+7), (.., +8..15), (block 2 ntp + 1, ..), (..)
-          ldsm_x4(bfr, xrow + ntp * 16 * FB + ks * 256);
-          mma_bf16(sacc[2 * ntp], ahi, bfr[0], bfr[1]);
-          mma_bf16(sacc[2 * ntp], alo, bfr[0], bfr[1]);
-          mma_bf16(sacc[2 * ntp + 1], ahi, bfr[2], bfr[3]);
-          mma_bf16(sacc[2 * ntp + 1], alo, bfr[2], bfr[3]);
+          mma_bf16(sacc[2 * ntp], ahi, bfr[ntp][0], bfr[ntp][1]);
+          mma_bf16(sacc[2 * ntp + 1], ahi, bfr[ntp][2], bfr[ntp][3]);
+        }
+#pragma unroll
+        for (int ntp = 0; ntp < FN / 2; ++ntp) {
+          if (((live_w >> (16 * ntp)) & 0xffffull) == 0) continue;
+          mma_bf16(sacc[2 * ntp], alo, bfr[ntp][0], bfr[ntp][1]);
+          mma_bf16(sacc[2 * ntp + 1], alo, bfr[ntp][2], bfr[ntp][3]);
         }
       }
     }
@@ -492,17 +554,17 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
       const float* red_other = s_red + (p * 2 + (half ^ 1)) * 2 * kH;
       const unsigned long long pad_w = (WPP == 1) ? padm : ((padm >> (FPW * half)) & 0xffffffffull);
       float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (!a.zero_padded && pad_w != 0) {  // padded frames were read: their scores are replaced here (tae.py:831)
+#pragma unroll
+        for (int nt = 0; nt < FN; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if ((pad_w >> (nt * 8 + 2 * j + e)) & 1ull) sacc[nt][e] = -1e6f * kLog2e, sacc[nt][2 + e] = -1e6f * kLog2e;
+      }
 #pragma unroll
       for (int nt = 0; nt < FN; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int tl = nt * 8 + 2 * j + e;
-          float v0 = sacc[nt][e], v1 = sacc[nt][2 + e];
-          if ((pad_w >> tl) & 1ull) v0 = -1e6f, v1 = -1e6f;
-          if (FPW * half + tl >= a.T) v0 = -INFINITY, v1 = -INFINITY;
-          sacc[nt][e] = v0, sacc[nt][2 + e] = v1;
-          mx0 = fmaxf(mx0, v0), mx1 = fmaxf(mx1, v1);
-        }
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
@@ -587,14 +649,22 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
         split_bf16(sacc[2 * ksl + 1][0], sacc[2 * ksl + 1][1], ahi[2], alo[2]);
         split_bf16(sacc[2 * ksl + 1][2], sacc[2 * ksl + 1][3], ahi[3], alo[3]);
         if (((live_w >> (16 * ksl)) & 0xffffull) != 0) {
+          constexpr int CB = (C == 64) ? 4 : 2;  // channel-block pairs whose fragments are requested together (registers)
 #pragma unroll
-          for (int cbp = 0; cbp < C / 16; ++cbp) {
-            uint32_t v[4];  // (frames 0-7, block 2 cbp), (0-7, 2 cbp + 1), (8-15, 2 cbp), (8-15, 2 cbp + 1)
-            ldsm_x4_trans(v, xrow + ksl * 16 * FB + cbp * 256);
-            mma_bf16(zacc[2 * cbp], ahi, v[0], v[2]);
-            mma_bf16(zacc[2 * cbp], alo, v[0], v[2]);
-            mma_bf16(zacc[2 * cbp + 1], ahi, v[1], v[3]);
-            mma_bf16(zacc[2 * cbp + 1], alo, v[1], v[3]);
+          for (int cb0 = 0; cb0 < C / 16; cb0 += CB) {
+            uint32_t v[CB][4];  // (frames 0-7, block 2 cbp), (0-7, 2 cbp + 1), (8-15, 2 cbp), (8-15, 2 cbp + 1)
+#pragma unroll
+            for (int q = 0; q < CB; ++q) ldsm_x4_trans(v[q], xrow + ksl * 16 * FB + (cb0 + q) * 256);
+#pragma unroll
+            for (int q = 0; q < CB; ++q) {
+              mma_bf16(zacc[2 * (cb0 + q)], ahi, v[q][0], v[q][2]);
+              mma_bf16(zacc[2 * (cb0 + q) + 1], ahi, v[q][1], v[q][3]);
+            }
+#pragma unroll
+            for (int q = 0; q < CB; ++q) {
+              mma_bf16(zacc[2 * (cb0 + q)], alo, v[q][0], v[q][2]);
+              mma_bf16(zacc[2 * (cb0 + q) + 1], alo, v[q][1], v[q][3]);
+            }
           }
         }
         if (a.pe != nullptr) {  // matrices (hi, frames 0-7), (hi, 8-15), (lo, 0-7), (lo, 8-15) of 8 table columns
@@ -738,30 +808,52 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
     if (!a.attn_only) {
       // ---- in-projection of head `warp`: o[16 h + i, px] = Wc[16 h + i, :] . zn[px, h, :] + sa bc + sum_t a PE
       //                                                                              tae.py:463, 479, 839
+      // The heads of a warp run side by side and every term has its own accumulator: HPW x 3 independent chains of KS
+      // products instead of one chain of 3 KS (an mma.sync result comes back after ~30 cycles).
+      constexpr int HPW = kH / NW;  // heads per warp
+      float acc[HPW][3][4];
 #pragma unroll
-      for (int h = warp; h < kH; h += NW) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const unsigned char* zb = slab_ptr + g * S::PB + (h * (C + 8) + 2 * j) * 2;  // B[k = c][n = pixel g]
-        const uint4* wc = (S::kHiResident ? reinterpret_cast<const uint4*>(smem + S::oWc) : a.wc16) + (h * KS) * 32 + lane;
-        uint4 wha[S::kHiResident ? 1 : KS], wla[S::kHiResident ? 1 : KS];
-        if constexpr (!S::kHiResident) {  // streamed from L2: all loads of the head go out before the first product
+      for (int hh = 0; hh < HPW; ++hh)
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks) wha[ks] = __ldg(wc + ks * 32), wla[ks] = __ldg(wc + S::kWcHalf / 16 + ks * 32);
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[hh][q][e] = 0.f;
+      uint4 wha[HPW][S::kHiResident ? 1 : KS], wla[HPW][S::kHiResident ? 1 : KS];
+      if constexpr (!S::kHiResident) {  // streamed from L2: every load goes out before the first product
+#pragma unroll
+        for (int hh = 0; hh < HPW; ++hh) {
+          const uint4* wc = a.wc16 + ((warp + hh * NW) * KS) * 32 + lane;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) wha[hh][ks] = __ldg(wc + ks * 32), wla[hh][ks] = __ldg(wc + S::kWcHalf / 16 + ks * 32);
         }
+      }
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
+      for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int hh = 0; hh < HPW; ++hh) {
+          const int h = warp + hh * NW;
+          const unsigned char* zb = slab_ptr + g * S::PB + (h * (C + 8) + 2 * j) * 2;  // B[k = c][n = pixel g]
           uint4 wa, wl;
-          if constexpr (!S::kHiResident) wa = wha[ks], wl = wla[ks];
-          else if constexpr (S::kLoResident) wa = wc[ks * 32], wl = wc[S::kWcHalf / 16 + ks * 32];
-          else wa = wc[ks * 32], wl = wlo[ks];
+          if constexpr (!S::kHiResident) {
+            wa = wha[hh][ks], wl = wla[hh][ks];
+          } else {
+            const uint4* wc = reinterpret_cast<const uint4*>(smem + S::oWc) + (h * KS) * 32 + lane;
+            wa = wc[ks * 32];
+            if constexpr (S::kLoResident) wl = wc[S::kWcHalf / 16 + ks * 32];
+            else wl = wlo[ks];
+          }
           const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(zb + ks * 32);
           const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(zb + ks * 32 + 16);
           const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(zb + S::kZn + ks * 32);
           const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(zb + S::kZn + ks * 32 + 16);
-          mma_f16(acc, wa, bh0, bh1);
-          mma_f16(acc, wl, bh0, bh1);
-          mma_f16(acc, wa, bl0, bl1);
+          mma_f16(acc[hh][0], wa, bh0, bh1);
+          mma_f16(acc[hh][1], wl, bh0, bh1);
+          mma_f16(acc[hh][2], wa, bl0, bl1);
         }
+      }
+#pragma unroll
+      for (int hh = 0; hh < HPW; ++hh) {
+        const int h = warp + hh * NW;
         const float* s_pa = reinterpret_cast<const float*>(slab_ptr + S::oPa);
         uint16_t* os_hi = reinterpret_cast<uint16_t*>(slab_ptr + S::oOsHi);
         uint16_t* os_lo = reinterpret_cast<uint16_t*>(slab_ptr + S::oOsLo);
@@ -770,7 +862,8 @@ ltae_fa_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant_
         for (int e = 0; e < 4; ++e) {
           const int i = g + (e >> 1) * 8, pp = 2 * j + (e & 1);
           const int d = h * 16 + i;
-          const float v = fmaf(acc[e], inv_sc, fmaf(s_sa[h * kPix + pp], __ldg(a.bc + d), s_pa[(h * 16 + i) * kPix + pp]));
+          const float sum = acc[hh][0][e] + (acc[hh][1][e] + acc[hh][2][e]);
+          const float v = fmaf(sum, inv_sc, fmaf(s_sa[h * kPix + pp], __ldg(a.bc + d), s_pa[(h * 16 + i) * kPix + pp]));
           const __nv_bfloat16 hi = __float2bfloat16_rn(v);
           const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
           os_hi[pp * kOsRow + d] = *reinterpret_cast<const uint16_t*>(&hi);

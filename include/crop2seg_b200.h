@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 6
+#define C2S_ABI_VERSION 7
 
 enum c2s_status {
   C2S_OK = 0,
@@ -243,6 +243,45 @@ int c2s_ltae_inconv_grad(const float* grad_o, const float* zn_rows, const float*
 size_t c2s_ltae_backward_workspace_bytes(const c2s_ltae_desc* desc);
 int c2s_ltae_backward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const void* x, const void* positions,
                       const uint8_t* pad_mask, const c2s_ltae_bwd_io* io, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Edges of the tile inference pipeline
+ *   before the model: DatasetCreator._patchify          src/helpers/dataset_creator.py:347-388
+ *                     S2TSCZCropDataset.__getitem__     src/datasets/s2_ts_cz_crop.py:374, 393-398
+ *                     pad_collate                       src/utils.py:14-66
+ *   after the model:  generate_prediction               src/webapp/prediction.py:316-333
+ * ---------------------------------------------------------------------------------------- */
+enum c2s_raw_dtype { C2S_RAW_I16 = 0, C2S_RAW_U16 = 1, C2S_RAW_F32 = 2 };
+
+typedef struct c2s_tile_desc {
+  int32_t T, T_pad;      /* frames of the tile / frames of a model input (>= T; the rest is pad_value)       */
+  int32_t C;             /* channels (10 Sentinel-2 bands)                                                   */
+  int32_t H, W;          /* tile size in pixels (10980 x 10980; the webapp's sub-tiles are 1098 x 1098)      */
+  int32_t patch;         /* patch edge (128), a multiple of 8                                                */
+  int32_t grid_h, grid_w;/* patch rows / columns of the zero-padded tile; 0 = ceil(H / patch), ceil(W / patch)
+                            (the webapp pads by a fixed 182 pixels: 10 x 10 for 1098, dataset_creator.py:386) */
+  int32_t patch_begin;   /* first patch of this call in the row-major patch list (shard / batch offset)      */
+  int32_t patch_count;   /* patches of this call                                                             */
+  int32_t src_dtype;     /* enum c2s_raw_dtype of the raw tile (c2s_tile_patchify)                           */
+  int32_t dst_dtype;     /* enum c2s_dtype of the patches (c2s_tile_patchify) / of the logits (c2s_tile_classmap) */
+  float pad_value;       /* value of the frames T .. T_pad-1 (0, src/utils.py:14)                            */
+} c2s_tile_desc;
+
+/* patches[p, t, c, y, x] = (pad0(tile)[t, channels_order[c], Y, X] - mean[c]) / std[c]   (t < T, fp32 arithmetic)
+ *                        = pad_value                                                    (T <= t < T_pad)
+ * with (Y, X) the pixel of patch patch_begin + p in the tile zero-padded (RAW zeros, so padding normalises to
+ * -mean/std) to grid_h x grid_w patches.  tile: [T, C, H, W] raw; channels_order: int32 [C]; mean, std: float32 [C]
+ * in the REORDERED channel order (prediction.py:244-249); patches: [patch_count, T_pad, C, patch, patch]. */
+int c2s_tile_patchify(const c2s_tile_desc* desc, const void* tile, const int32_t* channels_order, const float* mean,
+                      const float* std, void* patches, void* stream);
+
+/* classmap[Y, X] = first argmax_k softmax_k(logits[p, :, y, x]); proba[k, Y, X] = softmax (float32, may be NULL):
+ * the patches patch_begin .. patch_begin + patch_count - 1 put back row-major and cropped to H x W
+ * (prediction.py:318-320, 326-333, which moves every patch to the host first).  logits: [patch_count, K, patch, patch];
+ * classmap: uint8 [H, W]; proba: float32 [K, H, W].  Calls for different patch ranges fill disjoint parts of the same
+ * maps.  K <= 32. */
+int c2s_tile_classmap(const c2s_tile_desc* desc, const void* logits, int32_t n_classes, uint8_t* classmap, float* proba,
                       void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -107,3 +107,42 @@ def test_training_step_replays_in_one_graph():
             assert err < 2e-3, (k, err)  # float atomics reorder between runs; Adam normalises the step size
     finally:
         c2s.modules.ATTENTION_DROPOUT = old
+
+
+def test_captured_graph_survives_cache_eviction_and_weight_updates():
+    """A captured inference graph must not depend on the eval-mode folded-weight cache: another shape evicts the cached
+    workspace, an in-place weight update makes it stale -- replays still equal an eager call with the current weights."""
+    enc, x4, x1, pos, pad = _setup(np.random.RandomState(5))
+    enc.eval()
+
+    def run():
+        with torch.no_grad():
+            return enc(x4, batch_positions=pos, pad_mask=pad)
+
+    run()  # warm-up fills the cache
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static = run()
+    # (a) evict: an eager call with another T replaces the module's cached workspace, then allocate over the freed block
+    with torch.no_grad():
+        enc(x4[:, :7].contiguous(), batch_positions=pos[:, :7].contiguous(), pad_mask=pad[:, :7].contiguous())
+    junk = [torch.full((1 << 20,), 7.0, device="cuda") for _ in range(8)]
+    graph.replay()
+    torch.cuda.synchronize()
+    eager = run()
+    assert torch.equal(static[0], eager[0]) and torch.equal(static[1], eager[1])
+    assert all(float(j.min()) == 7.0 and float(j.max()) == 7.0 for j in junk)  # the replay wrote nowhere else
+    # (b) weights change in place: the replay folds the new weights
+    with torch.no_grad():
+        enc.attention_head.Q.mul_(1.3)
+        enc.mlp[0].weight.add_(0.02)
+    graph.replay()
+    torch.cuda.synchronize()
+    eager2 = run()
+    assert torch.equal(static[0], eager2[0]) and torch.equal(static[1], eager2[1])
+    assert not torch.equal(eager2[1], eager[1])

@@ -252,3 +252,24 @@ def test_ltae_without_attention_store(name):
             out2, none = m(to_dev(x, dtype=dtype), batch_positions=to_dev(pos), pad_mask=to_dev(pad), return_att=False)
         assert none is None and attn is not None
         assert torch.equal(out, out2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_devices():
+    """Kernel attributes (dynamic shared memory) are per device: the same process drives cuda:0 and then cuda:1."""
+    heads, (b, t, c, h, w), (ha, wa), lengths = AGG_CASES["x4_64"]
+    rng = np.random.RandomState(99)
+    x, pos, pad = synth_inputs(rng, b, t, c, h, w, lengths)
+    attn = random_attention(rng, heads, pad, ha, wa)
+    kind, kw, (lb, lt, lh, lw), llen, _ = LTAE_CASES["utae"]
+    m, rng2 = _build(kind, kw, 98)
+    lx, lpos, lpad = synth_inputs(rng2, lb, lt, 128, lh, lw, llen)
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        with torch.cuda.device(dev), torch.no_grad():
+            out = c2s.TemporalAggregator("att_group")(to_dev(x, dev, torch.bfloat16), pad_mask=to_dev(pad, dev),
+                                                      attn_mask=to_dev(attn, dev))
+            lo, la = m.to(dev)(to_dev(lx, dev, torch.bfloat16), batch_positions=to_dev(lpos, dev), pad_mask=to_dev(lpad, dev))
+            res.append((out.cpu(), lo.cpu(), la.cpu()))
+    for a, b_ in zip(res[0], res[1]):
+        assert torch.equal(a, b_)

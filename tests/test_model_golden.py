@@ -110,7 +110,7 @@ def test_cuda_hot_path_inside_the_reference_model(dtype):
             pass
         # the kernels' own error: >= 99.9 % against the pinned oracle on identical (rounded) inputs
         assert agree_oracle >= ARGMAX_AGREEMENT, record
-        # against the reference's fp32 class map the bf16 path may only lose what the input rounding itself loses
-        # (untrained random weights give many near-tied pixels; profiles/ holds the measured figures)
-        assert agree_reference >= agree_rounding - 0.002, record
+        # and the north-star gate itself: >= 99.9 % against the REFERENCE's fp32 class map (measured: 100 % of 2048
+        # pixels, profiles/r02_model_gate_bf16.json)
+        assert agree_reference >= ARGMAX_AGREEMENT, record
         assert rel_err(mine, ref) < 2e-2
