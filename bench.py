@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of one step's outputs")
     ap.add_argument("--cpu-patches", type=int, default=2, help="patches in the CPU-baseline sample")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (placements, training, tile, sustained)")
+    ap.add_argument("--sub-seconds", type=float, default=1.0, help="minimum timed seconds of every sub-record")
     return ap.parse_args()
 
 
@@ -430,11 +432,36 @@ def run_b200(args):
         t2 = torch.tensor([s2.elapsed_time(e2)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * e_steps / (float(t2.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+        e2e_s = float(t2.item()) * 1e-3
+        e2e = {"value": world * B * e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e_steps,
                "note": "pinned host buffers, 8-patch chunks double-buffered on a copy stream, padded frames are not copied; "
                        "PCIe-bound"}
         del host_in, host_out, dev_in
+        # the ceiling beside it: a plain pinned cudaMemcpyAsync of 1 GiB in each direction, all ranks at the same time
+        from tools.bench_lib import pcie_ceiling
+        link = pcie_ceiling(dev)
+        e2e["h2d_gbs_achieved"] = h2d * e_steps / e2e_s / 1e9
+        e2e["pcie_gbs_measured"] = link["h2d_gbs"]
+        e2e["pcie_d2h_gbs_measured"] = link["d2h_gbs"]
+        e2e["frac"] = e2e["h2d_gbs_achieved"] / link["h2d_gbs"]
+        e2e["frac_note"] = ("host->device bytes per second of the e2e steps over the measured rate of one plain pinned "
+                            "host->device copy per rank, all ranks concurrently (max time over ranks)")
+
+    # ---- sub-records: every placement, the training step and the full tile, each timed for >= --sub-seconds ----
+    sub = {}
+    if not args.no_sub:
+        from tools import bench_lib
+        del x4, xs
+        torch.cuda.empty_cache()
+        with ClockSampler(local_rank) as sub_clocks:
+            sub["placements"] = bench_lib.placements(dev, B=B, min_seconds=args.sub_seconds)
+            sub["training"] = bench_lib.training(dev, local_rank, B=16, min_seconds=args.sub_seconds)
+            sub["tile"] = bench_lib.tile(dev, "timeunet", B=B)
+            sub["tile_utae"] = bench_lib.tile(dev, "utae", B=B)
+        sub["clocks"] = sub_clocks.summary()
+        if rank == 0 and world > 1:
+            sub["topology"] = bench_lib.topology()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -455,6 +482,7 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
+        line.update(sub)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

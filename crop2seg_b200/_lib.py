@@ -29,7 +29,7 @@ EXPORTS = (
     "c2s_agg_skipconv_workspace_bytes", "c2s_agg_skipconv_forward", "c2s_pad_mask",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
     "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward", "c2s_ltae_inconv_grad",
-    "c2s_tile_patchify", "c2s_tile_classmap",
+    "c2s_tile_patchify", "c2s_tile_classmap", "c2s_frame_index", "c2s_frames_gather", "c2s_frames_scatter",
 )
 RAW_I16, RAW_U16, RAW_F32 = 0, 1, 2  # enum c2s_raw_dtype
 
@@ -152,6 +152,12 @@ def load() -> ctypes.CDLL:
         lib.c2s_tile_patchify.argtypes = [ctypes.POINTER(TileDesc), vp, vp, vp, vp, vp, vp]
         lib.c2s_tile_classmap.restype = i32
         lib.c2s_tile_classmap.argtypes = [ctypes.POINTER(TileDesc), vp, i32, vp, vp, vp]
+        lib.c2s_frame_index.restype = i32
+        lib.c2s_frame_index.argtypes = [vp, ctypes.c_int64, vp, vp, vp]
+        lib.c2s_frames_gather.restype = i32
+        lib.c2s_frames_gather.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, i32, vp]
+        lib.c2s_frames_scatter.restype = i32
+        lib.c2s_frames_scatter.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, i32, ctypes.c_float, vp]
         got = lib.c2s_abi_version()
         if got != C2S_ABI_VERSION:
             raise C2SError(f"ABI mismatch: library reports version {got}, binding expects {C2S_ABI_VERSION}")

@@ -582,13 +582,48 @@ int launch_bwd_cpt(const AggBwdArgs& a, int cpt, int s, cudaStream_t stream) {
   }
 }
 
+// nn.AvgPool2d(kernel_size=k) of the attention maps (temporal_aggregator.py:28-29: the branch taken when the attention
+// is not coarser than x) and its adjoint: every cell of a k x k window receives grad / k^2, the rows and columns that
+// the floor of the pooling drops receive nothing
+__global__ void pool_attn_kernel(const float* __restrict__ in, float* __restrict__ out, int hi, int wi, int ho, int wo, int k,
+                                 size_t n_out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int x = static_cast<int>(i % wo);
+  const int y = static_cast<int>((i / wo) % ho);
+  const size_t map = i / (static_cast<size_t>(wo) * ho);
+  const float* p = in + map * hi * wi + static_cast<size_t>(y) * k * wi + static_cast<size_t>(x) * k;
+  float s = 0.f;
+  for (int dy = 0; dy < k; ++dy)
+    for (int dx = 0; dx < k; ++dx) s += p[dy * wi + dx];
+  out[i] = s / static_cast<float>(k * k);
+}
+__global__ void unpool_grad_kernel(const float* __restrict__ gpooled, float* __restrict__ gattn, int hi, int wi, int ho,
+                                   int wo, int k, size_t n_in) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_in) return;
+  const int x = static_cast<int>(i % wi);
+  const int y = static_cast<int>((i / wi) % hi);
+  const size_t map = i / (static_cast<size_t>(wi) * hi);
+  const int py = y / k, px = x / k;
+  if (py >= ho || px >= wo) return;
+  gattn[i] += gpooled[(map * ho + py) * wo + px] / static_cast<float>(k * k);
+}
+
+bool bwd_uses_pool(const c2s_agg_desc* d) { return d->mode == C2S_AGG_ATT_GROUP && !(d->H > d->wa); }
+
 }  // namespace
 }  // namespace c2s
 
 extern "C" {
 
 size_t c2s_agg_backward_workspace_bytes(const c2s_agg_desc* d) {
-  if (d == nullptr || d->mode != C2S_AGG_ATT_MEAN) return 0;
+  if (d == nullptr) return 0;
+  if (c2s::bwd_uses_pool(d)) {  // pooled attention + its gradient (nothing for the same-resolution case k = 1)
+    const int k = d->H > 0 ? d->wa / d->H : 0;
+    return k > 1 ? 2 * static_cast<size_t>(d->n_heads) * d->B * d->T * d->H * d->W * sizeof(float) : 0;
+  }
+  if (d->mode != C2S_AGG_ATT_MEAN) return 0;
   // mean attention map + its gradient
   return 2 * static_cast<size_t>(d->B) * d->T * d->ha * d->wa * sizeof(float);
 }
@@ -616,6 +651,9 @@ int c2s_agg_backward(const c2s_agg_desc* d, const void* x, const float* attn, co
   int scale_class = 0;
   float* gmean = nullptr;
   size_t n_mean = 0;
+  float* gpool = nullptr;  // AvgPool2d branch: gradient of the pooled maps, spread over the windows at the end
+  size_t n_pool = 0;
+  int pool_k = 0;
   if (d->mode == C2S_AGG_MEAN) {
     a.attn = nullptr, a.gattn = nullptr;
     a.n_heads = 1, a.ha = 1, a.wa = 1, a.cpg = d->C, a.uniform = 1;
@@ -625,12 +663,33 @@ int c2s_agg_backward(const c2s_agg_desc* d, const void* x, const float* attn, co
     C2S_CHECK_ARG(attn != nullptr, "c2s_agg_backward: attn is NULL for an attention mode");
     C2S_CHECK_ARG(grad_attn == nullptr || x != nullptr, "c2s_agg_backward: x is needed for grad_attn");
     C2S_CHECK_ARG(d->n_heads > 0 && d->ha > 0 && d->wa > 0, "c2s_agg_backward: bad attention shape");
-    if (d->mode == C2S_AGG_ATT_GROUP && !(d->H > d->wa))
-      C2S_UNSUPPORTED("c2s_agg_backward: the AvgPool2d branch (attention %dx%d not coarser than x %dx%d) has no "
-                      "backward kernel", d->ha, d->wa, d->H, d->W);
     int heads = d->n_heads;
     const float* amap = attn;
     float* gmap = grad_attn;
+    int ha = d->ha, wa = d->wa;
+    if (bwd_uses_pool(d)) {  // temporal_aggregator.py:28-29
+      pool_k = d->wa / d->H;
+      C2S_CHECK_ARG(pool_k >= 1, "c2s_agg_backward: AvgPool2d kernel size would be 0");
+      const int ho = d->ha / pool_k, wo = d->wa / pool_k;
+      C2S_CHECK_ARG(ho == d->H && wo == d->W,
+                    "c2s_agg_backward: pooled attention %dx%d does not match x %dx%d (the reference fails to broadcast)",
+                    ho, wo, d->H, d->W);
+      if (pool_k > 1) {
+        n_pool = static_cast<size_t>(heads) * d->B * d->T * ho * wo;
+        C2S_CHECK_ARG(workspace != nullptr && workspace_bytes >= 2 * n_pool * sizeof(float),
+                      "c2s_agg_backward: the AvgPool2d branch needs %zu workspace bytes", 2 * n_pool * sizeof(float));
+        float* pooled = static_cast<float*>(workspace);
+        pool_attn_kernel<<<ceil_div(n_pool, 256), 256, 0, stream>>>(attn, pooled, d->ha, d->wa, ho, wo, pool_k, n_pool);
+        C2S_LAUNCH_CHECK("avg_pool");
+        amap = pooled;
+        if (grad_attn != nullptr) {
+          gpool = pooled + n_pool;
+          C2S_CUDA(cudaMemsetAsync(gpool, 0, n_pool * sizeof(float), stream));
+          gmap = gpool;
+        }
+      }
+      ha = ho, wa = wo;
+    }
     if (d->mode == C2S_AGG_ATT_MEAN) {
       n_mean = static_cast<size_t>(d->B) * d->T * d->ha * d->wa;
       C2S_CHECK_ARG(workspace != nullptr && workspace_bytes >= 2 * n_mean * sizeof(float),
@@ -648,11 +707,11 @@ int c2s_agg_backward(const c2s_agg_desc* d, const void* x, const float* attn, co
     }
     C2S_CHECK_ARG(d->C % heads == 0, "c2s_agg_backward: C=%d is not divisible by n_heads=%d", d->C, heads);
     a.attn = amap, a.gattn = gmap;
-    a.n_heads = heads, a.ha = d->ha, a.wa = d->wa, a.cpg = d->C / heads;
-    a.sy = static_cast<float>(d->ha) / static_cast<float>(d->H);
-    a.sx = static_cast<float>(d->wa) / static_cast<float>(d->W);
+    a.n_heads = heads, a.ha = ha, a.wa = wa, a.cpg = d->C / heads;
+    a.sy = static_cast<float>(ha) / static_cast<float>(d->H);
+    a.sx = static_cast<float>(wa) / static_cast<float>(d->W);
     for (int s : {2, 4, 8})
-      if (d->H == s * d->ha && d->W == s * d->wa) scale_class = s;
+      if (d->H == s * ha && d->W == s * wa) scale_class = s;
   }
   const int cpt = (a.cpg % 4 == 0) ? 4 : (a.cpg % 2 == 0 ? 2 : 1);
   const bool bf16 = d->dtype == C2S_BF16;
@@ -704,6 +763,11 @@ int c2s_agg_backward(const c2s_agg_desc* d, const void* x, const float* attn, co
   if (gmean != nullptr) {
     spread_head_mean_kernel<<<ceil_div(n_mean, 256), 256, 0, stream>>>(gmean, grad_attn, d->n_heads, n_mean);
     C2S_LAUNCH_CHECK("spread_head_mean");
+  }
+  if (gpool != nullptr) {
+    const size_t n_in = static_cast<size_t>(d->n_heads) * d->B * d->T * d->ha * d->wa;
+    unpool_grad_kernel<<<ceil_div(n_in, 256), 256, 0, stream>>>(gpool, grad_attn, d->ha, d->wa, d->H, d->W, pool_k, n_in);
+    C2S_LAUNCH_CHECK("avg_unpool");
   }
   return C2S_OK;
 }

@@ -30,44 +30,60 @@ struct TileArgs {
   float pad_value;
 };
 
+// 8 consecutive raw values as floats: 8-byte loads when the address allows it (a 10980-pixel int16 row starts on an
+// 8-byte boundary, a 16-byte one only every other row), scalar loads at ragged edges
 template <typename S>
-__device__ __forceinline__ float raw_value(const S* p) {
-  return static_cast<float>(__ldg(p));
+__device__ __forceinline__ void load_raw8(const S* src, int n_inside, float (&raw)[8]) {
+  if (n_inside == 8 && (reinterpret_cast<uintptr_t>(src) & 7u) == 0) {
+    constexpr int CH = sizeof(S);  // uint2 chunks: 2 (16-bit) or 4 (float)
+    uint2 w[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) w[k] = __ldg(reinterpret_cast<const uint2*>(src) + k);
+    const S* v = reinterpret_cast<const S*>(w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) raw[k] = static_cast<float>(v[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) raw[k] = k < n_inside ? static_cast<float>(__ldg(src + k)) : 0.f;  // np.pad(..., 'constant')
+  }
 }
 
-// one thread = 8 consecutive pixels of one (patch, frame, channel, row); consecutive threads = consecutive rows' pieces
+// one CTA = one (patch, frame, channel) plane of patch x patch pixels; one thread = 8 consecutive pixels of a row
 template <typename S, typename D>
 __global__ void __launch_bounds__(kTileThreads) tile_patchify_kernel(const TileArgs a) {
+  const int plane = blockIdx.x;
+  const int c = plane % a.C;
+  const int t = (plane / a.C) % a.T_pad;
+  const int p = plane / (a.C * a.T_pad);
   const int vec_per_row = a.patch / 8;
-  const long long n_vec = static_cast<long long>(a.patch_count) * a.T_pad * a.C * a.patch * vec_per_row;
-  const S* tile = static_cast<const S*>(a.tile);
-  D* out = static_cast<D*>(a.patches);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_vec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int xv = static_cast<int>(i % vec_per_row);
-    long long r = i / vec_per_row;
-    const int y = static_cast<int>(r % a.patch);
-    r /= a.patch;
-    const int c = static_cast<int>(r % a.C);
-    r /= a.C;
-    const int t = static_cast<int>(r % a.T_pad);
-    const int p = static_cast<int>(r / a.T_pad);
+  const int n_vec = a.patch * vec_per_row;
+  D* out = static_cast<D*>(a.patches) + static_cast<size_t>(plane) * a.patch * a.patch;
+  const bool behind = t >= a.T;  // pad_collate: frames behind the series hold pad_value (after the normalisation)
+  const int pid = a.patch_begin + p;
+  const int Y0 = (pid / a.grid_w) * a.patch, X00 = (pid % a.grid_w) * a.patch;
+  const float m = behind ? 0.f : __ldg(a.mean + c), s = behind ? 1.f : __ldg(a.stdv + c);
+  const S* plane_src = behind ? nullptr
+                              : static_cast<const S*>(a.tile) + (static_cast<size_t>(t) * a.C + __ldg(a.order + c)) * a.H * a.W;
+  for (int i = threadIdx.x; i < n_vec; i += kTileThreads) {
+    const int y = i / vec_per_row, xv = i - y * vec_per_row;
     float v[8];
-    if (t >= a.T) {  // pad_collate: frames behind the series hold pad_value (after the normalisation)
+    if (behind) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = a.pad_value;
     } else {
-      const int pid = a.patch_begin + p;
-      const int Y = (pid / a.grid_w) * a.patch + y, X0 = (pid % a.grid_w) * a.patch + xv * 8;
-      const float m = __ldg(a.mean + c), s = __ldg(a.stdv + c);
-      const S* src = tile + ((static_cast<size_t>(t) * a.C + __ldg(a.order + c)) * a.H + Y) * a.W + X0;
+      const int Y = Y0 + y, X0 = X00 + xv * 8;
+      const int inside = Y < a.H ? min(8, max(0, a.W - X0)) : 0;
+      float raw[8];
+      if (inside > 0) {
+        load_raw8(plane_src + static_cast<size_t>(Y) * a.W + X0, inside, raw);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float raw = (Y < a.H && X0 + k < a.W) ? raw_value(src + k) : 0.f;  // np.pad(..., 'constant') of the raw tile
-        v[k] = __fdiv_rn(__fsub_rn(raw, m), s);                                  // exactly (d - mean) / std in fp32
+        for (int k = 0; k < 8; ++k) raw[k] = 0.f;  // zero-padding of the RAW tile (dataset_creator.py:385-388)
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __fdiv_rn(__fsub_rn(raw[k], m), s);  // exactly (d - mean) / std in fp32
     }
-    D* dst = out + i * 8;
+    D* dst = out + static_cast<size_t>(i) * 8;
     if constexpr (sizeof(D) == 2) {
       st_stream_v4(dst, Elem<__nv_bfloat16>::pack(v));
     } else {
@@ -89,11 +105,9 @@ struct ClassArgs {
 template <typename D, int KMAX>
 __global__ void __launch_bounds__(kTileThreads) tile_classmap_kernel(const ClassArgs a) {
   const int pp = a.patch * a.patch;
-  const long long n = static_cast<long long>(a.patch_count) * pp;
   const D* logits = static_cast<const D*>(a.logits);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int p = static_cast<int>(i / pp), q = static_cast<int>(i % pp);
+  const int p = blockIdx.y;  // one patch per grid row
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < pp; q += gridDim.x * blockDim.x) {
     const int pid = a.patch_begin + p;
     const int Y = (pid / a.grid_w) * a.patch + q / a.patch, X = (pid % a.grid_w) * a.patch + q % a.patch;
     if (Y >= a.H || X >= a.W) continue;  // cropped away (prediction.py:332-333)
@@ -139,12 +153,6 @@ int check_tile_desc(const c2s_tile_desc* d, const char* who) {
   return C2S_OK;
 }
 
-int grid_for(long long items) {
-  const long long blocks = (items + kTileThreads - 1) / kTileThreads;
-  const long long cap = 148ll * 16;  // grid-stride loop: a few waves of the chip
-  return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
-}
-
 }  // namespace
 }  // namespace c2s
 
@@ -166,8 +174,9 @@ extern "C" int c2s_tile_patchify(const c2s_tile_desc* d, const void* tile, const
   a.T = d->T, a.T_pad = d->T_pad, a.C = d->C, a.H = d->H, a.W = d->W, a.patch = d->patch;
   a.grid_w = d->grid_w > 0 ? d->grid_w : ceil_div(d->W, d->patch);
   a.patch_begin = d->patch_begin, a.patch_count = d->patch_count, a.pad_value = d->pad_value;
-  const long long n_vec = static_cast<long long>(a.patch_count) * a.T_pad * a.C * a.patch * (a.patch / 8);
-  const int grid = grid_for(n_vec);
+  const long long planes = static_cast<long long>(a.patch_count) * a.T_pad * a.C;
+  if (planes > 0x7fffffffll) C2S_UNSUPPORTED("c2s_tile_patchify: more than 2^31 - 1 (patch, frame, channel) planes in one call");
+  const unsigned grid = static_cast<unsigned>(planes);
   const bool bf = d->dst_dtype == C2S_BF16;
 #define C2S_PATCHIFY(S)                                                                              \
   do {                                                                                               \
@@ -199,7 +208,8 @@ extern "C" int c2s_tile_classmap(const c2s_tile_desc* d, const void* logits, int
   a.K = n_classes, a.H = d->H, a.W = d->W, a.patch = d->patch;
   a.grid_w = d->grid_w > 0 ? d->grid_w : ceil_div(d->W, d->patch);
   a.patch_begin = d->patch_begin, a.patch_count = d->patch_count;
-  const int grid = grid_for(static_cast<long long>(a.patch_count) * a.patch * a.patch);
+  if (a.patch_count > 65535) C2S_UNSUPPORTED("c2s_tile_classmap: more than 65535 patches in one call");
+  const dim3 grid(static_cast<unsigned>(ceil_div(a.patch * a.patch, kTileThreads)), static_cast<unsigned>(a.patch_count));
   const bool bf = d->dst_dtype == C2S_BF16;
   if (n_classes <= 16) {
     if (bf) tile_classmap_kernel<__nv_bfloat16, 16><<<grid, kTileThreads, 0, stream>>>(a);

@@ -130,7 +130,8 @@ class _LTAEBase(nn.Module):
             if use_doy and not add_linear:
                 self.positional_encoder = AbsolutePositionalEncoder(self.d_model // n_head, repeat=n_head)
             else:
-                self.positional_encoder = PositionalEncoder(self.d_model // n_head, T=T, repeat=n_head,
+                # the reference never forwards its own T (tae.py:409-419): the encoder's period is always 1000
+                self.positional_encoder = PositionalEncoder(self.d_model // n_head, repeat=n_head,
                                                             add_linear=add_linear)
             if use_abs_rel_enc:
                 self.positional_encoder_abs = AbsolutePositionalEncoder(self.d_model // n_head, repeat=n_head)

@@ -57,7 +57,80 @@ def copy_valid_frames_(dst: torch.Tensor, src: torch.Tensor, lengths: Sequence[i
     return copied
 
 
-def smart_forward(forward, x: torch.Tensor, pad_value=None, pad_mask: torch.Tensor = None) -> torch.Tensor:
+def frame_slots(pad_mask: torch.Tensor):
+    """(slot, n_valid) for a pad mask of any shape (True = padded): ``slot`` int32, position of every frame among the
+    valid ones (-1 for padded frames), ``n_valid`` a DEVICE int32 scalar -- ``c2s_frame_index``, no host synchronisation."""
+    from . import _lib
+    from .ops import _require_cuda, _stream
+    _require_cuda(pad_mask, "pad_mask")
+    m = pad_mask.reshape(-1)
+    if m.dtype != torch.bool:
+        m = m != 0
+    m = m.contiguous().view(torch.uint8)
+    slot = torch.empty(m.numel(), dtype=torch.int32, device=m.device)
+    count = torch.empty((), dtype=torch.int32, device=m.device)
+    with torch.cuda.device(m.device):
+        status = _lib.load().c2s_frame_index(m.data_ptr(), m.numel(), slot.data_ptr(), count.data_ptr(), _stream(m.device))
+    _lib.check(status, "c2s_frame_index")
+    return slot, count
+
+
+def gather_frames(flat: torch.Tensor, slot: torch.Tensor, n_valid: int) -> torch.Tensor:
+    """``flat[~pad_mask]`` for flat[N, ...]: the valid frames packed in order (``c2s_frames_gather``)."""
+    from . import _lib
+    from .ops import _dtype_code, _require_cuda, _stream
+    _require_cuda(flat, "x")
+    flat = flat.contiguous()
+    packed = torch.empty((n_valid,) + tuple(flat.shape[1:]), dtype=flat.dtype, device=flat.device)
+    with torch.cuda.device(flat.device):
+        status = _lib.load().c2s_frames_gather(flat.data_ptr(), slot.data_ptr(), packed.data_ptr(), flat.shape[0],
+                                               flat[0].numel(), _dtype_code(flat, "x"), _stream(flat.device))
+    _lib.check(status, "c2s_frames_gather")
+    return packed
+
+
+def scatter_frames(packed: torch.Tensor, slot: torch.Tensor, pad_value: float) -> torch.Tensor:
+    """``temp = full(pad_value); temp[~pad_mask] = packed`` in one pass (``c2s_frames_scatter``)."""
+    from . import _lib
+    from .ops import _dtype_code, _require_cuda, _stream
+    _require_cuda(packed, "packed")
+    packed = packed.contiguous()
+    out = torch.empty((slot.numel(),) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+    with torch.cuda.device(packed.device):
+        status = _lib.load().c2s_frames_scatter(packed.data_ptr(), slot.data_ptr(), out.data_ptr(), slot.numel(),
+                                                packed[0].numel(), _dtype_code(packed, "packed"), float(pad_value),
+                                                _stream(packed.device))
+    _lib.check(status, "c2s_frames_scatter")
+    return out
+
+
+class _Gather(torch.autograd.Function):
+    """gather_frames with its adjoint (a scatter with zeros on the padded frames)."""
+
+    @staticmethod
+    def forward(ctx, flat, slot, n_valid):
+        ctx.slot = slot
+        return gather_frames(flat, slot, n_valid)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return scatter_frames(grad, ctx.slot, 0.0), None, None
+
+
+class _Scatter(torch.autograd.Function):
+    """scatter_frames with its adjoint (a gather: the padded frames are constants)."""
+
+    @staticmethod
+    def forward(ctx, packed, slot, pad_value):
+        ctx.slot, ctx.n_valid = slot, packed.shape[0]
+        return scatter_frames(packed, slot, pad_value)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return gather_frames(grad, ctx.slot, ctx.n_valid), None, None
+
+
+def smart_forward(forward, x: torch.Tensor, pad_value=None, pad_mask: torch.Tensor = None, lengths=None) -> torch.Tensor:
     """``TemporallySharedBlock.smart_forward`` (temp_shared_block.py:18-47) without its waste: apply ``forward`` (a block
     shared across the sequence, [N, C, H, W] -> [N, C', H', W']) to the non-padded frames of x[B, T, C, H, W] and
     return [B, T, C', H', W'] with ``pad_value`` on the padded frames.
@@ -66,7 +139,11 @@ def smart_forward(forward, x: torch.Tensor, pad_value=None, pad_mask: torch.Tens
     (``pad_mask_from_input``) or from the caller (``pad_mask`` [B, T], e.g. the one the model already derived from the
     raw input: padded frames stay exactly ``pad_value`` through the encoder, temp_shared_block.py:30-40) instead of
     comparing the whole tensor again; the output shape is taken from the real forward instead of an extra forward of
-    an all-zero dummy batch; the valid frames are gathered once by index."""
+    an all-zero dummy batch; the valid frames are packed and put back by two copy kernels driven by a device-side
+    scan of the mask (``c2s_frame_index`` / ``c2s_frames_gather`` / ``c2s_frames_scatter``) instead of boolean
+    indexing.  ``lengths`` (valid frames per sample, known on the host since ``pad_collate``, src/utils.py:20-66)
+    makes the call free of host synchronisations; without it the number of valid frames is read back once, because
+    the batch size of ``forward`` has to be known on the host."""
     if x.dim() == 4:
         return forward(x)
     b, t, c, h, w = x.shape
@@ -77,13 +154,13 @@ def smart_forward(forward, x: torch.Tensor, pad_value=None, pad_mask: torch.Tens
     if pad_mask is None:
         from .ops import pad_mask_from_input
         pad_mask = pad_mask_from_input(x, pad_value)
-    valid = (~pad_mask.reshape(-1)).nonzero(as_tuple=True)[0]  # the one host synchronisation (the reference has two)
-    if valid.numel() == b * t:
+    slot, count = frame_slots(pad_mask)
+    n_valid = int(sum(int(v) for v in lengths)) if lengths is not None else int(count.item())
+    if n_valid == b * t:
         out = forward(flat)
         return out.view(b, t, *out.shape[1:])
-    if valid.numel() == 0:
+    if n_valid == 0:
         raise RuntimeError("smart_forward: every frame is padded (the reference fails on the empty batch too)")
-    part = forward(flat.index_select(0, valid))
-    out = torch.full((b * t, *part.shape[1:]), float(pad_value), dtype=part.dtype, device=part.device)
-    out.index_copy_(0, valid, part)
+    part = forward(_Gather.apply(flat, slot, n_valid))
+    out = _Scatter.apply(part, slot, float(pad_value))
     return out.view(b, t, *out.shape[1:])

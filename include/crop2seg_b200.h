@@ -107,7 +107,8 @@ int c2s_agg_skipconv_forward(const c2s_agg_desc* desc, const void* x, const floa
  * grad_x / grad_attn may be NULL when not needed; grad_attn must be ZERO-FILLED by the caller (it is
  * accumulated with float atomics, so its low bits depend on the execution order -- the reference's own
  * backward is non-deterministic too, train.py:623-626).  x is only read when grad_attn is requested.
- * The AvgPool2d branch (attention finer than x, never taken by the shipped models) returns C2S_ERR_UNSUPPORTED. */
+ * The AvgPool2d branch (attention not coarser than x, temporal_aggregator.py:28-29) pools the attention into the
+ * workspace, differentiates against the pooled maps and spreads their gradient over the k x k windows. */
 size_t c2s_agg_backward_workspace_bytes(const c2s_agg_desc* desc);
 int c2s_agg_backward(const c2s_agg_desc* desc, const void* x, const float* attn, const uint8_t* pad_mask,
                      const void* grad_out, void* grad_x, float* grad_attn, void* workspace,
@@ -118,6 +119,21 @@ int c2s_agg_backward(const c2s_agg_desc* desc, const void* x, const float* attn,
  * 1 = padded.  A frame is left at the first value that differs, so only padded frames are read to the end. */
 int c2s_pad_mask(const void* x, int32_t dtype, int64_t n_frames, int64_t frame_elems, float pad_value,
                  uint8_t* mask, void* stream);
+
+/* Lengths-aware frame packing for blocks shared across the sequence -- TemporallySharedBlock.smart_forward,
+ * temp_shared_block.py:18-47: `out[~pad_mask]` / `temp[~pad_mask] = ...` without the
+ * nonzero() host synchronisation of boolean indexing.
+ *   c2s_frame_index   : slot[f] = number of valid frames before f (pad_mask[f] == 0), -1 for padded frames;
+ *                       *n_valid = number of valid frames (device scalar).  pad_mask: uint8 [n_frames].
+ *   c2s_frames_gather : packed[slot[f]] = frames[f] for every valid frame; frames: [n_frames][frame_elems],
+ *                       packed: [>= n_valid][frame_elems].  Padded frames are not read.
+ *   c2s_frames_scatter: out[f] = slot[f] >= 0 ? packed[slot[f]] : pad_value; out: [n_frames][frame_elems].
+ * dtype: enum c2s_dtype of frames / packed / out.  At most 65535 frames per gather / scatter call. */
+int c2s_frame_index(const uint8_t* pad_mask, int64_t n_frames, int32_t* slot, int32_t* n_valid, void* stream);
+int c2s_frames_gather(const void* frames, const int32_t* slot, void* packed, int64_t n_frames, int64_t frame_elems,
+                      int32_t dtype, void* stream);
+int c2s_frames_scatter(const void* packed, const int32_t* slot, void* out, int64_t n_frames, int64_t frame_elems,
+                       int32_t dtype, float pad_value, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * LTAE / LTAE4WTAE                                             tae.py:349-635

@@ -74,3 +74,62 @@ def test_smart_forward_matches_the_reference_block():
     assert tuple(full.shape) == outs["out"].shape
     pad = pad_mask_from_input(inp["x"], 0.0)
     assert np.all(out.cpu().numpy()[pad] == 0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("frame_shape", [(3, 8, 8), (5, 3, 3), (1, 1, 1)])
+def test_frame_packing_kernels_match_boolean_indexing(dtype, frame_shape):
+    """c2s_frame_index / gather / scatter == `out[~pad_mask]` and `temp[~pad_mask] = ...` (temp_shared_block.py:30-40),
+    bit for bit, with 16-byte and odd-sized frames, more frames than one scan round, all-valid and all-padded masks."""
+    import crop2seg_b200 as c2s
+    rng = np.random.RandomState(17)
+    n = 2500
+    pad = rng.uniform(size=n) < 0.3
+    pad[:40] = True
+    pad[-1] = False
+    x = torch.from_numpy(rng.standard_normal((n,) + frame_shape).astype(np.float32)).to(dtype).cuda()
+    mask = torch.from_numpy(pad).cuda()
+    slot, count = c2s.frame_slots(mask)
+    n_valid = int((~pad).sum())
+    assert int(count.item()) == n_valid
+    ref_slot = np.where(pad, -1, np.cumsum(~pad) - 1).astype(np.int32)
+    assert np.array_equal(slot.cpu().numpy(), ref_slot)
+    packed = c2s.gather_frames(x, slot, n_valid)
+    assert torch.equal(packed, x[~mask])
+    out = c2s.scatter_frames(packed * 2, slot, -3.5)
+    want = torch.full_like(x, -3.5)
+    want[~mask] = x[~mask] * 2
+    assert torch.equal(out, want)
+    for m in (np.zeros(70, bool), np.ones(70, bool)):
+        s2, c2 = c2s.frame_slots(torch.from_numpy(m).cuda())
+        assert int(c2.item()) == int((~m).sum())
+        assert np.array_equal(s2.cpu().numpy(), np.where(m, -1, np.arange(70)).astype(np.int32))
+
+
+@pytest.mark.gpu
+def test_smart_forward_without_host_sync_and_with_gradients():
+    """With the lengths known on the host (pad_collate) smart_forward never reads the device; its gradients equal the
+    ones of boolean indexing."""
+    import crop2seg_b200 as c2s
+    cfg, inp, params, outs = load("smart_forward")
+    conv = torch.nn.Conv2d(3, 5, kernel_size=4, stride=2, padding=1)
+    conv.load_state_dict({k[len("conv."):]: torch.from_numpy(v) for k, v in params.items()})
+    conv = conv.cuda()
+    fwd = lambda z: torch.relu(conv(z))  # noqa: E731
+    x = torch.from_numpy(inp["x"]).cuda()
+    pad = pad_mask_from_input(inp["x"], 0.0)
+    lengths = (~pad).sum(axis=1).tolist()
+    out = c2s.smart_forward(fwd, x, pad_value=cfg["pad_value"], pad_mask=torch.from_numpy(pad).cuda(), lengths=lengths)
+    assert np.abs(out.detach().cpu().numpy() - outs["out"]).max() < 1e-5
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    g_kernel = conv.weight.grad.clone()
+    conv.weight.grad = None
+    b, t = x.shape[:2]
+    flat = x.view(b * t, *x.shape[2:])
+    m = torch.from_numpy(pad.reshape(-1)).cuda()
+    temp = torch.ones((b * t,) + tuple(out.shape[2:]), device="cuda") * cfg["pad_value"]
+    temp[~m] = fwd(flat[~m])  # the reference's statements (temp_shared_block.py:30-40)
+    (temp.view_as(out) * w).sum().backward()
+    assert torch.allclose(conv.weight.grad, g_kernel, rtol=1e-5, atol=1e-6)
