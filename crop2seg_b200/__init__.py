@@ -7,6 +7,7 @@ Public surface (mirrors the reference's interface for this path, SURVEY.md secti
     install()                               swap the three classes into the reference's model files
     shard_patches()                         patch sharding for multi-GPU inference (sharding.py)
     copy_valid_frames_()                    host -> device staging that skips padded frames (staging.py)
+    CrossEntropyLoss, FocalCELoss, boundary_target   loss side of the training step (losses.py)
     TilePatchifier, ClassMap                tile pipeline edges on the device: raw tile -> model inputs, logits -> class map (tile.py)
 
 The arithmetic lives in ``lib/libcrop2seg_b200.so`` (``include/crop2seg_b200.h``), built in-tree by
@@ -19,5 +20,7 @@ from .staging import copy_valid_frames_, frame_slots, gather_frames, scatter_fra
 from . import ops  # noqa: F401
 from .tile import ClassMap, TilePatchifier, patch_grid  # noqa: F401
 from .ops import pad_mask_from_input  # noqa: F401
+from . import losses  # noqa: F401
+from .losses import CrossEntropyLoss, FocalCELoss, boundary_target  # noqa: F401
 
-__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "smart_forward", "pad_mask_from_input", "ops", "TilePatchifier", "ClassMap", "patch_grid", "frame_slots", "gather_frames", "scatter_frames"]
+__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "smart_forward", "pad_mask_from_input", "ops", "TilePatchifier", "ClassMap", "patch_grid", "frame_slots", "gather_frames", "scatter_frames", "losses", "CrossEntropyLoss", "FocalCELoss", "boundary_target"]

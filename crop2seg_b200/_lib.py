@@ -30,7 +30,9 @@ EXPORTS = (
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
     "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward", "c2s_ltae_inconv_grad",
     "c2s_tile_patchify", "c2s_tile_classmap", "c2s_frame_index", "c2s_frames_gather", "c2s_frames_scatter",
+    "c2s_boundary_target", "c2s_seg_loss_workspace_bytes", "c2s_seg_loss_forward", "c2s_seg_loss_backward",
 )
+LOSS_CROSS_ENTROPY, LOSS_FOCAL = 0, 1  # enum c2s_loss_kind
 RAW_I16, RAW_U16, RAW_F32 = 0, 1, 2  # enum c2s_raw_dtype
 
 
@@ -46,6 +48,11 @@ class SkipConvParams(ctypes.Structure):
 class TileDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("T", "T_pad", "C", "H", "W", "patch", "grid_h", "grid_w", "patch_begin",
                                               "patch_count", "src_dtype", "dst_dtype")] + [("pad_value", ctypes.c_float)]
+
+
+class LossDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "K", "H", "W", "dtype", "kind", "ignore_index", "size_average")] + \
+               [("gamma", ctypes.c_float), ("label_smoothing", ctypes.c_float)]
 
 
 class LtaeDesc(ctypes.Structure):
@@ -158,6 +165,14 @@ def load() -> ctypes.CDLL:
         lib.c2s_frames_gather.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, i32, vp]
         lib.c2s_frames_scatter.restype = i32
         lib.c2s_frames_scatter.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, i32, ctypes.c_float, vp]
+        lib.c2s_boundary_target.restype = i32
+        lib.c2s_boundary_target.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+        lib.c2s_seg_loss_workspace_bytes.restype = sz
+        lib.c2s_seg_loss_workspace_bytes.argtypes = []
+        lib.c2s_seg_loss_forward.restype = i32
+        lib.c2s_seg_loss_forward.argtypes = [ctypes.POINTER(LossDesc), vp, vp, vp, vp, vp, sz, vp]
+        lib.c2s_seg_loss_backward.restype = i32
+        lib.c2s_seg_loss_backward.argtypes = [ctypes.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp]
         got = lib.c2s_abi_version()
         if got != C2S_ABI_VERSION:
             raise C2SError(f"ABI mismatch: library reports version {got}, binding expects {C2S_ABI_VERSION}")

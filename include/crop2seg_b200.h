@@ -301,6 +301,46 @@ int c2s_tile_classmap(const c2s_tile_desc* desc, const void* logits, int32_t n_c
                       void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Loss side of the training step
+ *   get_dilated + boundary labels        src/learning/utils.py:198-222, 283-285
+ *   nn.CrossEntropyLoss(weight, label_smoothing) on [B,K,H,W] scores   train.py:462-467, learning/utils.py:322
+ *   FocalCELoss(gamma=2.0)               src/learning/focal_loss.py:7-44, learning/utils.py:269, 318
+ * ---------------------------------------------------------------------------------------- */
+enum c2s_loss_kind { C2S_LOSS_CROSS_ENTROPY = 0, C2S_LOSS_FOCAL = 1 };
+
+typedef struct c2s_loss_desc {
+  int32_t B, K, H, W;    /* scores[B,K,H,W], target[B,H,W] int64                                              */
+  int32_t dtype;         /* enum c2s_dtype of the scores and of their gradient                                */
+  int32_t kind;          /* enum c2s_loss_kind                                                                */
+  int32_t ignore_index;  /* FocalCELoss.ignore_index (-100); nn.CrossEntropyLoss always ignores -100           */
+  int32_t size_average;  /* FocalCELoss.size_average: mean over the kept pixels (1) or sum (0)                 */
+  float gamma;           /* FocalCELoss.gamma                                                                  */
+  float label_smoothing; /* nn.CrossEntropyLoss(label_smoothing=...)                                           */
+} c2s_loss_desc;
+
+/* boundary[b,y,x] = 1 where more than one class occurs in the 4- (or 8-) neighbourhood of (y,x) including itself, the
+ * image border adding no class (zero padding of the one-hot planes), else 0 -- `torch.where(get_dilated(y, K, dev,
+ * connectivity).sum(1) > 1, 1, 0)` without the B x K x H x W one-hot tensor and its grouped convolution.
+ * target, boundary: int64 [B,H,W]. */
+int c2s_boundary_target(const int64_t* target, int32_t B, int32_t H, int32_t W, int32_t connectivity, int64_t* boundary,
+                        void* stream);
+
+/* loss (device float scalar):
+ *   kind CROSS_ENTROPY: sum_i [(1-eps) w[y_i] nll_i + eps/K sum_k w[k] (-log p_ik)] / sum_i w[y_i]   over y_i != -100
+ *   kind FOCAL        : mean (or sum) over y_i != ignore_index of -(1 - p_i)^gamma log p_i,  p_i = softmax(scores_i)[y_i];
+ *                       with a class weight the reference's [N,1] x [N] broadcast (focal_loss.py:34-36) is kept: the loss
+ *                       is (sum_i w[y_i]) (sum_j focal_j), divided by N^2 for the mean
+ * weight: float32 [K] or NULL.  Labels outside [0, K) that are not the ignore value are dropped like ignored ones (torch
+ * raises a device assertion for them).  The workspace (c2s_seg_loss_workspace_bytes, 8-byte aligned) carries the
+ * normalisation from the forward to c2s_seg_loss_backward, which writes grad_scores = grad_loss * d loss / d scores
+ * (grad_loss: device float scalar). Deterministic: fixed-order two-stage reduction, no atomics. */
+size_t c2s_seg_loss_workspace_bytes(void);
+int c2s_seg_loss_forward(const c2s_loss_desc* desc, const void* scores, const int64_t* target, const float* weight,
+                         float* loss, void* workspace, size_t workspace_bytes, void* stream);
+int c2s_seg_loss_backward(const c2s_loss_desc* desc, const void* scores, const int64_t* target, const float* weight,
+                          const void* workspace, const float* grad_loss, void* grad_scores, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * library services
  * ---------------------------------------------------------------------------------------- */
 int c2s_abi_version(void);
