@@ -15,7 +15,7 @@ The arithmetic lives in ``lib/libcrop2seg_b200.so`` (``include/crop2seg_b200.h``
 """
 from .modules import LTAE, LTAE4WTAE, TemporalAggregator  # noqa: F401
 from .install import install, uninstall  # noqa: F401
-from .sharding import gather_shards, shard_bounds, shard_patches  # noqa: F401
+from .sharding import GradientBucket, gather_shards, shard_bounds, shard_patches  # noqa: F401
 from .staging import copy_valid_frames_, frame_slots, gather_frames, scatter_frames, smart_forward, valid_lengths  # noqa: F401
 from . import ops  # noqa: F401
 from .tile import ClassMap, TilePatchifier, patch_grid  # noqa: F401
@@ -23,4 +23,4 @@ from .ops import pad_mask_from_input  # noqa: F401
 from . import losses  # noqa: F401
 from .losses import CrossEntropyLoss, FocalCELoss, boundary_target  # noqa: F401
 
-__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "smart_forward", "pad_mask_from_input", "ops", "TilePatchifier", "ClassMap", "patch_grid", "frame_slots", "gather_frames", "scatter_frames", "losses", "CrossEntropyLoss", "FocalCELoss", "boundary_target"]
+__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "smart_forward", "pad_mask_from_input", "ops", "TilePatchifier", "ClassMap", "patch_grid", "frame_slots", "gather_frames", "scatter_frames", "GradientBucket", "losses", "CrossEntropyLoss", "FocalCELoss", "boundary_target"]

@@ -28,7 +28,7 @@ EXPORTS = (
     "c2s_agg_workspace_bytes", "c2s_agg_forward", "c2s_agg_backward_workspace_bytes", "c2s_agg_backward",
     "c2s_agg_skipconv_workspace_bytes", "c2s_agg_skipconv_forward", "c2s_pad_mask",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
-    "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward", "c2s_ltae_inconv_grad",
+    "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward", "c2s_ltae_inconv_grad", "c2s_ltae_fold_backward",
     "c2s_tile_patchify", "c2s_tile_classmap", "c2s_frame_index", "c2s_frames_gather", "c2s_frames_scatter",
     "c2s_boundary_target", "c2s_seg_loss_workspace_bytes", "c2s_seg_loss_forward", "c2s_seg_loss_backward",
 )
@@ -85,6 +85,15 @@ class LtaeBwdIo(ctypes.Structure):
 
 LTAE_MLP_BWD_IO_FIELDS = ("o_rows", "grad_out", "bn_mean", "bn_var", "grad_o", "grad_mlp_weight", "grad_mlp_bias",
                           "grad_bn_weight", "grad_bn_bias", "grad_out_norm_weight", "grad_out_norm_bias")
+
+
+LTAE_FOLD_BWD_IO_FIELDS = ("grad_u", "grad_cpos", "grad_gamma_direct", "grad_beta_direct", "grad_in_norm_weight",
+                           "grad_in_norm_bias", "grad_inconv_weight", "grad_inconv_bias", "grad_query", "grad_key_weight",
+                           "grad_key_bias", "grad_pe")
+
+
+class LtaeFoldBwdIo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_FOLD_BWD_IO_FIELDS]
 
 
 class LtaeMlpBwdIo(ctypes.Structure):
@@ -173,6 +182,9 @@ def load() -> ctypes.CDLL:
         lib.c2s_seg_loss_forward.argtypes = [ctypes.POINTER(LossDesc), vp, vp, vp, vp, vp, sz, vp]
         lib.c2s_seg_loss_backward.restype = i32
         lib.c2s_seg_loss_backward.argtypes = [ctypes.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp]
+        lib.c2s_ltae_fold_backward.restype = i32
+        lib.c2s_ltae_fold_backward.argtypes = [ctypes.POINTER(LtaeDesc), ctypes.POINTER(LtaeParams),
+                                               ctypes.POINTER(LtaeFoldBwdIo), vp, sz, vp]
         got = lib.c2s_abi_version()
         if got != C2S_ABI_VERSION:
             raise C2SError(f"ABI mismatch: library reports version {got}, binding expects {C2S_ABI_VERSION}")

@@ -9,9 +9,11 @@
     A  ``c2s_ltae_backward`` (CUDA, ``csrc/c2s_ltae_bwd.cu``) does everything that touches the [N, T, C] features:
        it recomputes the attention, back-propagates through the value sums, the softmax, the scores and the input
        GroupNorm, writes grad_x and reduces the gradients of the folded score weights U[C,16] and cpos[B,T,16];
-    F  the chain from (grad_U, grad_cpos, grad_pe) to the state_dict tensors (Q, fc1_k, inconv, in_norm,
-       positional tables): the adjoint of the weight folding of ``csrc/c2s_ltae_prep.cu`` on [16, 256]-sized
-       tensors, plus ``c2s_ltae_inconv_grad`` for the direct in-projection terms.
+    F  ``c2s_ltae_fold_backward`` (CUDA, ``csrc/c2s_ltae_fold_bwd.cu``, two launches on stage A's workspace): the
+       chain from (grad_U, grad_cpos) to the state_dict tensors (Q, fc1_k, inconv, in_norm) -- the adjoint of the
+       weight folding of ``csrc/c2s_ltae_prep.cu`` -- plus ``c2s_ltae_inconv_grad`` for the direct in-projection
+       terms.  Only LEARNABLE positional tables (use_doy / use_abs_rel_enc / add_linear) add torch autograd of the
+       [B, T, 256] table construction.
   No [N, T, D] activation is ever materialised.  There is no torch fallback: encoders without ``inconv``
   (d_model=None) and output GroupNorm groups wider than 16 channels raise in training (forward-only support).
 """
@@ -139,54 +141,21 @@ def _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params
              "pe_fc_weight", "pe_fc_bias", "pe_abs_fc_weight", "pe_abs_fc_bias")
     if any(need.get(k) for k in front):
         with torch.no_grad():
-            dk = cfg["d_k"]
-            rs = 1.0 / (dk ** 0.5)
-            gamma, beta = raw["in_norm_weight"].float(), raw["in_norm_bias"].float()
-            wc, bc = raw["inconv_weight"].float().reshape(D, c), raw["inconv_bias"].float()
-            q, wk = raw["query"].float().reshape(h, dk), raw["key_weight"].float().reshape(h, dk, D)
-            bk = raw["key_bias"].float().reshape(h, dk)
-            qk = torch.einsum("hj,hjd->hd", q, wk) * rs           # [h, D]
-            m = qk @ wc                                            # [h, C]: U = m^T * gamma
-            g_u = res["grad_u"][:, :h]                             # [C, h]
-            g_cpos = res["grad_cpos"][:, :, :h].reshape(b * t, h)  # [B T, h]
-            g_m = g_u.t() * gamma[None, :]
-            g_qk = g_m @ wc.t()
-            g_wc = qk.t() @ g_m
-            g_gamma = (g_u * m.t()).sum(1)
-            wb = bc + wc @ beta                                    # cpos = qk (wb + pe) + q . bk / sqrt(dk)
-            g_ub = g_cpos.sum(0)
-            g_qk += g_ub[:, None] * wb[None, :]
-            g_wb = g_ub @ qk
+            # one call (two launches) on the workspace of stage A; the in-projection's direct term is added by
+            # c2s_ltae_inconv_grad (one launch over the rows)
+            want = {k: bool(need.get(k)) for k in front[:7]}
+            shapes = {k: tuple(raw[k].shape) for k in front[:7] if raw.get(k) is not None}
+            pe_learnable_now = pe_learnable and cfg["pe_mode"] != _lib.PE_NONE
+            if pe_learnable_now and res["grad_pe"] is None:  # attention-only encoders: the table acts through the scores only
+                res["grad_pe"] = torch.zeros((b, t, D), dtype=torch.float32, device=x.device)
+            folded = ops.ltae_fold_backward(res, want, shapes, grad_pe_through_scores=pe_learnable_now)
             g_pe = res["grad_pe"]
-            if cfg["pe_mode"] != _lib.PE_NONE:
-                pe = _positional(cfg, {k: (v.float() if v is not None and v.is_floating_point() else v)
-                                       for k, v in raw.items()}, positions, 0).reshape(b * t, D)
-                g_qk += g_cpos.t() @ pe
-                via_cpos = (g_cpos @ qk).view(b, t, D)
-                g_pe = via_cpos if g_pe is None else g_pe + via_cpos
-            g_wc += g_wb[:, None] * beta[None, :]
-            if need["in_norm_weight"]:
-                grads["in_norm_weight"] = g_gamma + (0 if attn_only else res["grad_gamma"])
-            if need["in_norm_bias"]:
-                grads["in_norm_bias"] = wc.t() @ g_wb + (0 if attn_only else res["grad_beta"])
-            if not attn_only:
-                if need["inconv_weight"]:  # direct terms: one kernel over the rows (c2s_ltae_inconv_grad)
-                    g_wc = g_wc.contiguous()
-                    g_wb = g_wb.contiguous().clone() if need["inconv_bias"] else g_wb
-                    ops.ltae_inconv_grad(g_o.contiguous(), res["zn_rows"].contiguous(), res["sa_rows"].contiguous(), g_wc,
-                                         g_wb if need["inconv_bias"] else None, h)
-                elif need["inconv_bias"]:
-                    g_wb = g_wb + torch.einsum("nhi,nh->hi", g_o.view(n, h, dh), res["sa_rows"][:, :h]).reshape(D)
-            if need["inconv_weight"]:
-                grads["inconv_weight"] = g_wc
-            if need["inconv_bias"]:
-                grads["inconv_bias"] = g_wb
-            if need["query"]:
-                grads["query"] = torch.einsum("hd,hjd->hj", g_qk, wk) * rs + g_ub[:, None] * bk * rs
-            if need["key_weight"]:
-                grads["key_weight"] = q[:, :, None] * g_qk[:, None, :] * rs
-            if need["key_bias"]:
-                grads["key_bias"] = g_ub[:, None] * q * rs
+            if not attn_only and (need["inconv_weight"] or need["inconv_bias"]):
+                g_wc = folded["inconv_weight"].view(D, c) if need["inconv_weight"] else torch.zeros((D, c), dtype=torch.float32, device=x.device)
+                g_wb = folded.get("inconv_bias")
+                ops.ltae_inconv_grad(g_o.contiguous(), res["zn_rows"].contiguous(), res["sa_rows"].contiguous(), g_wc,
+                                     g_wb, h)
+            grads.update(folded)
         pe_names = [k for k in ("pe_fc_weight", "pe_fc_bias", "pe_abs_fc_weight", "pe_abs_fc_bias")
                     if need.get(k) and raw[k] is not None]
         if pe_names and g_pe is not None:  # learnable tables / add_linear: the small table graph through autograd

@@ -629,7 +629,9 @@ size_t c2s_ltae_backward_workspace_bytes(const c2s_ltae_desc* d) {
   c2s_ltae_desc t = *d;  // the same flag surgery as c2s_ltae_backward
   t.flags &= ~C2S_LTAE_REUSE_FOLDED;
   t.flags |= C2S_LTAE_BN_BATCH_STATS;
-  return c2s_ltae_workspace_bytes(&t);
+  // + the scratch of c2s_ltae_fold_backward (g_qk [h][D], g_ub [16]), which runs on the same workspace
+  return c2s_ltae_workspace_bytes(&t) +
+         (c2s::align64(static_cast<size_t>(d->n_head) * d->d_model) + c2s::align64(c2s::kMaxHeads)) * sizeof(float);
 }
 
 int c2s_ltae_backward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const void* x, const void* positions,

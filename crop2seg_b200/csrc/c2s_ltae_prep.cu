@@ -195,11 +195,11 @@ int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* p
   C2S_LAUNCH_CHECK("ltae_fold_wb");
   fold_ub_kernel<<<kMaxHeads, kPrepThreads, 0, stream>>>(qk, ws + lay.wb, p.query, p.key_bias, ws + lay.ub, h, dk, D);
   C2S_LAUNCH_CHECK("ltae_fold_ub");
+  if (need_transposed && d.has_inconv) {  // attention-only encoders too: c2s_ltae_fold_backward reads Wc^T
+    transpose_kernel<<<ceil_div(D * C, kPrepThreads), kPrepThreads, 0, stream>>>(p.inconv_weight, ws + lay.wct, D, C);
+    C2S_LAUNCH_CHECK("ltae_transpose_inconv");
+  }
   if (!attn_only && need_transposed) {
-    if (d.has_inconv) {
-      transpose_kernel<<<ceil_div(D * C, kPrepThreads), kPrepThreads, 0, stream>>>(p.inconv_weight, ws + lay.wct, D, C);
-      C2S_LAUNCH_CHECK("ltae_transpose_inconv");
-    }
     transpose_kernel<<<ceil_div(d.c_out * D, kPrepThreads), kPrepThreads, 0, stream>>>(p.mlp_weight, ws + lay.wmt,
                                                                                       d.c_out, D);
     C2S_LAUNCH_CHECK("ltae_transpose_mlp");

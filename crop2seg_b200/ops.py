@@ -380,7 +380,31 @@ def ltae_backward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: 
         status = lib.c2s_ltae_backward(ctypes.byref(desc), ctypes.byref(cparams), x.data_ptr(), _ptr(pos), _ptr(pad),
                                        ctypes.byref(io), ws.data_ptr(), ws_bytes, _stream(dev))
     _lib.check(status, "c2s_ltae_backward")
+    res["_fold"] = (desc, cparams, keep, ws, ws_bytes)  # c2s_ltae_fold_backward reads the folded tensors of this workspace
     return res
+
+
+def ltae_fold_backward(res: Dict[str, torch.Tensor], want: Dict[str, bool], shapes: Dict[str, tuple],
+                       grad_pe_through_scores: bool = False) -> Dict[str, torch.Tensor]:
+    """``c2s_ltae_fold_backward`` on the result of :func:`ltae_backward`: gradients of ``in_norm_weight/bias``,
+    ``inconv_weight/bias`` (folded part), ``query``, ``key_weight``, ``key_bias`` -- the ones ``want`` names --
+    as float32 tensors of ``shapes``.  ``grad_pe_through_scores``: also add grad_cpos . qk to ``res['grad_pe']``."""
+    desc, cparams, keep, ws, ws_bytes = res["_fold"]
+    dev = res["grad_u"].device
+    io = _lib.LtaeFoldBwdIo(grad_u=res["grad_u"].data_ptr(), grad_cpos=res["grad_cpos"].data_ptr(),
+                            grad_gamma_direct=_ptr(res.get("grad_gamma")), grad_beta_direct=_ptr(res.get("grad_beta")))
+    out = {}
+    for k in ("in_norm_weight", "in_norm_bias", "inconv_weight", "inconv_bias", "query", "key_weight", "key_bias"):
+        if want.get(k):
+            out[k] = torch.empty(shapes[k], dtype=torch.float32, device=dev)
+            setattr(io, "grad_" + k, out[k].data_ptr())
+    if grad_pe_through_scores and res.get("grad_pe") is not None:
+        io.grad_pe = res["grad_pe"].data_ptr()
+    with torch.cuda.device(dev):
+        status = _lib.load().c2s_ltae_fold_backward(ctypes.byref(desc), ctypes.byref(cparams), ctypes.byref(io), ws.data_ptr(),
+                                                    ws_bytes, _stream(dev))
+    _lib.check(status, "c2s_ltae_fold_backward")
+    return out
 
 
 def ltae_mlp_backward(o_rows: torch.Tensor, grad_out: torch.Tensor, params: Dict[str, Optional[torch.Tensor]],

@@ -49,3 +49,55 @@ def gather_shards(local, world_size: int, group=None):
     parts = [torch.empty_like(padded) for _ in range(world_size)]
     dist.all_gather(parts, padded.contiguous(), group=group)
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+class GradientBucket:
+    """One flat fp32 buffer that holds every gradient of ``params`` (each ``p.grad`` is a view into it), so that the
+    data-parallel training step of the hot path needs exactly ONE collective: ``all_reduce()`` averages the buffer over
+    the ranks in place (NCCL over NVLink / NVSwitch), with no per-parameter hooks, no flatten / unflatten copies and no
+    bucket bookkeeping on the host.  SURVEY.md section 8e: training = replicas + one gradient all-reduce; BatchNorm
+    statistics stay per replica like in the reference (train.py builds no SyncBatchNorm).
+
+        bucket = GradientBucket(encoder.parameters())
+        loss.backward(); bucket.all_reduce(); optimizer.step(); bucket.zero()
+
+    ``optimizer.zero_grad(set_to_none=True)`` would detach the views: use ``bucket.zero()`` (one memset) instead.
+    """
+
+    def __init__(self, params, group=None):
+        import torch
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradientBucket: no trainable parameter")
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.group = group
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("GradientBucket: parameters must be float32 on one device")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self) -> None:
+        self.flat.zero_()
+        for p in self.params:  # an optimizer may have replaced a view (set_to_none): re-attach
+            if p.grad is None or p.grad.untyped_storage().data_ptr() != self.flat.untyped_storage().data_ptr():
+                self._reattach()
+                break
+
+    def _reattach(self) -> None:
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def all_reduce(self) -> None:
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM,
+                        group=self.group)
+        if dist.get_backend(self.group) != "nccl":  # gloo has no AVG
+            self.flat.div_(dist.get_world_size(self.group))

@@ -256,6 +256,29 @@ int c2s_ltae_mlp_backward(const c2s_ltae_desc* desc, const c2s_ltae_params* para
 int c2s_ltae_inconv_grad(const float* grad_o, const float* zn_rows, const float* sa_rows, float* grad_inconv_weight,
                          float* grad_inconv_bias, int64_t n_rows, int32_t n_head, int32_t d_model, int32_t C, void* stream);
 
+/* Adjoint of the weight folding: grad_u / grad_cpos (and the direct in_norm terms) of c2s_ltae_backward -> gradients of
+ * in_norm, inconv, attention_head.Q and attention_head.fc1_k (what autograd derives from tae.py:463-479, 760-778).  Must be
+ * called with the SAME desc, params and workspace right after c2s_ltae_backward (its folded tensors and positional table
+ * are read from the workspace).  Output pointers may be NULL.  grad_inconv_weight / bias receive the folded part only:
+ * c2s_ltae_inconv_grad adds the direct term.  grad_pe (acc [B][T][d_model], may be NULL) receives += grad_cpos . qk, the
+ * path of a learnable positional table through the scores.  Deterministic (no atomics). */
+typedef struct c2s_ltae_fold_bwd_io {
+  const float* grad_u;            /* in  [C][16]      from c2s_ltae_backward                      */
+  const float* grad_cpos;         /* in  [B][T][16]                                               */
+  const float* grad_gamma_direct; /* in  [C] or NULL  (c2s_ltae_bwd_io.grad_gamma)                */
+  const float* grad_beta_direct;  /* in  [C] or NULL  (c2s_ltae_bwd_io.grad_beta)                 */
+  float* grad_in_norm_weight;     /* out [C]                                                      */
+  float* grad_in_norm_bias;       /* out [C]                                                      */
+  float* grad_inconv_weight;      /* out [d_model][C]                                             */
+  float* grad_inconv_bias;        /* out [d_model]                                                */
+  float* grad_query;              /* out [n_head][d_k]                                            */
+  float* grad_key_weight;         /* out [n_head*d_k][d_model]                                    */
+  float* grad_key_bias;           /* out [n_head*d_k]                                             */
+  float* grad_pe;                 /* acc [B][T][d_model] or NULL                                  */
+} c2s_ltae_fold_bwd_io;
+int c2s_ltae_fold_backward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const c2s_ltae_fold_bwd_io* io,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 size_t c2s_ltae_backward_workspace_bytes(const c2s_ltae_desc* desc);
 int c2s_ltae_backward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const void* x, const void* positions,
                       const uint8_t* pad_mask, const c2s_ltae_bwd_io* io, void* workspace, size_t workspace_bytes,

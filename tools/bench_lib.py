@@ -165,7 +165,7 @@ def placements(dev, B=64, min_seconds=1.0, only=("wtae", "timeunet", "timeunet_a
 
 
 # ------------------------------------------------------------------------------------------------ configs[3]
-def training(dev, local_rank, B=16, min_seconds=1.0, seed=1234):
+def training(dev, local_rank, B=16, min_seconds=1.0, seed=1234, ddp=False):
     """U-TAE hot path, forward + backward + Adam, DDP gradient all-reduce over the ranks (BASELINE configs[3])."""
     world = _world()
     rank = dist.get_rank() if world > 1 else 0
@@ -182,14 +182,20 @@ def training(dev, local_rank, B=16, min_seconds=1.0, seed=1234):
     randomise(enc, np.random.RandomState(seed))
     enc = enc.to(dev).train()
     enc.assume_zero_padded = True
-    model = torch.nn.parallel.DistributedDataParallel(enc, device_ids=[local_rank]) if world > 1 else enc
+    # data parallelism: ONE flat gradient buffer, ONE NCCL all-reduce per step (crop2seg_b200.GradientBucket); `ddp=True`
+    # wraps the encoder in DistributedDataParallel instead (per-bucket hooks), for comparison
+    bucket = None if ddp else c2s.GradientBucket(enc.parameters())
+    model = torch.nn.parallel.DistributedDataParallel(enc, device_ids=[local_rank]) if (ddp and world > 1) else enc
     agg = c2s.TemporalAggregator(mode="att_group")
     opt = torch.optim.Adam(enc.parameters(), lr=1e-3)  # train.py: Adam, lr 1e-3
     projs = [torch.randn((B, 128, LTAE_RES, LTAE_RES), device=dev, generator=gen).to(torch.bfloat16)] + \
             [torch.randn((B, c, r, r), device=dev, generator=gen).to(torch.bfloat16) for c, r in LEVELS]
 
     def step():
-        opt.zero_grad(set_to_none=True)
+        if bucket is None:
+            opt.zero_grad(set_to_none=True)
+        else:
+            bucket.zero()
         for x in [x4] + xs:
             x.grad = None
         out, att = model(x4, batch_positions=pos, pad_mask=pad)
@@ -197,6 +203,8 @@ def training(dev, local_rank, B=16, min_seconds=1.0, seed=1234):
         for x, pr in zip(xs, projs[1:]):
             loss = loss + (agg(x, pad_mask=pad, attn_mask=att) * pr).float().mean()
         loss.backward()
+        if bucket is not None:
+            bucket.all_reduce()
         opt.step()
         return loss
 
@@ -208,8 +216,8 @@ def training(dev, local_rank, B=16, min_seconds=1.0, seed=1234):
     bwd = 2 * n_valid * e_in + 2 * B * T_FRAMES * e_in + 2 * B * e_in + 2 * attn_bytes  # x again, grad_x, grad_out, attn + grad_attn
     rec = _record("U-TAE placement training step", ms, steps, n, B, fwd + bwd,
                   "BASELINE configs[3] hot path: LTAE(train: batch statistics, both dropouts) + 3x TemporalAggregator "
-                  "forward + backward, Adam step" + (", DistributedDataParallel (NCCL all-reduce of the encoder's "
-                                                     "gradients)" if world > 1 else "")
+                  "forward + backward, Adam step" + ((", DistributedDataParallel" if ddp else ", one NCCL all-reduce of one flat "
+                                                      "gradient buffer (GradientBucket)") if world > 1 else "")
                   + "; synthetic loss (fixed random projection of the four outputs: the decoder is outside the path)",
                   {"mean_valid_frames": float(np.mean(lengths))})
     del x4, xs, projs
