@@ -20,7 +20,7 @@ PE_NONE, PE_SINUSOID, PE_SINUSOID_LINEAR, PE_DOY_TABLE = 0, 1, 2, 3
 LTAE_ATTN_ONLY, LTAE_SKIP_ATTN_STORE, LTAE_ZERO_PADDED, LTAE_BN_BATCH_STATS, LTAE_REUSE_FOLDED = 1, 2, 4, 8, 16
 # enum c2s_option / c2s_ltae_kernel (kernel-selection switches for parity tests and A/B measurements)
 OPT_LTAE_KERNEL, OPT_AGG_KERNEL, OPT_AGG_TAPS = 0, 1, 2
-LTAE_KERNEL_AUTO, LTAE_KERNEL_GENERAL, LTAE_KERNEL_SLAB, LTAE_KERNEL_STREAM = 0, 1, 2, 3
+LTAE_KERNEL_AUTO, LTAE_KERNEL_GENERAL, LTAE_KERNEL_SLAB, LTAE_KERNEL_TEAM = 0, 1, 2, 3
 
 EXPORTS = (
     "c2s_abi_version", "c2s_last_error", "c2s_launch_count", "c2s_reset_launch_count", "c2s_last_kernel",

@@ -87,7 +87,7 @@ int64_t c2s_launch_count(void) { return c2s::g_launches.load(); }
 void c2s_reset_launch_count(void) { c2s::g_launches.store(0); }
 
 int c2s_set_option(int option, int value) {
-  const int max_value[3] = {C2S_LTAE_KERNEL_STREAM, 1, 1};
+  const int max_value[3] = {C2S_LTAE_KERNEL_TEAM, 1, 1};
   if (option < 0 || option >= 3 || value < 0 || value > max_value[option]) {
     c2s::set_error("c2s_set_option: unknown option %d / value %d", option, value);
     return C2S_ERR_BAD_ARGUMENT;

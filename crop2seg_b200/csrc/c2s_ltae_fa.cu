@@ -25,59 +25,13 @@
 //              GroupNorm runs over 4-8 channels and amplifies errors where a group is almost constant.
 //                                                                                              tae.py:463, 486-488
 // Frame blocks without a live frame are skipped in both products.
-#include <cuda.h>
-#include <cuda_fp16.h>
-
 #include <cstdlib>
 #include <type_traits>
 
-#include "c2s_ltae_prep.cuh"
+#include "c2s_ltae_fa.cuh"
 
 namespace c2s {
 namespace {
-
-constexpr int kPix = 8;            // pixels per tile; WPP warps (2 for C = 128, 1 for C = 64) share a pixel
-constexpr int kTP = 64;            // frames in the slab
-constexpr int kH = 16;             // heads
-constexpr int kD = 256;            // d_model
-constexpr int kAP = 72;            // pitch of the [h][t] fp32 tiles
-constexpr int kAsP = kH * kAP + 4;  // attention staging: floats per pixel
-constexpr int kPeRow = kTP + 8;    // positional table rows [d][t] (bf16), 144 B pitch
-constexpr int kOsRow = kD + 8;     // o rows [pixel][d] (16-bit), pitch in elements
-constexpr float kLog2e = 1.4426950408889634f;
-
-struct FaArgs {
-  const __nv_bfloat16* x;
-  const uint8_t* pad;
-  const unsigned long long* masks;  // [B][2]: frames to read, padded frames (bit t)
-  __nv_bfloat16* out;
-  float* attn;
-  const float* ufrag;     // [C/16][32][8] fp32, A-fragment order, times log2(e)
-  const uint4* wc16;      // [hi | lo][16 heads][C/16][32] fp16 A fragments of inconv.weight * scale
-  const float* wscale;    // {scale, 1 / scale}
-  const float* cpos;      // [B, T, 16]
-  const float* pe;        // [B, T, 256] or nullptr
-  const float* bc;        // [256]
-  const float* bm;        // [c_out]
-  const float* gamma;
-  const float* beta;
-  const float* bnf;       // [2, c_out] or nullptr (training)
-  const float* on_w;
-  const float* on_b;
-  float* ypre;
-  const uint8_t* attn_keep;  // [16, B, T, hw] dropout keep mask or nullptr
-  const uint8_t* mlp_keep;   // [B, c_out, hw] or nullptr
-  float attn_keep_scale, mlp_keep_scale;
-  __nv_bfloat16* o_hi;       // [B*hw][256] rows for the tcgen05 MLP kernel
-  __nv_bfloat16* o_lo;
-  float* save_o;             // [B*hw][256] fp32 copy of the same rows for the backward, or nullptr
-  int B, T, hw;
-  int attn_only, skip_attn_store, zero_padded;
-  float gn_eps;
-  int tiles_per_b;
-  int n_tiles;
-  unsigned long long* dbg;
-};
 
 template <int C, int WPP>
 struct FaSmem {
@@ -123,107 +77,6 @@ struct FaSmem {
   static_assert(kStageApart || kPix * kAsP * 4 <= kSlab, "attention staging must fit in the slab");
 };
 
-__device__ __forceinline__ uint32_t s32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void stsm_x4(uint32_t addr, const uint32_t (&r)[4]) {
-  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3])
-               : "memory");
-}
-// D += A(16x16, row) * B(16x8, col), fp32 accumulate
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void mma_f16(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-// v = hi + lo with hi, lo bf16: ~16 mantissa bits survive
-__device__ __forceinline__ void split_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  hi = pack_bf16(v0, v1);
-  lo = pack_bf16(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xffff0000u));
-}
-// same with fp16 halves: ~22 mantissa bits survive (|v| must stay below 65504)
-__device__ __forceinline__ void split_f16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(v0, v1);
-  const __half2 l = __floats2half2_rn(v0 - __low2float(h), v1 - __high2float(h));
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-// packed fp32 pairs (FADD2 / FFMA2 on sm_100): two lanes of arithmetic per issue slot
-__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ float ex2(float v) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-  return r;
-}
 
 // Phase timing for development (build with -DC2S_FA_TIMING, run with C2S_FA_DBG=1): warp 1 of CTA 0 accumulates the
 // cycles since the start of the tile at every checkpoint; the host prints the means at the next launch.
@@ -1103,7 +956,7 @@ int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void
   a.tiles_per_b = hw / kPix;
   if (static_cast<long long>(d.B) * a.tiles_per_b > 0x3fffffffll) C2S_UNSUPPORTED("c2s_ltae_forward: too many pixel tiles");
   a.n_tiles = d.B * a.tiles_per_b;
-#ifdef C2S_FA_TIMING
+#if defined(C2S_FA_TIMING) || defined(C2S_TEAM_TIMING)
   static unsigned long long* dbg = nullptr;
   if (getenv("C2S_FA_DBG") != nullptr) {
     if (dbg == nullptr) cudaMalloc(&dbg, 32 * 8);
@@ -1123,7 +976,9 @@ int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void
     ltae_mlp_tc_buffers(d, ws + lay.tc, &a.o_hi, &a.o_lo, &w_hi, &w_lo);
   }
   int status;
-  if (C == 128)
+  if (option(C2S_OPT_LTAE_KERNEL) != C2S_LTAE_KERNEL_SLAB && ltae_team_eligible(C, a))
+    status = ltae_team_launch(C, map16, map4, map1, a, stream);
+  else if (C == 128)
     status = fa_launch<128, 2>(map16, map4, map1, a, stream, "ltae_forward<fa,C=128>");
   else
     status = fa_launch<64, 1>(map16, map4, map1, a, stream, "ltae_forward<fa,C=64>");

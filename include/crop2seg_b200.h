@@ -382,8 +382,8 @@ enum c2s_option {
 enum c2s_ltae_kernel {
   C2S_LTAE_KERNEL_AUTO = 0,
   C2S_LTAE_KERNEL_GENERAL = 1, /* fp32 CUDA-core kernel (c2s_ltae.cu), any shape                                   */
-  C2S_LTAE_KERNEL_SLAB = 2,    /* persistent whole-slab kernel (c2s_ltae_fa.cu) where eligible, else general       */
-  C2S_LTAE_KERNEL_STREAM = 3   /* frame-ring streaming kernel (c2s_ltae_stream.cu) where eligible, else general    */
+  C2S_LTAE_KERNEL_SLAB = 2,    /* whole-slab kernel with CTA-wide phases (c2s_ltae_fa.cu) where eligible, else general */
+  C2S_LTAE_KERNEL_TEAM = 3    /* team-pipelined slab kernel (c2s_ltae_team.cu) where eligible, else slab / general */
 };
 int c2s_set_option(int option, int value); /* C2S_ERR_BAD_ARGUMENT for an unknown option / value */
 int c2s_get_option(int option);            /* current value, -1 for an unknown option            */

@@ -36,7 +36,7 @@ LTAE_CASES = {
 
 def kernel_name_ok(name):
     """The shipped shapes are served by one of the two tensor-core attention kernels, never by the general one."""
-    return name.startswith("ltae_forward<fa") or name.startswith("ltae_forward<stream")
+    return name.startswith("ltae_forward<fa") or name.startswith("ltae_forward<team")
 
 
 def _build(kind, kw, seed):
@@ -251,7 +251,13 @@ def test_ltae_without_attention_store(name):
             out, attn = m(to_dev(x, dtype=dtype), batch_positions=to_dev(pos), pad_mask=to_dev(pad))
             out2, none = m(to_dev(x, dtype=dtype), batch_positions=to_dev(pos), pad_mask=to_dev(pad), return_att=False)
         assert none is None and attn is not None
-        assert torch.equal(out, out2)
+        if dtype == torch.float32 or name == "utae":
+            assert torch.equal(out, out2)
+        else:  # Time-Unet shape in bf16: without the attention store the team-pipelined kernel serves the call
+            assert _lib.last_ltae_kernel().startswith("ltae_forward<team")
+            ref_out, _ = ltae_forward(oracle_config(kind, kw), oracle_params(m), bf16_round(x), pos, pad)
+            assert rel_err(out2.float().cpu().numpy(), ref_out) < 1e-2
+            assert rel_err(out2.float().cpu().numpy(), out.float().cpu().numpy()) < 1e-2
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
@@ -273,3 +279,52 @@ def test_one_process_two_devices():
             res.append((out.cpu(), lo.cpu(), la.cpu()))
     for a, b_ in zip(res[0], res[1]):
         assert torch.equal(a, b_)
+
+
+TEAM_CASES = {
+    # name: (kwargs extra, (B, T, H, W), lengths or None = ragged incl. an all-padded series, synth extra)
+    "full": ({}, (3, 61, 16, 16), [61, 61, 61], {}),
+    "ragged": ({}, (6, 61, 16, 16), [61, 27, 0, 44, 1, 16], {}),
+    "many_tiles": ({}, (5, 61, 32, 32), None, {}),           # 640 tiles: every team walks over several
+    "t64": ({}, (2, 64, 8, 8), [64, 33], {}),
+    "t20": ({}, (3, 20, 8, 8), [20, 7, 16], {}),            # whole 16-frame blocks behind T
+    "no_mask": ({}, (2, 33, 8, 8), [33, 33], {"no_mask": True}),
+    "no_pe": (dict(positional_encoding=False), (2, 40, 8, 8), [40, 21], {"no_positions": True}),
+    "doy": (dict(use_doy=True), (2, 61, 8, 8), [61, 30], {"doy": True}),
+    "abs_rel": (dict(use_abs_rel_enc=True), (2, 40, 8, 8), [31, 40], {"abs_rel": True}),
+    "c_out32": (dict(mlp=[256, 32]), (2, 61, 8, 8), [61, 45], {}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(TEAM_CASES))
+@pytest.mark.parametrize("zero_padded", [False, True])
+def test_team_kernel_matches_oracle_and_the_slab_kernel(name, zero_padded):
+    """The team-pipelined kernel (c2s_ltae_team.cu: C = 64, attention not stored) against the oracle and against the
+    whole-slab kernel on the same call."""
+    extra_kw, (b, t, h, w), lengths, extra = TEAM_CASES[name]
+    kw = dict(in_channels=64, n_head=16, d_k=4, mlp=[256, 64], d_model=256)
+    kw.update(extra_kw)
+    m, rng = _build("ltae", kw, 8100 + len(name))
+    m.assume_zero_padded = zero_padded
+    if lengths is None:
+        lengths = [t] + [max(1, t - (i * 7) % (t // 2 + 1)) for i in range(1, b)]
+        lengths[b // 2] = 0
+    x, pos, pad = synth_inputs(rng, b, t, 64, h, w, lengths, doy=extra.get("doy", False), abs_rel=extra.get("abs_rel", False))
+    if not zero_padded and pad.any():  # padded frames that are NOT zero: they count in the statistics, not in the attention
+        x = x + 0.3 * pad[:, :, None, None, None] * rng.standard_normal(x.shape).astype(np.float32)
+    pos = None if extra.get("no_positions") else pos
+    pad = None if extra.get("no_mask") else pad
+    xr = bf16_round(x)
+    ref_out, _ = ltae_forward(oracle_config("ltae", kw), oracle_params(m), xr, pos, pad)
+    args = (to_dev(x, dtype=torch.bfloat16),)
+    kwargs = dict(batch_positions=None if pos is None else to_dev(pos), pad_mask=None if pad is None else to_dev(pad), return_att=False)
+    with torch.no_grad():
+        out, none = m(*args, **kwargs)
+        assert none is None and _lib.last_ltae_kernel() == "ltae_forward<team,C=64>", _lib.last_ltae_kernel()
+        with _lib.option(_lib.OPT_LTAE_KERNEL, _lib.LTAE_KERNEL_SLAB):
+            out_s, _ = m(*args, **kwargs)
+            assert _lib.last_ltae_kernel().startswith("ltae_forward<fa")
+    o = out.float().cpu().numpy()
+    assert np.isfinite(o).all()
+    assert rel_err(o, ref_out) < 1e-2, rel_err(o, ref_out)
+    assert rel_err(o, out_s.float().cpu().numpy()) < 1e-2
