@@ -16,8 +16,13 @@
 //     without a live frame are skipped, and a probability that is exactly 0 meets stale but finite data;
 //   * the softmax normalisation is deferred: the value sums use exp2(s - max) and are scaled by 1 / sum with the
 //     GroupNorm affine.
-// Serves what c2s_ltae_team_eligible says (today: C = 64, attention not stored, no dropout mask); everything else
-// goes to c2s_ltae_fa.cu.
+// C = 128 (U-TAE): the slab is 128 KB, so there is ONE team of 16 warps, two warps per pixel: the scores and the softmax
+// are split over the frames (32 each; maximum and sum meet through shared memory), the value products over the
+// CHANNELS (64 each) -- the pair exchanges its probabilities (16 registers per lane) instead of 64 registers of partial
+// sums -- and the in-projection of a head is split over k between the two warps of a pair.  The attention (always
+// consumed by U-TAE's aggregations) is staged in the epilogue scratch and stored as 32-byte segments.
+// Serves what c2s_ltae_team_eligible says (no dropout mask, not attention-only; C = 64 only without the attention
+// store); everything else goes to c2s_ltae_fa.cu.
 #include <type_traits>
 
 #include "c2s_ltae_fa.cuh"
@@ -37,17 +42,25 @@ struct TeamSmem {
   static constexpr int kZnPix = 2 * HR * kZnRow + 16;  // per pixel: HR hi rows, HR lo rows; pixel blocks 4 banks apart
   static_assert((kZnPix / 4) % 32 == 4, "pixel blocks of zn must sit 4 banks apart");
   static constexpr int kSub = (C == 64) ? 2 : 1;     // GroupNorm groups per 8-channel block
-  static constexpr int kOst = 8 * 80;                // per-warp staging of 8 o-row pieces (80-byte pitch)
+  static constexpr int kOstRows = 8 * 80;            // staging of 8 o-row pieces per projecting warp (80-byte pitch)
+  static constexpr int kOst = kOstRows + (WPP == 2 ? 512 : 0);  // + the partner's partial in-projection (WPP = 2)
+  static constexpr int kPartW = 72;                  // float2 per warp: [8 px][4 blocks][kSub] + 8 (bank spread)
+  static constexpr int kPaPix = 2 * kH * 8 + 4;      // floats per pixel of the positional sums (+4: bank spread)
+  // epilogue scratch: zn tiles of one round; with two warps per pixel also the probability exchange
+  // ([TW][16 registers][32 lanes]), the partial in-projections and the attention staging ([8 px][kAsP] floats)
+  static constexpr int kEx = (WPP == 2) ? TW * 16 * 128 : 0;
+  static constexpr int kStage = (WPP == 2) ? kPix * kAsP * 4 : 0;
+  static constexpr int kZnAll = kPix * kZnPix;
+  static constexpr int kScratch = kZnAll > kEx ? (kZnAll > kStage ? kZnAll : kStage) : (kEx > kStage ? kEx : kStage);
   // ---- per team ----
   static constexpr int oSlab = 0;
   static constexpr int oZn = oSlab + kSlab;
-  static constexpr int oPart = oZn + kPix * kZnPix;                 // float2 [TW][8 px][4][kSub] statistics partials
-  static constexpr int kPartW = 72;                                 // float2 per warp: [8 px][4 blocks][kSub] + 8 (bank spread)
-  static constexpr int kPaPix = 2 * kH * 8 + 4;                     // floats per pixel of the positional sums (+4: bank spread)
+  static constexpr int oPart = oZn + kScratch;                      // float2 [TW][8 px][4][kSub] statistics partials
   static constexpr int oPa = oPart + TW * kPartW * 8;               // float [8 px][i / 8][16 h][i % 8]
-  static constexpr int oRm = oPa + kPix * kPaPix * 4;               // float [8 px][2][16]: rstd, mean * rstd per group
-  static constexpr int oOst = oRm + kPix * 2 * 16 * 4;
-  static constexpr int oCpos = oOst + TW * kOst;                    // float [16][kAP]
+  static constexpr int oRm = oPa + kPix * kPaPix * 4;               // float [TW][2][16]: rstd, mean * rstd per group
+  static constexpr int oOst = oRm + TW * 2 * 16 * 4;
+  static constexpr int oRed = oOst + kPix * kOst;                   // float [8 px][2 warps][max | sum][16] (WPP = 2)
+  static constexpr int oCpos = oRed + (WPP == 2 ? kPix * 2 * 2 * kH * 4 : 0);  // float [16][kAP]
   static constexpr int oPeHi = oCpos + kH * kAP * 4;                // bf16 [16][kPeRow]
   static constexpr int oPeLo = oPeHi + 16 * kPeRow * 2;
   static constexpr int oBar = oPeLo + 16 * kPeRow * 2;              // 4 mbarriers + release counter
@@ -92,7 +105,7 @@ __global__ void __launch_bounds__(512, 1)
 ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant__ CUtensorMap map4,
                  const __grid_constant__ CUtensorMap map1, const FaArgs a) {
   using S = TeamSmem<C>;
-  static_assert(C == 64, "one warp per pixel");
+  constexpr int WPP = S::WPP;              // warps per pixel
   constexpr int TW = S::TW, TT = 32 * TW;  // warps / threads of a team
   constexpr int CPG = C / kH;              // channels per GroupNorm group
   constexpr int KS = C / 16;               // k-steps over channels
@@ -102,12 +115,14 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
   constexpr int FB = S::kFB;
   constexpr int SUB = S::kSub;
   constexpr int HR = S::HR;
-  constexpr int FN = kTP / 8;              // score n-tiles per warp
+  constexpr int FPW = kTP / WPP;           // frames per warp in the scores and the softmax
+  constexpr int FN = FPW / 8;              // score n-tiles per warp
+  constexpr int CW = C / WPP;              // channels per warp in the value products
   extern __shared__ __align__(1024) unsigned char smem[];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int team = warp / TW, tw = warp % TW, ttid = tid - team * TT;
-  const int p = tw;                              // pixel of this warp
+  const int p = tw / WPP, half = tw % WPP;       // pixel of this warp; which frames (scores) / channels (values) it owns
   const int j = lane & 3, g = lane >> 2;         // fragment coordinates
   const int mat = lane >> 3, mr = lane & 7;      // ldmatrix: this lane supplies row mr of matrix mat
   const int bar_id = 1 + team;
@@ -118,8 +133,10 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
   unsigned char* zn_ptr = tb + S::oZn;
   float2* s_part = reinterpret_cast<float2*>(tb + S::oPart);
   float* s_pa = reinterpret_cast<float*>(tb + S::oPa);
-  float* s_rm = reinterpret_cast<float*>(tb + S::oRm) + p * 32;  // this warp's rstd[16], mean * rstd[16]
-  unsigned char* ost = tb + S::oOst + tw * S::kOst;
+  float* s_rm = reinterpret_cast<float*>(tb + S::oRm) + tw * 32;  // this warp's copy of rstd[16], mean * rstd[16]
+  unsigned char* ost = tb + S::oOst + p * S::kOst;
+  float* s_red = reinterpret_cast<float*>(tb + S::oRed);
+  const uint32_t pair_bar = 3 + p;               // named barrier of the two warps of a pixel (WPP = 2)
   float* s_cpos = reinterpret_cast<float*>(tb + S::oCpos);
   __nv_bfloat16* s_pe_hi = reinterpret_cast<__nv_bfloat16*>(tb + S::oPeHi);
   __nv_bfloat16* s_pe_lo = reinterpret_cast<__nv_bfloat16*>(tb + S::oPeLo);
@@ -174,7 +191,12 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
     }
   };
 
+#ifdef C2S_TEAM_ONLY0  // experiment: one team per CTA, the other one leaves (how much do the teams slow each other down?)
+  if (team != 0) return;
+  const int first = blockIdx.x, stride = gridDim.x;
+#else
   const int first = blockIdx.x * S::TEAMS + team, stride = gridDim.x * S::TEAMS;
+#endif
   unsigned long long live = 0, padm = 0;
   if (first < a.n_tiles) {
     const int b0 = first / a.tiles_per_b;
@@ -330,16 +352,18 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
     }
 
     TEAM_DBG(3);  // statistics
-    // ---- scores S^T[h, t] of pixel p, all 64 frames ------------------------------------------------ tae.py:827-831
+    // ---- scores S^T[h, t] of pixel p, frames FPW half .. FPW half + FPW - 1 ------------------------- tae.py:827-831
+    const uint32_t wblk = (blk >> (FN / 2 * half)) & ((1u << (FN / 2)) - 1u);  // this warp's 16-frame blocks
     float sacc[FN][4];
 #pragma unroll
     for (int nt = 0; nt < FN; ++nt) {
-      const int t = nt * 8 + 2 * j;
+      const int t = (FN * half + nt) * 8 + 2 * j;
       const float2 c0 = *reinterpret_cast<const float2*>(s_cpos + g * kAP + t);
       const float2 c1 = *reinterpret_cast<const float2*>(s_cpos + (g + 8) * kAP + t);
       sacc[nt][0] = c0.x, sacc[nt][1] = c0.y, sacc[nt][2] = c1.x, sacc[nt][3] = c1.y;
     }
-    const uint32_t xrow = slab + ((p ^ mr) << 4) + (mat & 1) * 128 + ((mat >> 1) * 8 + mr) * FB;
+    const uint32_t xbase = slab + ((p ^ mr) << 4) + (mat & 1) * 128 + ((mat >> 1) * 8 + mr) * FB;
+    const uint32_t xrow = xbase + FPW * half * FB;  // first frame of this warp's scores
     auto scores = [&](auto all_) {
       constexpr bool ALL = decltype(all_)::value;
 #pragma unroll 2
@@ -355,22 +379,22 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
         uint32_t bfr[FN / 2][4];  // (block 2 ntp, channels 16 ks..+7), (.., +8..15), (block 2 ntp + 1, ..), (..)
 #pragma unroll
         for (int ntp = 0; ntp < FN / 2; ++ntp)
-          if (ALL || ((blk >> ntp) & 1u)) ldsm_x4(bfr[ntp], xrow + ntp * 16 * FB + ks * 256);
+          if (ALL || ((wblk >> ntp) & 1u)) ldsm_x4(bfr[ntp], xrow + ntp * 16 * FB + ks * 256);
 #pragma unroll
         for (int ntp = 0; ntp < FN / 2; ++ntp) {
-          if (!ALL && !((blk >> ntp) & 1u)) continue;
+          if (!ALL && !((wblk >> ntp) & 1u)) continue;
           mma_bf16(sacc[2 * ntp], ahi, bfr[ntp][0], bfr[ntp][1]);
           mma_bf16(sacc[2 * ntp + 1], ahi, bfr[ntp][2], bfr[ntp][3]);
         }
 #pragma unroll
         for (int ntp = 0; ntp < FN / 2; ++ntp) {
-          if (!ALL && !((blk >> ntp) & 1u)) continue;
+          if (!ALL && !((wblk >> ntp) & 1u)) continue;
           mma_bf16(sacc[2 * ntp], alo, bfr[ntp][0], bfr[ntp][1]);
           mma_bf16(sacc[2 * ntp + 1], alo, bfr[ntp][2], bfr[ntp][3]);
         }
       }
     };
-    if (blk == 0xfu) scores(std::true_type{});
+    if (wblk == (1u << (FN / 2)) - 1u) scores(std::true_type{});
     else scores(std::false_type{});
 
     TEAM_DBG(4);  // scores
@@ -378,14 +402,14 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
     float inv0, inv1;
     {
       // padded frames and frames behind T: their scores are REPLACED (masked_fill, tae.py:831), whatever the slab holds
-      const unsigned long long ov = padm | beyond;
+      const unsigned long long ov = (padm | beyond) >> (FPW * half);
 #pragma unroll
       for (int nt = 0; nt < FN; ++nt) {
         const uint32_t byte = static_cast<uint32_t>(ov >> (8 * nt)) & 0xffu;  // uniform
         if (byte != 0) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int t = nt * 8 + 2 * j + e;
+            const int t = FPW * half + nt * 8 + 2 * j + e;
             if ((byte >> (2 * j + e)) & 1u) {
               const float v = t >= a.T ? -INFINITY : -1e6f * kLog2e;
               sacc[nt][e] = v, sacc[nt][2 + e] = v;
@@ -403,6 +427,14 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float* red = s_red + (p * 2 + half) * 2 * kH;
+      const float* red_other = s_red + (p * 2 + (half ^ 1)) * 2 * kH;
+      if constexpr (WPP == 2) {
+        if (j == 0) red[g] = mx0, red[g + 8] = mx1;
+        team_bar(pair_bar, 64);
+        mx0 = fmaxf(mx0, red_other[g]);  // T >= 1: at least one side is finite
+        mx1 = fmaxf(mx1, red_other[g + 8]);
+      }
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < FN; ++nt) {
@@ -417,45 +449,82 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
       d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
       d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
       d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+      if constexpr (WPP == 2) {  // the sum is formed in the same order by both warps
+        if (j == 0) red[kH + g] = d0, red[kH + g + 8] = d1;
+        team_bar(pair_bar, 64);
+        const float lo0 = half ? red_other[kH + g] : d0, hi0 = half ? d0 : red_other[kH + g];
+        const float lo1 = half ? red_other[kH + g + 8] : d1, hi1 = half ? d1 : red_other[kH + g + 8];
+        d0 = lo0 + hi0, d1 = lo1 + hi1;
+      }
       inv0 = 1.f / d0, inv1 = 1.f / d1;  // T >= 1: the maximum contributes exp2(0) = 1
     }
 
     TEAM_DBG(5);  // softmax
-    // ---- values: z[h, c] = sum_t e[h, t] x[t, c] (+ 16 positional columns), un-normalised ------------- tae.py:839
-    float zacc[C / 8][4];
-    float pacc[2][4];
+    // ---- values: z[h, c] = sum_t e[h, t] x[t, c] (+ positional columns), un-normalised; all frames, CW channels -- tae.py:839
+    constexpr int NP = 2 / WPP;  // positional 8-column tiles per warp
+    float zacc[CW / 8][4];
+    float pacc[NP][4];
 #pragma unroll
-    for (int nt = 0; nt < C / 8; ++nt)
+    for (int nt = 0; nt < CW / 8; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) zacc[nt][i] = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+    for (int nt = 0; nt < NP; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) pacc[nt][i] = 0.f;
     {
+      // two warps per pixel: the probabilities of this warp's frames (hi / lo A fragments, 16 registers per lane) go to
+      // the partner through shared memory, the partner's come back: every warp then owns ALL frames of ITS channels
+      uint32_t* ex_mine = reinterpret_cast<uint32_t*>(zn_ptr) + tw * 16 * 32 + lane;
+      const uint32_t* ex_theirs = reinterpret_cast<const uint32_t*>(zn_ptr) + (tw ^ 1) * 16 * 32 + lane;
+      uint32_t own[WPP == 2 ? FN / 2 : 1][8];
+      if constexpr (WPP == 2) {
+#pragma unroll
+        for (int kl = 0; kl < FN / 2; ++kl) {
+          split_bf16(sacc[2 * kl][0], sacc[2 * kl][1], own[kl][0], own[kl][4]);
+          split_bf16(sacc[2 * kl][2], sacc[2 * kl][3], own[kl][1], own[kl][5]);
+          split_bf16(sacc[2 * kl + 1][0], sacc[2 * kl + 1][1], own[kl][2], own[kl][6]);
+          split_bf16(sacc[2 * kl + 1][2], sacc[2 * kl + 1][3], own[kl][3], own[kl][7]);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) ex_mine[(kl * 8 + r) * 32] = own[kl][r];
+        }
+        team_bar(pair_bar, 64);
+      }
       const uint32_t pe_row = s32((mat >> 1) ? s_pe_lo : s_pe_hi) + static_cast<uint32_t>(mr * kPeRow + (mat & 1) * 8) * 2u;
       const bool has_pe = a.pe != nullptr;
       auto values = [&](auto all_) {
         constexpr bool ALL = decltype(all_)::value;
 #pragma unroll
-        for (int ksl = 0; ksl < FN / 2; ++ksl) {
+        for (int kg = 0; kg < kTP / 16; ++kg) {
           // a block without a live frame: its probabilities meet rows that are zero in the reference (x = 0 on padded
           // frames), so the feature products are skipped; the positional sums are not (an all-padded series attends
           // uniformly, tae.py:831-836)
-          const bool on = ALL || ((blk >> ksl) & 1u);
+          const bool on = ALL || ((blk >> kg) & 1u);
           if (!on && !has_pe) continue;
           uint32_t ahi[4], alo[4];
-          split_bf16(sacc[2 * ksl][0], sacc[2 * ksl][1], ahi[0], alo[0]);
-          split_bf16(sacc[2 * ksl][2], sacc[2 * ksl][3], ahi[1], alo[1]);
-          split_bf16(sacc[2 * ksl + 1][0], sacc[2 * ksl + 1][1], ahi[2], alo[2]);
-          split_bf16(sacc[2 * ksl + 1][2], sacc[2 * ksl + 1][3], ahi[3], alo[3]);
+          if constexpr (WPP == 1) {
+            split_bf16(sacc[2 * kg][0], sacc[2 * kg][1], ahi[0], alo[0]);
+            split_bf16(sacc[2 * kg][2], sacc[2 * kg][3], ahi[1], alo[1]);
+            split_bf16(sacc[2 * kg + 1][0], sacc[2 * kg + 1][1], ahi[2], alo[2]);
+            split_bf16(sacc[2 * kg + 1][2], sacc[2 * kg + 1][3], ahi[3], alo[3]);
+          } else {
+            constexpr int KL = (FN / 2 > 0) ? FN / 2 : 1;
+            const int owner = kg / KL, kl = kg % KL;  // compile-time after unrolling
+            if (owner == half) {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) ahi[r] = own[kl][r], alo[r] = own[kl][4 + r];
+            } else {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) ahi[r] = ex_theirs[(kl * 8 + r) * 32], alo[r] = ex_theirs[(kl * 8 + 4 + r) * 32];
+            }
+          }
           if (on) {
             constexpr int CB = 2;  // channel-block pairs whose fragments are requested together (registers)
 #pragma unroll
-            for (int cb0 = 0; cb0 < C / 16; cb0 += CB) {
+            for (int cb0 = 0; cb0 < CW / 16; cb0 += CB) {
               uint32_t v[CB][4];  // (frames 0-7, block 2 cbp), (0-7, 2 cbp + 1), (8-15, 2 cbp), (8-15, 2 cbp + 1)
 #pragma unroll
-              for (int q = 0; q < CB; ++q) ldsm_x4_trans(v[q], xrow + ksl * 16 * FB + (cb0 + q) * 256);
+              for (int q = 0; q < CB; ++q) ldsm_x4_trans(v[q], xbase + kg * 16 * FB + (CW / 16 * half + cb0 + q) * 256);
 #pragma unroll
               for (int q = 0; q < CB; ++q) {
                 mma_bf16(zacc[2 * (cb0 + q)], ahi, v[q][0], v[q][2]);
@@ -469,11 +538,12 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
             }
           }
           if (has_pe) {  // matrices (hi, frames 0-7), (hi, 8-15), (lo, 0-7), (lo, 8-15) of 8 table columns
-            uint32_t bp[2][4];
+            uint32_t bp[NP][4];
 #pragma unroll
-            for (int nt2 = 0; nt2 < 2; ++nt2) ldsm_x4(bp[nt2], pe_row + static_cast<uint32_t>(nt2 * 8 * kPeRow + ksl * 16) * 2u);
+            for (int nt2 = 0; nt2 < NP; ++nt2)
+              ldsm_x4(bp[nt2], pe_row + static_cast<uint32_t>((WPP == 2 ? half : nt2) * 8 * kPeRow + kg * 16) * 2u);
 #pragma unroll
-            for (int nt2 = 0; nt2 < 2; ++nt2) {
+            for (int nt2 = 0; nt2 < NP; ++nt2) {
               mma_bf16(pacc[nt2], ahi, bp[nt2][0], bp[nt2][1]);
               mma_bf16(pacc[nt2], alo, bp[nt2][0], bp[nt2][1]);
               mma_bf16(pacc[nt2], ahi, bp[nt2][2], bp[nt2][3]);
@@ -502,25 +572,55 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
     if (nxt < a.n_tiles) load_pivots(nxt, nlive);  // consumed at the top of the next tile
 
     TEAM_DBG(7);  // release + pivots
-    // ---- epilogue, two rounds of 8 heads: GroupNorm affine -> fp16 hi/lo zn tiles, per-head in-projection --------
     const size_t row0 = static_cast<size_t>(b) * a.hw + pix0;
+    if constexpr (WPP == 2) {
+      // the probability exchange shares its space with the attention staging and the zn tiles: everyone is done reading
+      team_bar(bar_id, TT);
+      if (a.attn != nullptr && !a.skip_attn_store) {  // attn[h, b, t, pix0 .. pix0 + 7] as 32-byte segments   tae.py:490-493
+        float* stage = reinterpret_cast<float*>(zn_ptr);
+        float* as = stage + p * kAsP;
+#pragma unroll
+        for (int nt = 0; nt < FN; ++nt) {
+          const int t = (FN * half + nt) * 8 + 2 * j;
+          *reinterpret_cast<float2*>(as + g * kAP + t) = make_float2(sacc[nt][0] * inv0, sacc[nt][1] * inv0);
+          *reinterpret_cast<float2*>(as + (g + 8) * kAP + t) = make_float2(sacc[nt][2] * inv1, sacc[nt][3] * inv1);
+        }
+        team_bar(bar_id, TT);
+        {
+          const int pp = lane & 7, tq = lane >> 3, h = tw;  // TW = 16 warps = 16 heads
+          float* dst = a.attn + ((static_cast<size_t>(h) * a.B + b) * a.T + tq) * a.hw + pix0 + pp;
+          const float* src = stage + pp * kAsP + h * kAP + tq;
+          const size_t step = static_cast<size_t>(4) * a.hw;
+          float v[kTP / 4];
+#pragma unroll
+          for (int u = 0; u < kTP / 4; ++u) v[u] = src[4 * u];  // t = tq + 4 u <= 63: inside the staging rows
+#pragma unroll
+          for (int u = 0; u < kTP / 4; ++u)
+            if (tq + 4 * u < a.T) dst[u * step] = v[u];
+        }
+        team_bar(bar_id, TT);
+      }
+    }
+
+    // ---- epilogue, two rounds of 8 heads: GroupNorm affine -> fp16 hi/lo zn tiles, per-head in-projection --------
+    constexpr int KSW = KS / WPP;  // k-steps of the in-projection per warp (the pair splits k)
 #pragma unroll
     for (int rnd = 0; rnd < 2; ++rnd) {
-      // in-projection weights of head 8 rnd + tw (fp16 hi + lo A fragments, L2 resident): requested first, they fly
+      // in-projection weights of head 8 rnd + p (fp16 hi + lo A fragments, L2 resident): requested first, they fly
       // while the zn tiles are written and across the barrier
-      const int h = 8 * rnd + tw;
-      uint4 wha[KS], wla[KS];
+      const int h = 8 * rnd + p;
+      uint4 wha[KSW], wla[KSW];
       {
-        const uint4* wc = a.wc16 + (h * KS) * 32 + lane;
+        const uint4* wc = a.wc16 + (h * KS + KSW * half) * 32 + lane;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) wha[ks] = __ldg(wc + ks * 32), wla[ks] = __ldg(wc + kD * C * 2 / 16 + ks * 32);
+        for (int ks = 0; ks < KSW; ++ks) wha[ks] = __ldg(wc + ks * 32), wla[ks] = __ldg(wc + kD * C * 2 / 16 + ks * 32);
       }
       {
         unsigned char* zb = zn_ptr + p * S::kZnPix + g * S::kZnRow;  // head row g of this round, pixel p
         const float inv = rnd ? inv1 : inv0;
 #pragma unroll
-        for (int nt = 0; nt < C / 8; ++nt) {
-          const int c = nt * 8 + 2 * j;
+        for (int nt = 0; nt < CW / 8; ++nt) {
+          const int c = CW * half + nt * 8 + 2 * j;
           const int grp = c / CPG;
           const float r = s_rm[grp] * inv, m = s_rm[16 + grp];
           const float2 gm = *reinterpret_cast<const float2*>(s_gam + c), bt = *reinterpret_cast<const float2*>(s_gam + C + c);
@@ -534,8 +634,9 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
         }
         const int hz = g + 8 * rnd;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          *reinterpret_cast<float2*>(s_pa + p * S::kPaPix + (q * kH + hz) * 8 + 2 * j) =
+        for (int q = 0; q < NP; ++q) {
+          const int qq = (WPP == 2) ? half : q;  // which half of the 16 positional columns
+          *reinterpret_cast<float2*>(s_pa + p * S::kPaPix + (qq * kH + hz) * 8 + 2 * j) =
               make_float2(pacc[q][2 * rnd] * inv, pacc[q][2 * rnd + 1] * inv);
         }
       }
@@ -549,9 +650,9 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
       {
-        const unsigned char* zb = zn_ptr + g * S::kZnPix + tw * S::kZnRow + 2 * j * 2;  // B[k = c][n = pixel g]
+        const unsigned char* zb = zn_ptr + g * S::kZnPix + p * S::kZnRow + 2 * j * 2 + KSW * half * 32;  // B[k = c][n = pixel g]
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
+        for (int ks = 0; ks < KSW; ++ks) {
           const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(zb + ks * 32);
           const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(zb + ks * 32 + 16);
           const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(zb + HR * S::kZnRow + ks * 32);
@@ -561,16 +662,30 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
           mma_f16(acc[2], wha[ks], bl0, bl1);
         }
       }
-      float v[4];
+      float sum[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {  // accumulator: rows i = g, g + 8; columns pixel 2j, 2j + 1
-        const int i = g + (e >> 1) * 8, pp = 2 * j + (e & 1);
-        const int d = h * 16 + i;
-        const float sum = acc[0][e] + (acc[1][e] + acc[2][e]);
-        v[e] = fmaf(sum, inv_sc, s_bc[d] + s_pa[pp * S::kPaPix + ((e >> 1) * kH + h) * 8 + g]);
-        if (a.save_o != nullptr) a.save_o[(row0 + pp) * kD + d] = v[e];
+      for (int e = 0; e < 4; ++e) sum[e] = acc[0][e] + (acc[1][e] + acc[2][e]);
+      if constexpr (WPP == 2) {  // the two halves of k meet: the second warp of the pair hands its partial sums over
+        float* px = reinterpret_cast<float*>(ost + S::kOstRows) + lane;
+        if (half == 1) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) px[e * 32] = sum[e];
+        }
+        team_bar(pair_bar, 64);
+        if (half == 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sum[e] += px[e * 32];
+        }
       }
-      {
+      if (half == 0) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {  // accumulator: rows i = g, g + 8; columns pixel 2j, 2j + 1
+          const int i = g + (e >> 1) * 8, pp = 2 * j + (e & 1);
+          const int d = h * 16 + i;
+          v[e] = fmaf(sum[e], inv_sc, s_bc[d] + s_pa[pp * S::kPaPix + ((e >> 1) * kH + h) * 8 + g]);
+          if (a.save_o != nullptr) a.save_o[(row0 + pp) * kD + d] = v[e];
+        }
         // rows of o for the tcgen05 MLP kernel: stmatrix.trans turns (i, pixel pair) fragments into 16-byte pieces
         // [pixel][8 consecutive i]; matrices: hi i 0-7, hi i 8-15, lo i 0-7, lo i 8-15
         uint32_t m4[4];
@@ -613,15 +728,17 @@ int team_launch(const CUtensorMap& map16, const CUtensorMap& map4, const CUtenso
 }  // namespace
 
 bool ltae_team_eligible(int C, const FaArgs& a) {
-  if (C != 64) return false;
-  if (a.attn_only || a.attn_keep != nullptr) return false;
-  if (a.attn != nullptr && !a.skip_attn_store) return false;  // the attention would have to be staged: c2s_ltae_fa.cu
+  if (C != 64 && C != 128) return false;
+  if (a.attn_only || a.attn_keep != nullptr) return false;  // LTAE4WTAE and training-mode dropout: c2s_ltae_fa.cu
+  // C = 64: two slabs leave no room for the attention staging
+  if (C == 64 && a.attn != nullptr && !a.skip_attn_store) return false;
   return true;
 }
 
 int ltae_team_launch(int C, const CUtensorMap& map16, const CUtensorMap& map4, const CUtensorMap& map1, const FaArgs& a,
                      cudaStream_t stream) {
   if (C == 64) return team_launch<64>(map16, map4, map1, a, stream, "ltae_forward<team,C=64>");
+  if (C == 128) return team_launch<128>(map16, map4, map1, a, stream, "ltae_forward<team,C=128>");
   set_error("ltae_team_launch: C=%d has no team kernel", C);
   return C2S_ERR_UNSUPPORTED;
 }

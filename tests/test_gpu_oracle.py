@@ -93,8 +93,14 @@ def test_tensor_core_path_is_selected():
     m, rng = _build(kind, kw, 1)
     x, pos, pad = synth_inputs(rng, b, t, 128, h, w, lengths)
     (out_tc, attn_tc), kernel = _call(m, kind, x, pos, pad, general=False, dtype=torch.bfloat16)
-    # tensor-core attention kernel followed by the tcgen05 row GEMM of the MLP
-    assert kernel == "ltae_mlp<tcgen05>" and kernel_name_ok(_lib.last_ltae_kernel())
+    # tensor-core attention kernel followed by the tcgen05 row GEMM of the MLP; the U-TAE encoder in eval mode is served
+    # by the team-pipelined kernel, the whole-slab kernel on request gives the same answer
+    assert kernel == "ltae_mlp<tcgen05>" and _lib.last_ltae_kernel() == "ltae_forward<team,C=128>"
+    with _lib.option(_lib.OPT_LTAE_KERNEL, _lib.LTAE_KERNEL_SLAB), torch.no_grad():
+        out_s, attn_s = m(to_dev(x, dtype=torch.bfloat16), batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+        assert _lib.last_ltae_kernel() == "ltae_forward<fa,C=128>"
+    assert rel_err(attn_tc.cpu().numpy(), attn_s.cpu().numpy()) < 1e-4
+    assert rel_err(out_tc.float().cpu().numpy(), out_s.float().cpu().numpy()) < 1e-2
     (out_g, attn_g), kernel = _call(m, kind, x, pos, pad, general=True, dtype=torch.bfloat16)
     assert kernel == "ltae_forward<general>"
     assert rel_err(attn_tc.cpu().numpy(), attn_g.cpu().numpy()) < 1e-3
