@@ -112,17 +112,30 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-// v = hi + lo with hi, lo bf16: ~16 mantissa bits survive
+// v = hi + lo with hi, lo bf16: ~16 mantissa bits survive.  The residual v - hi is formed by mixed-precision adds that read
+// the 16-bit halves of the packed register in place (FHADD.BF16): 5 instructions per pair instead of 6.
 __device__ __forceinline__ void split_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
   hi = pack_bf16(v0, v1);
-  lo = pack_bf16(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xffff0000u));
+  uint32_t nh;
+  uint16_t l, h;
+  float r0, r1;
+  asm("neg.bf16x2 %0, %1;" : "=r"(nh) : "r"(hi));
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(l), "=h"(h) : "r"(nh));
+  asm("add.rn.f32.bf16 %0, %1, %2;" : "=f"(r0) : "h"(l), "f"(v0));
+  asm("add.rn.f32.bf16 %0, %1, %2;" : "=f"(r1) : "h"(h), "f"(v1));
+  lo = pack_bf16(r0, r1);
 }
-// same with fp16 halves: ~22 mantissa bits survive (|v| must stay below 65504)
+// same with fp16 halves: ~22 mantissa bits survive (|v| must stay below 65504); the negation folds into FHADD: 4 instructions
 __device__ __forceinline__ void split_f16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(v0, v1);
-  const __half2 l = __floats2half2_rn(v0 - __low2float(h), v1 - __high2float(h));
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  uint32_t nh;
+  uint16_t l, h;
+  float r0, r1;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+  asm("neg.f16x2 %0, %1;" : "=r"(nh) : "r"(hi));
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(l), "=h"(h) : "r"(nh));
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(r0) : "h"(l), "f"(v0));
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(r1) : "h"(h), "f"(v1));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 // packed fp32 pairs (FADD2 / FFMA2 on sm_100): two lanes of arithmetic per issue slot
 __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
