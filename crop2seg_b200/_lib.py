@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 7
+C2S_ABI_VERSION = 8
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -29,6 +29,7 @@ EXPORTS = (
     "c2s_agg_skipconv_workspace_bytes", "c2s_agg_skipconv_forward", "c2s_pad_mask",
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
     "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward", "c2s_ltae_inconv_grad", "c2s_ltae_fold_backward",
+    "c2s_ltae_rows_forward",
     "c2s_tile_patchify", "c2s_tile_classmap", "c2s_frame_index", "c2s_frames_gather", "c2s_frames_scatter",
     "c2s_boundary_target", "c2s_seg_loss_workspace_bytes", "c2s_seg_loss_forward", "c2s_seg_loss_backward",
 )
@@ -141,6 +142,8 @@ def load() -> ctypes.CDLL:
         lib.c2s_agg_skipconv_forward.restype = i32
         lib.c2s_agg_skipconv_forward.argtypes = [ctypes.POINTER(AggDesc), vp, vp, vp, ctypes.POINTER(SkipConvParams), vp,
                                                  vp, sz, vp]
+        lib.c2s_ltae_rows_forward.restype = i32
+        lib.c2s_ltae_rows_forward.argtypes = [vp, vp, vp, i32, vp, vp]
         lib.c2s_ltae_inconv_grad.restype = i32
         lib.c2s_ltae_inconv_grad.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64, i32, i32, i32, vp]
         lib.c2s_pad_mask.restype = i32

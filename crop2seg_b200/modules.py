@@ -215,10 +215,12 @@ class _LTAEBase(nn.Module):
                 "mlp_keep_scale": 1.0 / (1.0 - mlp_p)}
 
     def _check_inputs(self, x, batch_positions):
-        if self.num_queries != 1:
-            # the reference accepts num_queries > 1 here but every shipped model then crashes in the
-            # aggregator (temporal_aggregator.py:23)
-            raise NotImplementedError("crop2seg_b200: num_queries > 1 is not supported by the fused kernels")
+        if self.num_queries != 1 and (self.training or not isinstance(self, LTAE)):
+            # num_queries > 1 (tae.py:495-499) is served in eval mode by one pass per query (LTAE.forward); in training
+            # mode the reference's BatchNorm1d statistics run over the rows of ALL queries at once, which a per-query
+            # pass cannot reproduce.  Every shipped reference model crashes for it in the aggregator anyway
+            # (temporal_aggregator.py:23).
+            raise NotImplementedError("crop2seg_b200: num_queries > 1 is supported by LTAE in eval mode only")
         if x.shape[2] != self.in_channels:
             raise RuntimeError(f"Expected {self.in_channels} input channels, got x of shape {tuple(x.shape)}")
         if self.positional_encoder is not None and batch_positions is not None:
@@ -271,6 +273,44 @@ class LTAE(_LTAEBase):
         self._check_inputs(x, batch_positions)
         if return_att is None:
             return_att = self.return_attention
+        if self.num_queries != 1:
+            # tae.py:495-499: out[B, n, C', H, W], attn[n_head, B, n, T, H, W].  The queries never interact (separate
+            # softmax rows, row-wise MLP, eval-mode BatchNorm): one pass of the single-query kernels per query.
+            return self._forward_queries(x, batch_positions, pad_mask, return_att)
+        return self._forward_one(x, batch_positions, pad_mask, return_att)
+
+    @torch.no_grad()
+    def _forward_queries(self, x, batch_positions, pad_mask, return_att):
+        """num_queries = n > 1, eval mode (tae.py:486-499): out[B, n, C', H, W], attn[n_head, B, n, T, H, W].  The
+        attention rows of the queries are independent: one pass of the single-query kernels per query yields its
+        attention and its rows ``o``; ``out_norm`` runs over the channels of a group AND the n queries (it is applied
+        to [B*H*W, C', n], tae.py:488), so the rows are finished jointly by ``c2s_ltae_rows_forward``."""
+        bn = self.mlp[2]
+        if not bn.track_running_stats:
+            raise NotImplementedError("crop2seg_b200: num_queries > 1 needs BatchNorm running statistics")
+        b, t, _, h, w = x.shape
+        c_out = self._widths[-1]
+        params = self._front_params(x.device)
+        params.update({
+            "mlp_weight": self.mlp[0].weight, "mlp_bias": self.mlp[0].bias, "bn_weight": bn.weight, "bn_bias": bn.bias,
+            "bn_running_mean": bn.running_mean, "bn_running_var": bn.running_var,
+            "out_norm_weight": self.out_norm.weight, "out_norm_bias": self.out_norm.bias,
+        })
+        rows, attns = [], []
+        for i in range(self.num_queries):
+            params["query"] = self.attention_head.Q[:, i:i + 1, :]  # Q[n_head, n, d_k] -> the rows of one query
+            _, attn, _, o_rows = ops.ltae_forward(
+                x, batch_positions, pad_mask, params, n_head=self.n_head, d_k=self.d_k, d_model=self.d_model,
+                has_inconv=self.inconv is not None, c_out=c_out, pe_mode=self._pe_mode(), pe_abs=self.use_abs_rel_enc,
+                need_attn=return_att, zero_padded=self.assume_zero_padded, bn_batch_stats=False,
+                gn_eps=self.in_norm.eps, bn_eps=bn.eps, save_o=True)
+            rows.append(o_rows)
+            attns.append(attn)
+        out = ops.ltae_rows_forward(torch.stack(rows), params, batch=b, height=h, width=w, n_head=self.n_head,
+                                    d_model=self.d_model, c_out=c_out, dtype=x.dtype, gn_eps=self.out_norm.eps, bn_eps=bn.eps)
+        return out, (torch.stack(attns, dim=2) if return_att else None)
+
+    def _forward_one(self, x, batch_positions, pad_mask, return_att):
         bn = self.mlp[2]
         train_bn = self.training or not bn.track_running_stats
         params = self._front_params(x.device)

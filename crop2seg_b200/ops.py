@@ -311,6 +311,31 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
     return out, attn, stats
 
 
+def ltae_rows_forward(o_rows: torch.Tensor, params: Dict[str, Optional[torch.Tensor]], *, batch: int, height: int,
+                      width: int, n_head: int, d_model: int, c_out: int, dtype: torch.dtype, gn_eps: float = 1e-5,
+                      bn_eps: float = 1e-5) -> torch.Tensor:
+    """``c2s_ltae_rows_forward``: the rows behind the attention of an encoder with n > 1 learned queries, eval mode
+    (tae.py:486-499): ``o_rows`` [n, B*H*W, d_model] (float32, the ``save_o`` rows of one ``ltae_forward`` per query)
+    -> ``out`` [B, n, c_out, H, W]; the output GroupNorm runs over the channels of a group and the n queries."""
+    _require_cuda(o_rows, "o_rows")
+    dev = o_rows.device
+    n_q = o_rows.shape[0]
+    if o_rows.dim() != 3 or tuple(o_rows.shape[1:]) != (batch * height * width, d_model):
+        raise RuntimeError(f"crop2seg_b200: o_rows has shape {tuple(o_rows.shape)}")
+    o = o_rows.to(torch.float32).contiguous()
+    out = torch.empty((batch, n_q, c_out, height, width), dtype=dtype, device=dev)
+    desc = _lib.LtaeDesc(B=batch, T=1, C=n_head, H=height, W=width, n_head=n_head, d_k=1, d_model=d_model, c_out=c_out,
+                         has_inconv=1, pe_mode=_lib.PE_NONE, pe_abs=0, pos_dtype=0, dtype=_dtype_code(out, "out"), flags=0,
+                         gn_eps=gn_eps, bn_eps=bn_eps, attn_keep_scale=1.0, mlp_keep_scale=1.0)
+    keep = []
+    cparams = _lib.LtaeParams(**{k: _f32(params.get(k), dev, keep) for k in _lib.LTAE_PARAM_FIELDS})
+    with torch.cuda.device(dev):
+        status = _lib.load().c2s_ltae_rows_forward(ctypes.byref(desc), ctypes.byref(cparams), o.data_ptr(), n_q,
+                                                   out.data_ptr(), _stream(dev))
+    _lib.check(status, "c2s_ltae_rows_forward")
+    return out
+
+
 def ltae_backward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: Optional[torch.Tensor],
                   params: Dict[str, Optional[torch.Tensor]], grad_o: Optional[torch.Tensor],
                   grad_attn: Optional[torch.Tensor], *, n_head: int, d_k: int, d_model: int, has_inconv: bool,
@@ -348,8 +373,16 @@ def ltae_backward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: 
         keep.append(m)
         cparams.attn_keep = m.data_ptr()
     f32 = dict(dtype=torch.float32, device=dev)
+    # the accumulated (atomic) outputs are slices of ONE zero-filled buffer: one memset instead of one per tensor
+    want_pe = (not attn_only) and need_grad_pe and pe_mode != _lib.PE_NONE
+    sizes = [c * 16, b * t * 16] + ([c, c] if not attn_only else []) + ([b * t * d_model] if want_pe else [])
+    offs = [0]
+    for sz in sizes:
+        offs.append(offs[-1] + (sz + 3) // 4 * 4)  # 16-byte aligned slices
+    zeros = torch.zeros(offs[-1], dtype=torch.float32, device=dev)
     res = {
-        "grad_x": torch.empty_like(x), "grad_u": torch.zeros((c, 16), **f32), "grad_cpos": torch.zeros((b, t, 16), **f32),
+        "grad_x": torch.empty_like(x), "grad_u": zeros[offs[0]:offs[0] + c * 16].view(c, 16),
+        "grad_cpos": zeros[offs[1]:offs[1] + b * t * 16].view(b, t, 16),
         "grad_gamma": None, "grad_beta": None, "zn_rows": None, "sa_rows": None, "grad_pe": None,
     }
     io = _lib.LtaeBwdIo()
@@ -359,10 +392,10 @@ def ltae_backward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: 
         go = grad_o.to(**f32).contiguous()
         keep.append(go)
         io.grad_o = go.data_ptr()
-        res["grad_gamma"], res["grad_beta"] = torch.zeros(c, **f32), torch.zeros(c, **f32)
+        res["grad_gamma"], res["grad_beta"] = zeros[offs[2]:offs[2] + c], zeros[offs[3]:offs[3] + c]
         res["zn_rows"], res["sa_rows"] = torch.empty((n, n_head, c), **f32), torch.empty((n, 16), **f32)
-        if need_grad_pe and pe_mode != _lib.PE_NONE:
-            res["grad_pe"] = torch.zeros((b, t, d_model), **f32)
+        if want_pe:
+            res["grad_pe"] = zeros[offs[4]:offs[4] + b * t * d_model].view(b, t, d_model)
     if grad_attn is not None:
         ga = grad_attn.to(**f32).contiguous()
         if tuple(ga.shape) != (n_head, b, t, h, w):
@@ -434,9 +467,11 @@ def ltae_mlp_backward(o_rows: torch.Tensor, grad_out: torch.Tensor, params: Dict
         keep.append(m)
         cparams.mlp_keep = m.data_ptr()
     f32 = dict(dtype=torch.float32, device=dev)
-    res = {"grad_o": torch.empty((n, d_model), **f32), "mlp_weight": torch.zeros((c_out, d_model), **f32)}
-    for k in ("mlp_bias", "bn_weight", "bn_bias", "out_norm_weight", "out_norm_bias"):
-        res[k] = torch.zeros(c_out, **f32)
+    cpad = (c_out + 3) // 4 * 4
+    zeros = torch.zeros(c_out * d_model + 5 * cpad, dtype=torch.float32, device=dev)  # one memset for the six accumulators
+    res = {"grad_o": torch.empty((n, d_model), **f32), "mlp_weight": zeros[:c_out * d_model].view(c_out, d_model)}
+    for i, k in enumerate(("mlp_bias", "bn_weight", "bn_bias", "out_norm_weight", "out_norm_bias")):
+        res[k] = zeros[c_out * d_model + i * cpad:c_out * d_model + i * cpad + c_out]
     o = o_rows.to(**f32).contiguous()
     mean, var = bn_mean.to(**f32).contiguous(), bn_var.to(**f32).contiguous()
     io = _lib.LtaeMlpBwdIo(o_rows=o.data_ptr(), grad_out=g.data_ptr(), bn_mean=mean.data_ptr(), bn_var=var.data_ptr(),

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 7
+#define C2S_ABI_VERSION 8
 
 enum c2s_status {
   C2S_OK = 0,
@@ -206,6 +206,17 @@ int c2s_ltae_forward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, c
                      const void* positions, const uint8_t* pad_mask, void* out, float* attn,
                      float* bn_batch_mean, float* bn_batch_var, void* workspace,
                      size_t workspace_bytes, void* stream);
+
+/* Encoders with several learned queries (num_queries = n > 1, eval mode)                    tae.py:486-499
+ * The attention head returns n rows per pixel; mlp.0 / BatchNorm1d (running statistics) / ReLU act row by row, but
+ * out_norm is applied to the transposed tensor [B*H*W, c_out, n] (tae.py:488): the statistics of a group run over its
+ * channels AND the n queries.  The caller runs c2s_ltae_forward once per query (params->query = the rows of that
+ * query, params->save_o = its rows o) and hands the stacked rows over:
+ *   o_rows : float32 [n_queries][B*H*W][d_model]
+ *   out    : [B][n_queries][c_out][H][W] in desc->dtype
+ * desc: B, H, W, d_model, c_out, n_head, dtype, gn_eps, bn_eps are read. */
+int c2s_ltae_rows_forward(const c2s_ltae_desc* desc, const c2s_ltae_params* params, const float* o_rows,
+                          int32_t n_queries, void* out, void* stream);
 
 /* Backward of LTAE.forward / LTAE4WTAE.forward through everything that touches the [B*H*W, T, C] features
  * (autograd of tae.py:451-504 in the reference).  The rows after the attention (MLP, BatchNorm, ReLU, output

@@ -54,9 +54,28 @@ def test_ltae_fp32_matches_reference(name, zero_padded):
             assert np.all(a[:, b, pad[b]] == 0.0)
 
 
-def test_two_queries_is_rejected_loudly():
-    cfg, inp, params, _ = load("ltae_two_queries")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_two_queries_match_reference(dtype):
+    """num_queries = 2 (tae.py:495-499): out[B, n, C', H, W], attn[n_head, B, n, T, H, W], one kernel pass per query."""
+    cfg, inp, params, outs = load("ltae_two_queries")
     m = module_from_fixture(cfg, params).eval()
+    x = inp["x"] if dtype == torch.float32 else bf16_round(inp["x"])
+    with torch.no_grad():
+        out, attn = m(to_dev(x, dtype=dtype), batch_positions=to_dev(inp["positions"]), pad_mask=to_dev(inp["pad_mask"]))
+    assert out.shape == outs["out"].shape and attn.shape == outs["attn"].shape
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    assert rel_err(attn.cpu().numpy(), outs["attn"]) < tol
+    assert rel_err(out.float().cpu().numpy(), outs["out"]) < tol
+    pad = inp["pad_mask"]
+    a = attn.cpu().numpy()
+    for b in np.nonzero(~pad.all(axis=1))[0]:
+        assert np.all(a[:, b, :, pad[b]] == 0.0)
+
+
+def test_two_queries_in_training_mode_are_rejected_loudly():
+    """BatchNorm1d batch statistics run over the rows of all queries at once in the reference: not served per query."""
+    cfg, inp, params, _ = load("ltae_two_queries")
+    m = module_from_fixture(cfg, params).train()
     with pytest.raises(NotImplementedError):
         m(to_dev(inp["x"]), batch_positions=to_dev(inp["positions"]), pad_mask=to_dev(inp["pad_mask"]))
 
