@@ -21,6 +21,8 @@ from . import ops  # noqa: F401
 from .tile import ClassMap, TilePatchifier, patch_grid  # noqa: F401
 from .ops import pad_mask_from_input  # noqa: F401
 from . import losses  # noqa: F401
+from . import conv  # noqa: F401
+from .conv import ConvBlock, ConvLayer, DownConvBlock  # noqa: F401
 from .losses import CrossEntropyLoss, FocalCELoss, boundary_target  # noqa: F401
 
-__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "smart_forward", "pad_mask_from_input", "ops", "TilePatchifier", "ClassMap", "patch_grid", "frame_slots", "gather_frames", "scatter_frames", "GradientBucket", "losses", "CrossEntropyLoss", "FocalCELoss", "boundary_target"]
+__all__ = ["LTAE", "LTAE4WTAE", "TemporalAggregator", "install", "uninstall", "shard_patches", "shard_bounds", "gather_shards", "copy_valid_frames_", "valid_lengths", "smart_forward", "pad_mask_from_input", "ops", "TilePatchifier", "ClassMap", "patch_grid", "frame_slots", "gather_frames", "scatter_frames", "GradientBucket", "losses", "CrossEntropyLoss", "FocalCELoss", "boundary_target", "conv", "ConvLayer", "ConvBlock", "DownConvBlock"]

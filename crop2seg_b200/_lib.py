@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 8
+C2S_ABI_VERSION = 9
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -30,6 +30,7 @@ EXPORTS = (
     "c2s_ltae_workspace_bytes", "c2s_ltae_forward", "c2s_ltae_backward_workspace_bytes", "c2s_ltae_backward",
     "c2s_ltae_mlp_backward_workspace_bytes", "c2s_ltae_mlp_backward", "c2s_ltae_inconv_grad", "c2s_ltae_fold_backward",
     "c2s_ltae_rows_forward",
+    "c2s_conv2d_supported", "c2s_conv2d_workspace_bytes", "c2s_conv2d_forward", "c2s_group_stats", "c2s_group_norm_relu",
     "c2s_tile_patchify", "c2s_tile_classmap", "c2s_frame_index", "c2s_frames_gather", "c2s_frames_scatter",
     "c2s_boundary_target", "c2s_seg_loss_workspace_bytes", "c2s_seg_loss_forward", "c2s_seg_loss_backward",
 )
@@ -99,6 +100,10 @@ class LtaeFoldBwdIo(ctypes.Structure):
 
 class LtaeMlpBwdIo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in LTAE_MLP_BWD_IO_FIELDS]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("frames", "c_in", "c_out", "H", "W", "kernel", "stride", "padding", "dtype")]
 
 
 class C2SError(RuntimeError):
@@ -188,6 +193,17 @@ def load() -> ctypes.CDLL:
         lib.c2s_ltae_fold_backward.restype = i32
         lib.c2s_ltae_fold_backward.argtypes = [ctypes.POINTER(LtaeDesc), ctypes.POINTER(LtaeParams),
                                                ctypes.POINTER(LtaeFoldBwdIo), vp, sz, vp]
+        lib.c2s_conv2d_supported.restype = i32
+        lib.c2s_conv2d_supported.argtypes = [ctypes.POINTER(ConvDesc)]
+        lib.c2s_conv2d_workspace_bytes.restype = sz
+        lib.c2s_conv2d_workspace_bytes.argtypes = [ctypes.POINTER(ConvDesc)]
+        lib.c2s_conv2d_forward.restype = i32
+        lib.c2s_conv2d_forward.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, sz, vp]
+        lib.c2s_group_stats.restype = i32
+        lib.c2s_group_stats.argtypes = [vp, i32, ctypes.c_int64, i32, ctypes.c_int64, i32, vp, vp]
+        lib.c2s_group_norm_relu.restype = i32
+        lib.c2s_group_norm_relu.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, ctypes.c_int64, i32, ctypes.c_int64, i32,
+                                            ctypes.c_float, i32, vp]
         got = lib.c2s_abi_version()
         if got != C2S_ABI_VERSION:
             raise C2SError(f"ABI mismatch: library reports version {got}, binding expects {C2S_ABI_VERSION}")

@@ -1,0 +1,494 @@
+// Shared convolutional encoder over the (batch x time) frames, sm_100a.
+// Reference: ConvLayer = Conv2d(k, padding_mode='reflect') -> GroupNorm(n_groups) -> ReLU, src/backbones/conv.py:29-96;
+// ConvBlock (conv.py:164-200), DownConvBlock (conv.py:238-296) and their smart_forward over B*T frames
+// (src/backbones/temp_shared_block.py:18-47).
+//
+//   c2s_conv2d_forward   3x3 / stride 1 / reflect padding as an implicit GEMM on the 5th-generation tensor cores:
+//                        D[pixel, c_out] = sum_{tap, c} X[pixel + tap, c] * W[c_out, tap, c]      (bf16 x bf16 -> fp32)
+//     * one persistent CTA per SM walks over (frame, band of image rows) units; M = one image row of 128 pixels,
+//       N = 64 output channels, K = 9 taps x C_in;
+//     * the input row y of a frame is brought in ONCE: four producer warps read the NCHW rows (16-byte loads),
+//       transpose 8 channel x 8 pixel blocks in registers (PRMT) and store them pixel-major into a ring slot
+//       [130 pixels][64 channels] in the K-major 128-byte-swizzled layout tcgen05 reads (chunk ^ (row & 7); the two halo
+//       pixels are the reflected ones, so the padding costs nothing);
+//     * the nine taps of an output row are nine START ADDRESSES into three ring slots (rows y-1, y, y+1 -- reflected at the
+//       frame edges -- shifted by 0 / 1 / 2 pixel rows of 128 bytes; tools/ubench/umma_rowshift.cu shows that the matrix
+//       descriptor accepts any 128-byte-aligned start when the swizzle follows the absolute address), so shared memory is
+//       filled at 1x the input bytes instead of 9x;
+//     * the prepared weights [64][9 * C_in] (bf16, K-major, 64-wide swizzled chunks) stay resident in shared memory;
+//     * one elected thread issues tcgen05.mma (M 128, N 64, K 16) into one of two TMEM accumulators; tcgen05.commit frees
+//       ring slots and hands the accumulator to four epilogue warps (tcgen05.ld), which add the bias, store the raw
+//       (pre-normalisation) row as bf16 NCHW and keep the GroupNorm sums of their frame in registers (one atomic per warp
+//       and quarter of the channels per unit).
+//   c2s_group_stats      per-(frame, group) sum / sum of squares of a raw NCHW tensor (layers whose convolution ran elsewhere)
+//   c2s_group_norm_relu  y = relu((x - mean) * rstd * gamma + beta) [+ residual]: the second, element-wise pass
+//                        (GroupNorm needs the statistics of the whole frame before the first output element).
+// Forward only (inference).  bf16 features; the statistics and the normalisation are fp32.
+#include "c2s_common.cuh"
+
+namespace c2s {
+namespace {
+
+constexpr int kCW = 128;             // image width served by the tensor-core kernel = UMMA M
+constexpr int kCN = 64;              // output channels = UMMA N
+constexpr int kSlotBytes = 17408;    // 130 pixel rows x 128 B, rounded up to the 1024-byte swizzle atom
+constexpr int kRing = 6;             // input rows in flight
+constexpr int kConvThreads = 288;    // warp 0: MMA issuer, warps 1-4: producers, warps 5-8: epilogue
+constexpr int kStatQuarters = 4;     // statistics granularity of the tensor-core kernel: 16 channels
+
+struct ConvArgs {
+  const __nv_bfloat16* x;    // [frames][c_in][H][128]
+  __nv_bfloat16* y;          // [frames][64][H][128] raw convolution output (bias added)
+  const float* bias;         // [64] or nullptr
+  float* stats;              // [frames][4][2] sum, sum of squares per 16-channel quarter (accumulated), or nullptr
+  const __nv_bfloat16* wp;   // [64][chunks * 64] prepared weights, k = tap * CK + c
+  int frames, c_in, H, rows_per_unit, units_per_frame, n_units;
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart; any 128-byte aligned start
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// the unit -> (frame, rows) arithmetic shared by the three roles
+struct Unit {
+  int f, y0, y1, lo, hi;  // output rows [y0, y1), input rows [lo, hi]
+};
+__device__ __forceinline__ Unit unit_of(const ConvArgs& a, int u) {
+  Unit t;
+  t.f = u / a.units_per_frame;
+  const int band = u - t.f * a.units_per_frame;
+  t.y0 = band * a.rows_per_unit;
+  t.y1 = min(t.y0 + a.rows_per_unit, a.H);
+  t.lo = max(t.y0 - 1, 0);
+  t.hi = min(t.y1, a.H - 1);
+  return t;
+}
+
+template <int CK>
+__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvArgs a) {
+  constexpr int KS = CK / 16;                      // k-steps (MMA instructions) per tap
+  constexpr int NCHUNK = (9 * CK + 63) / 64;       // 64-wide K chunks of the resident weights
+  constexpr int CB = CK / 8;                       // 8-channel blocks per pixel row
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * kRing + 4];  // full[R], empty[R], tfull[2], tempty[2]
+  __shared__ uint32_t tmem_s;
+  __shared__ float s_bias[kCN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (s32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* sm = smem_raw + (base - s32(smem_raw));
+  const uint32_t ring = base + NCHUNK * 8192;
+  unsigned char* ring_ptr = sm + NCHUNK * 8192;
+  const uint32_t bar0 = s32(&bars[0]);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kRing + s); };
+  auto tfull = [&](int b) { return bar0 + 8u * (2 * kRing + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (2 * kRing + 2 + b); };
+
+  if (tid == 0) {
+    for (int s = 0; s < kRing; ++s) mbar_init(full(s), 128), mbar_init(empty(s), 1);
+    for (int b = 0; b < 2; ++b) mbar_init(tfull(b), 1), mbar_init(tempty(b), 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s32(&tmem_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < kCN) s_bias[tid] = a.bias != nullptr ? a.bias[tid] : 0.f;
+  // resident weights: [chunk][64 rows n][128 B], 16-byte pieces at chunk position c16 ^ (n & 7)
+  for (int i = tid; i < kCN * NCHUNK * 8; i += kConvThreads) {
+    const int c16 = i & 7, j = (i >> 3) % NCHUNK, n = i / (8 * NCHUNK);
+    const uint4 v = *reinterpret_cast<const uint4*>(a.wp + static_cast<size_t>(n) * (NCHUNK * 64) + j * 64 + c16 * 8);
+    *reinterpret_cast<uint4*>(sm + j * 8192 + n * 128 + ((c16 ^ (n & 7)) << 4)) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tacc = tmem_s;
+
+  if (warp == 0) {
+    // ---- MMA issuer ----------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      uint32_t idesc = 0;
+      idesc |= 1u << 4;                                  // D = fp32
+      idesc |= 1u << 7;                                  // A = bf16
+      idesc |= 1u << 10;                                 // B = bf16
+      idesc |= static_cast<uint32_t>(kCN >> 3) << 17;    // N
+      idesc |= static_cast<uint32_t>(kCW >> 4) << 24;    // M
+      unsigned g_base = 0, o = 0;
+      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        const Unit t = unit_of(a, u);
+        const int n_in = t.hi - t.lo + 1;
+        int have = 0, freed = 0;
+        for (int y = t.y0; y < t.y1; ++y) {
+          const int need = min(y + 1, a.H - 1) - t.lo + 1;
+          while (have < need) {
+            const unsigned gi = g_base + have;
+            mbar_wait(full(gi % kRing), (gi / kRing) & 1u);
+            ++have;
+          }
+          const unsigned buf = o & 1u;
+          if (o >= 2) mbar_wait(tempty(buf), ((o >> 1) - 1u) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            int ry = y + dy;
+            ry = ry < 0 ? -ry : (ry >= a.H ? 2 * a.H - 2 - ry : ry);  // reflect (conv.py:76 padding_mode)
+            const unsigned gi = g_base + static_cast<unsigned>(ry - t.lo);
+            const uint32_t a0 = ring + (gi % kRing) * kSlotBytes + (1 + dx) * 128;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const int s = tap * KS + ks;
+              umma_bf16(tacc + buf * kCN, umma_desc_k_sw128(a0 + ks * 32),
+                        umma_desc_k_sw128(base + (s >> 2) * 8192 + (s & 3) * 32), idesc, s != 0);
+            }
+          }
+          umma_commit(tfull(buf));
+          ++o;
+          // input rows below y are not needed by later output rows of this unit
+          const int free_to = y - t.lo;
+          while (freed < free_to) {
+            umma_commit(empty((g_base + freed) % kRing));
+            ++freed;
+          }
+        }
+        while (freed < n_in) {
+          umma_commit(empty((g_base + freed) % kRing));
+          ++freed;
+        }
+        g_base += n_in;
+      }
+    }
+  } else if (warp <= 4) {
+    // ---- producers: one 8 channel x 8 pixel block per thread and input row -------------------------------------------
+    const int ptid = tid - 32;
+    const int cb = ptid % CB, pb = ptid / CB;
+    const bool active = pb < kCW / 8;
+    unsigned g = 0;
+    const size_t plane = static_cast<size_t>(a.H) * kCW;
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+      const Unit t = unit_of(a, u);
+      for (int r = t.lo; r <= t.hi; ++r, ++g) {
+        const unsigned slot = g % kRing;
+        if (g >= kRing) mbar_wait(empty(slot), ((g / kRing) - 1u) & 1u);
+        if (active) {
+          uint4 v[8];
+          const __nv_bfloat16* src = a.x + (static_cast<size_t>(t.f) * a.c_in + cb * 8) * plane + static_cast<size_t>(r) * kCW + pb * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            v[i] = (cb * 8 + i < a.c_in) ? __ldg(reinterpret_cast<const uint4*>(src + i * plane)) : make_uint4(0, 0, 0, 0);
+          unsigned char* sl = ring_ptr + slot * kSlotBytes;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+            // word j / 2 of channel i holds pixels (j & ~1, j | 1) of that channel
+            auto word = [&](int i) -> uint32_t {
+              return (j >> 1) == 0 ? v[i].x : ((j >> 1) == 1 ? v[i].y : ((j >> 1) == 2 ? v[i].z : v[i].w));
+            };
+            uint4 w;
+            w.x = __byte_perm(word(0), word(1), sel);
+            w.y = __byte_perm(word(2), word(3), sel);
+            w.z = __byte_perm(word(4), word(5), sel);
+            w.w = __byte_perm(word(6), word(7), sel);
+            const int row = pb * 8 + j + 1;
+            *reinterpret_cast<uint4*>(sl + row * 128 + ((cb ^ (row & 7)) << 4)) = w;
+            if (pb == 0 && j == 1) *reinterpret_cast<uint4*>(sl + ((cb ^ 0) << 4)) = w;                       // pixel -1 = pixel 1
+            if (pb == kCW / 8 - 1 && j == 6) *reinterpret_cast<uint4*>(sl + 129 * 128 + ((cb ^ (129 & 7)) << 4)) = w;  // pixel 128 = pixel 126
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> tensor-core (async proxy) reads
+        mbar_arrive(full(slot));
+      }
+    }
+  } else {
+    // ---- epilogue: TMEM lanes 32 q .. 32 q + 31 = pixels of the row --------------------------------------------------
+    const int q = warp & 3;
+    const int x = q * 32 + lane;
+    unsigned o = 0;
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+      const Unit t = unit_of(a, u);
+      float s1[kStatQuarters], s2[kStatQuarters];
+#pragma unroll
+      for (int k = 0; k < kStatQuarters; ++k) s1[k] = 0.f, s2[k] = 0.f;
+      for (int y = t.y0; y < t.y1; ++y, ++o) {
+        const unsigned buf = o & 1u;
+        mbar_wait(tfull(buf), (o >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tacc + (static_cast<uint32_t>(q * 32) << 16) + buf * kCN;
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(tempty(buf));  // the accumulator is in registers: the next row but one may overwrite it
+        __nv_bfloat16* dst = a.y + (static_cast<size_t>(t.f) * kCN * a.H + y) * kCW + x;
+        const size_t cstride = static_cast<size_t>(a.H) * kCW;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float v0 = __uint_as_float(r0[c]) + s_bias[c], v1 = __uint_as_float(r1[c]) + s_bias[32 + c];
+          dst[c * cstride] = __float2bfloat16_rn(v0);
+          dst[(32 + c) * cstride] = __float2bfloat16_rn(v1);
+          s1[c >> 4] += v0, s2[c >> 4] = fmaf(v0, v0, s2[c >> 4]);
+          s1[2 + (c >> 4)] += v1, s2[2 + (c >> 4)] = fmaf(v1, v1, s2[2 + (c >> 4)]);
+        }
+      }
+      if (a.stats != nullptr) {
+#pragma unroll
+        for (int k = 0; k < kStatQuarters; ++k) {
+          const float t1 = warp_sum(s1[k]), t2 = warp_sum(s2[k]);
+          if (lane == 0) {
+            atomicAdd(a.stats + (static_cast<size_t>(t.f) * kStatQuarters + k) * 2, t1);
+            atomicAdd(a.stats + (static_cast<size_t>(t.f) * kStatQuarters + k) * 2 + 1, t2);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tacc) : "memory");
+}
+
+// weight[c_out][c_in][3][3] fp32 -> wp[c_out][chunks * 64] bf16 with k = tap * CK + c (zero for c >= c_in and behind 9 CK)
+__global__ void conv_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int ck,
+                                        int k_total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c_out * k_total) return;
+  const int n = i / k_total, k = i - n * k_total;
+  const int tap = k / ck, c = k - tap * ck;
+  float v = 0.f;
+  if (tap < 9 && c < c_in) v = w[(static_cast<size_t>(n) * c_in + c) * 9 + tap];
+  wp[i] = __float2bfloat16_rn(v);
+}
+
+// ---- GroupNorm over (channels of the group) x H x W of one frame -----------------------------------------------------
+constexpr int kStatThreads = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(kStatThreads) group_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, size_t span) {
+  // block (g, f): the group's channels are contiguous in NCHW: one span of cpg * H * W elements
+  const size_t blk = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+  const T* p = x + blk * span;
+  float s1 = 0.f, s2 = 0.f;
+  for (size_t i = threadIdx.x; i < span; i += kStatThreads) {
+    const float v = Elem<T>::load(p + i);
+    s1 += v, s2 = fmaf(v, v, s2);
+  }
+  __shared__ double r1[kStatThreads / 32], r2[kStatThreads / 32];
+  s1 = warp_sum(s1), s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) r1[threadIdx.x >> 5] = s1, r2[threadIdx.x >> 5] = s2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int i = 0; i < kStatThreads / 32; ++i) t1 += r1[i], t2 += r2[i];
+    stats[blk * 2] = static_cast<float>(t1), stats[blk * 2 + 1] = static_cast<float>(t2);
+  }
+}
+
+struct NormArgs {
+  const void* x;         // raw [frames][C][hw]
+  const void* residual;  // [frames][C][hw] or nullptr
+  void* out;
+  const float* stats;    // [frames][n_sub][2]
+  const float* gamma;
+  const float* beta;
+  int C, hw, n_groups, n_sub, relu;
+  float eps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) group_norm_relu_kernel(const NormArgs a) {
+  constexpr int VEC = Elem<T>::kVec;
+  const int f = blockIdx.y;
+  const size_t per_frame = static_cast<size_t>(a.C) * a.hw;
+  const size_t e = (static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x) * VEC;
+  if (e >= per_frame) return;
+  const int c = static_cast<int>(e / a.hw);  // hw % VEC == 0: the vector stays inside one channel
+  const int cpg = a.C / a.n_groups, g = c / cpg, spg = a.n_sub / a.n_groups;
+  double t1 = 0.0, t2 = 0.0;
+  for (int k = 0; k < spg; ++k) {
+    t1 += a.stats[(static_cast<size_t>(f) * a.n_sub + g * spg + k) * 2];
+    t2 += a.stats[(static_cast<size_t>(f) * a.n_sub + g * spg + k) * 2 + 1];
+  }
+  const double n = static_cast<double>(cpg) * a.hw;
+  const double mean = t1 / n;
+  double var = t2 / n - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  const float sc = rstd * a.gamma[c], sh = a.beta[c] - static_cast<float>(mean) * sc;
+  const size_t off = static_cast<size_t>(f) * per_frame + e;
+  float v[VEC];
+  Elem<T>::unpack(*reinterpret_cast<const uint4*>(static_cast<const T*>(a.x) + off), v);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = fmaf(v[i], sc, sh);
+    if (a.relu) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (a.residual != nullptr) {
+    float rv[VEC];
+    Elem<T>::unpack(*reinterpret_cast<const uint4*>(static_cast<const T*>(a.residual) + off), rv);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] += rv[i];
+  }
+  *reinterpret_cast<uint4*>(static_cast<T*>(a.out) + off) = Elem<T>::pack(v);
+}
+
+int conv_ck(int c_in) { return c_in <= 16 ? 16 : 64; }
+int conv_chunks(int ck) { return (9 * ck + 63) / 64; }
+
+}  // namespace
+}  // namespace c2s
+
+extern "C" {
+
+int c2s_conv2d_supported(const c2s_conv_desc* d) {
+  if (d == nullptr) return 0;
+  return d->kernel == 3 && d->stride == 1 && d->padding == 1 && d->W == c2s::kCW && d->H >= 2 && d->c_out == c2s::kCN &&
+         (d->c_in <= 16 || d->c_in == 64) && d->c_in >= 1 && d->dtype == C2S_BF16 && d->frames > 0;
+}
+
+size_t c2s_conv2d_workspace_bytes(const c2s_conv_desc* d) {
+  if (!c2s_conv2d_supported(d)) return 0;
+  return static_cast<size_t>(c2s::kCN) * c2s::conv_chunks(c2s::conv_ck(d->c_in)) * 64 * sizeof(__nv_bfloat16);
+}
+
+int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const float* weight, const float* bias, void* y, float* stats,
+                       void* workspace, size_t workspace_bytes, void* stream_ptr) {
+  using namespace c2s;
+  C2S_CHECK_ARG(desc != nullptr && x != nullptr && weight != nullptr && y != nullptr, "c2s_conv2d_forward: NULL argument");
+  const c2s_conv_desc& d = *desc;
+  if (!c2s_conv2d_supported(desc))
+    C2S_UNSUPPORTED("c2s_conv2d_forward: serves 3x3 / stride 1 / reflect padding 1, W = 128, c_out = 64, c_in <= 16 or 64, bf16 "
+                    "(got k=%d s=%d p=%d W=%d c_in=%d c_out=%d dtype=%d)", d.kernel, d.stride, d.padding, d.W, d.c_in, d.c_out,
+                    d.dtype);
+  C2S_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0,
+                "c2s_conv2d_forward: x and y must be 16-byte aligned");
+  const size_t need = c2s_conv2d_workspace_bytes(desc);
+  C2S_CHECK_ARG(workspace != nullptr && workspace_bytes >= need, "c2s_conv2d_forward: workspace of %zu bytes needed, %zu given",
+                need, workspace_bytes);
+  int status = check_device();
+  if (status != C2S_OK) return status;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_ptr);
+  const int ck = conv_ck(d.c_in), chunks = conv_chunks(ck), k_total = chunks * 64;
+  __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(workspace);
+  conv_weight_prep_kernel<<<ceil_div(kCN * k_total, 256), 256, 0, stream>>>(weight, wp, kCN, d.c_in, ck, k_total);
+  C2S_LAUNCH_CHECK("conv_weight_prep");
+  if (stats != nullptr) C2S_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(d.frames) * kStatQuarters * 2 * sizeof(float), stream));
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  ConvArgs a{};
+  a.x = static_cast<const __nv_bfloat16*>(x), a.y = static_cast<__nv_bfloat16*>(y), a.bias = bias, a.stats = stats, a.wp = wp;
+  a.frames = d.frames, a.c_in = d.c_in, a.H = d.H;
+  // whole frames per unit when there are enough of them to balance the SMs, bands of rows otherwise
+  a.rows_per_unit = d.H;
+  while (a.rows_per_unit > 16 && static_cast<long long>(d.frames) * ceil_div(d.H, a.rows_per_unit) < 4LL * sms) a.rows_per_unit /= 2;
+  a.units_per_frame = ceil_div(d.H, a.rows_per_unit);
+  a.n_units = d.frames * a.units_per_frame;
+  const int grid = a.n_units < sms ? a.n_units : sms;
+  const size_t smem = static_cast<size_t>(chunks) * 8192 + static_cast<size_t>(kRing) * kSlotBytes + 1024;
+  if (ck == 16) {
+    C2S_SMEM_ATTR(conv3x3_tc_kernel<16>, smem);
+    conv3x3_tc_kernel<16><<<grid, kConvThreads, smem, stream>>>(a);
+  } else {
+    C2S_SMEM_ATTR(conv3x3_tc_kernel<64>, smem);
+    conv3x3_tc_kernel<64><<<grid, kConvThreads, smem, stream>>>(a);
+  }
+  C2S_LAUNCH_CHECK("conv3x3_reflect<tcgen05>");
+  return C2S_OK;
+}
+
+int c2s_group_stats(const void* x, int32_t dtype, int64_t frames, int32_t channels, int64_t hw, int32_t n_groups, float* stats,
+                    void* stream_ptr) {
+  using namespace c2s;
+  C2S_CHECK_ARG(x != nullptr && stats != nullptr, "c2s_group_stats: NULL argument");
+  C2S_CHECK_ARG(frames > 0 && channels > 0 && hw > 0 && n_groups > 0 && channels % n_groups == 0,
+                "c2s_group_stats: bad shape frames=%lld C=%d hw=%lld groups=%d", static_cast<long long>(frames), channels,
+                static_cast<long long>(hw), n_groups);
+  C2S_CHECK_ARG(dtype == C2S_F32 || dtype == C2S_BF16, "c2s_group_stats: unknown dtype %d", dtype);
+  int status = check_device();
+  if (status != C2S_OK) return status;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_ptr);
+  const size_t span = static_cast<size_t>(channels / n_groups) * hw;
+  dim3 grid(n_groups, static_cast<unsigned>(frames));
+  if (dtype == C2S_BF16)
+    group_stats_kernel<__nv_bfloat16><<<grid, kStatThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), stats, span);
+  else
+    group_stats_kernel<float><<<grid, kStatThreads, 0, stream>>>(static_cast<const float*>(x), stats, span);
+  C2S_LAUNCH_CHECK("group_stats");
+  return C2S_OK;
+}
+
+int c2s_group_norm_relu(const void* x, const float* stats, int32_t n_sub, const float* gamma, const float* beta,
+                        const void* residual, void* out, int32_t dtype, int64_t frames, int32_t channels, int64_t hw,
+                        int32_t n_groups, float eps, int32_t relu, void* stream_ptr) {
+  using namespace c2s;
+  C2S_CHECK_ARG(x != nullptr && stats != nullptr && gamma != nullptr && beta != nullptr && out != nullptr,
+                "c2s_group_norm_relu: NULL argument");
+  C2S_CHECK_ARG(frames > 0 && channels > 0 && hw > 0 && n_groups > 0 && channels % n_groups == 0 && n_sub > 0 &&
+                    n_sub % n_groups == 0,
+                "c2s_group_norm_relu: bad shape");
+  C2S_CHECK_ARG(dtype == C2S_F32 || dtype == C2S_BF16, "c2s_group_norm_relu: unknown dtype %d", dtype);
+  const int vec = dtype == C2S_BF16 ? 8 : 4;
+  C2S_CHECK_ARG(hw % vec == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(residual) % 16 == 0,
+                "c2s_group_norm_relu: planes must be whole, aligned 16-byte vectors");
+  int status = check_device();
+  if (status != C2S_OK) return status;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_ptr);
+  NormArgs a{};
+  a.x = x, a.residual = residual, a.out = out, a.stats = stats, a.gamma = gamma, a.beta = beta;
+  a.C = channels, a.hw = static_cast<int>(hw), a.n_groups = n_groups, a.n_sub = n_sub, a.relu = relu, a.eps = eps;
+  dim3 grid(ceil_div(static_cast<long long>(channels) * hw / vec, 256), static_cast<unsigned>(frames));
+  if (dtype == C2S_BF16)
+    group_norm_relu_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
+  else
+    group_norm_relu_kernel<float><<<grid, 256, 0, stream>>>(a);
+  C2S_LAUNCH_CHECK("group_norm_relu");
+  return C2S_OK;
+}
+
+}  // extern "C"

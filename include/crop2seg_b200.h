@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 8
+#define C2S_ABI_VERSION 9
 
 enum c2s_status {
   C2S_OK = 0,
@@ -377,6 +377,45 @@ int c2s_seg_loss_backward(const c2s_loss_desc* desc, const void* scores, const i
 /* ------------------------------------------------------------------------------------------
  * library services
  * ---------------------------------------------------------------------------------------- */
+/* ------------------------------------------------------------------------------------------
+ * Shared convolutional encoder over the B*T frames
+ *   ConvLayer = Conv2d(reflect padding) -> GroupNorm -> ReLU      src/backbones/conv.py:29-96
+ *   ConvBlock / DownConvBlock                                      conv.py:164-200, 238-296
+ *   smart_forward over the valid frames                            temp_shared_block.py:18-47
+ * Forward only.  Frames are packed (c2s_frame_index / c2s_frames_gather): [frames][C][H][W].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct c2s_conv_desc {
+  int32_t frames;                  /* packed frames                                              */
+  int32_t c_in, c_out;
+  int32_t H, W;                    /* input resolution                                           */
+  int32_t kernel, stride, padding; /* nn.Conv2d(k, stride, padding, padding_mode='reflect')      */
+  int32_t dtype;                   /* enum c2s_dtype of x and y                                  */
+} c2s_conv_desc;
+
+/* 1 when c2s_conv2d_forward serves the layer on the tensor cores: 3x3, stride 1, padding 1, W = 128, c_out = 64,
+ * c_in <= 16 or c_in = 64, bf16 (U-TAE's in_conv: utae.py:128-136).  Other layers are the caller's business. */
+int c2s_conv2d_supported(const c2s_conv_desc* desc);
+size_t c2s_conv2d_workspace_bytes(const c2s_conv_desc* desc); /* prepared bf16 weights */
+
+/* y[f, o, y, x] = bias[o] + sum_{c, ky, kx} weight[o, c, ky, kx] * x[f, c, reflect(y + ky - 1), reflect(x + kx - 1)]
+ *   x      : [frames, c_in, H, W] bf16          weight : float32 [c_out, c_in, 3, 3] (nn.Conv2d.weight), bias float32 [c_out] | NULL
+ *   y      : [frames, c_out, H, W] bf16, the RAW convolution output (GroupNorm needs the whole frame first)
+ *   stats  : float32 [frames][4][2] = (sum, sum of squares) of the fp32 outputs per frame and quarter of the channels
+ *            (written, not accumulated), for c2s_group_norm_relu with n_sub = 4; or NULL */
+int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const float* weight, const float* bias, void* y,
+                       float* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* stats[f][g] = (sum, sum of squares) over the channels of group g and the hw pixels of frame f of x[frames, C, hw]. */
+int c2s_group_stats(const void* x, int32_t dtype, int64_t frames, int32_t channels, int64_t hw, int32_t n_groups,
+                    float* stats, void* stream);
+
+/* out = act(GroupNorm(x)) [+ residual]: nn.GroupNorm(n_groups, C) with the statistics of c2s_conv2d_forward (n_sub = 4)
+ * or c2s_group_stats (n_sub = n_groups), then ReLU when `relu` (conv.py:83-86), then the residual of DownConvBlock
+ * (`out + conv2(out)`, conv.py:291).  x, residual, out : [frames, C, hw] in `dtype`; out may alias x. */
+int c2s_group_norm_relu(const void* x, const float* stats, int32_t n_sub, const float* gamma, const float* beta,
+                        const void* residual, void* out, int32_t dtype, int64_t frames, int32_t channels, int64_t hw,
+                        int32_t n_groups, float eps, int32_t relu, void* stream);
+
 int c2s_abi_version(void);
 const char* c2s_last_error(void);
 /* Number of kernels this library launched (all threads of the process) since the last reset

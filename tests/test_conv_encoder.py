@@ -1,0 +1,144 @@
+"""Shared convolutional encoder blocks: ``crop2seg_b200.ConvBlock`` / ``DownConvBlock``.
+
+CPU: the ``state_dict`` contract against the reference blocks' own keys (fixtures of tests/golden/make_conv_golden.py),
+loud failures for what the inference path does not serve.
+GPU (``-m gpu``): the tcgen05 implicit-GEMM convolution against a plain fp32 torch convolution of the same bf16 operands
+(bands, whole-frame units, several units per CTA, 10 and 64 input channels), its GroupNorm sums, the normalisation pass,
+and the blocks through ``smart_forward`` against what the reference blocks produced.  bf16 features: 1e-2 of max|ref|.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import crop2seg_b200 as c2s
+from crop2seg_b200 import conv as c2s_conv
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_conv_golden import CASES, synth_frames  # noqa: E402  (seeded generator only; no reference import)
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_BF16 = 1e-2
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+    cfg = json.loads(str(z["cfg"]))
+    params = {k[len("param::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param::")}
+    return cfg, params, z["out"]
+
+
+def _block(cfg, params):
+    blk = getattr(c2s, cfg["kind"])(**cfg["kwargs"])
+    missing, unexpected = blk.load_state_dict(params, strict=True)
+    assert not missing and not unexpected
+    return blk.eval()
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_state_dict_matches_the_reference_block(name):
+    cfg, params, _ = _load(name)
+    blk = getattr(c2s, cfg["kind"])(**cfg["kwargs"])
+    assert list(blk.state_dict().keys()) == list(params.keys())  # same keys, same order
+    for k, v in blk.state_dict().items():
+        assert tuple(v.shape) == tuple(params[k].shape), k
+    _block(cfg, params)
+
+
+def test_what_is_not_served_fails_loudly():
+    with pytest.raises(NotImplementedError):
+        c2s.ConvBlock([10, 64], norm="batch")
+    with pytest.raises(NotImplementedError):
+        c2s.ConvBlock([10, 64], norm="group", conv_type="depthwise_separable")
+    blk = c2s.ConvBlock([10, 64], norm="group")  # training mode by default
+    with pytest.raises(NotImplementedError):
+        blk(torch.zeros(1, 10, 4, 128))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        blk.eval()(torch.zeros(1, 10, 4, 128))
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _torch_conv(x, w, b):
+    xp = torch.nn.functional.pad(x.float(), (1, 1, 1, 1), mode="reflect")
+    return torch.nn.functional.conv2d(xp, w.to(torch.bfloat16).float(), b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("frames,c_in,h", [(3, 64, 12), (2, 10, 7), (1, 64, 2), (5, 3, 33), (150, 64, 16), (20, 64, 128)])
+def test_tensor_core_convolution_matches_torch(frames, c_in, h):
+    g = torch.Generator(device="cuda").manual_seed(frames * 131 + c_in)
+    x = torch.randn((frames, c_in, h, 128), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((64, c_in, 3, 3), device="cuda", generator=g) * (1.0 / (3.0 * c_in ** 0.5))
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    conv = torch.nn.Conv2d(c_in, 64, 3, padding=1, padding_mode="reflect")
+    assert c2s_conv.conv2d_supported(x, conv)
+    y, stats = c2s_conv.conv2d_reflect_forward(x, w, b)
+    torch.cuda.synchronize()
+    assert c2s.ops._lib.load().c2s_last_kernel().decode() == "conv3x3_reflect<tcgen05>"
+    ref = _torch_conv(x, w, b)
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16
+    err = (y.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 6e-3, err  # bf16 rounding of the stored output; the products are exact, the sums fp32
+    # GroupNorm sums of the fp32 values, per frame and quarter of the channels
+    q = ref.view(frames, 4, -1)
+    s1, s2 = q.sum(-1), (q * q).sum(-1)
+    assert torch.allclose(stats[..., 0], s1, rtol=2e-3, atol=2e-3 * s1.abs().max().item())
+    assert torch.allclose(stats[..., 1], s2, rtol=2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("residual", [False, True])
+def test_group_norm_relu_matches_torch(dtype, residual):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn((3, 64, 8, 24), device="cuda", generator=g) * 2 + 0.5).to(dtype)
+    res = torch.randn((3, 64, 8, 24), device="cuda", generator=g).to(dtype) if residual else None
+    norm = torch.nn.GroupNorm(4, 64).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.3 * torch.randn(64, device="cuda", generator=g))
+        norm.bias.copy_(0.2 * torch.randn(64, device="cuda", generator=g))
+    stats = c2s_conv.group_stats(x, 4)
+    out = c2s_conv.group_norm_relu(x, stats, norm, relu=True, residual=res)
+    with torch.no_grad():
+        ref = torch.relu(norm(x.float()))
+        if residual:
+            ref = ref + res.float()
+    tol = 1e-5 if dtype == torch.float32 else TOL_BF16
+    assert _rel(out.float().cpu().numpy(), ref.cpu().numpy()) < tol
+    # statistics at a finer granularity (16 sub-groups; the convolution kernel hands over 4) give the same result
+    out16 = c2s_conv.group_norm_relu(x, c2s_conv.group_stats(x, 16), norm, relu=True, residual=res)
+    assert _rel(out16.float().cpu().numpy(), out.float().cpu().numpy()) < (1e-6 if dtype == torch.float32 else TOL_BF16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_blocks_match_the_reference(name):
+    cfg, params, ref = _load(name)
+    blk = _block(cfg, params).cuda()
+    x = synth_frames(cfg["seed"], tuple(cfg["shape"]), [tuple(p) for p in cfg["padded"]], cfg["relu_input"])
+    with torch.no_grad():
+        out = blk.smart_forward(torch.from_numpy(x).cuda().to(torch.bfloat16))
+    assert tuple(out.shape) == ref.shape and out.dtype == torch.bfloat16
+    got = out.float().cpu().numpy()
+    assert _rel(got, ref) < TOL_BF16 * 2, _rel(got, ref)  # two to three bf16 layers deep
+    for b, t in cfg["padded"]:  # padded frames come back as pad_value, exactly (temp_shared_block.py:30-40)
+        assert np.all(got[b, t] == 0.0)
+
+
+@pytest.mark.gpu
+def test_in_conv_runs_on_the_tensor_core_kernel():
+    blk = c2s.ConvBlock([10, 64, 64], pad_value=0, norm="group").cuda().eval()
+    x = torch.randn((2, 10, 6, 128), device="cuda").to(torch.bfloat16)
+    c2s.ops._lib.reset_launch_count()
+    with torch.no_grad():
+        blk(x)
+    torch.cuda.synchronize()
+    # per layer: weight preparation, convolution, normalisation pass (the statistics come out of the convolution)
+    assert c2s.ops._lib.launch_count() == 6
