@@ -464,6 +464,7 @@ def run_b200(args):
             sub["training"] = bench_lib.training(dev, local_rank, B=16, min_seconds=args.sub_seconds)
             sub["tile"] = bench_lib.tile(dev, "timeunet", B=B)
             sub["tile_utae"] = bench_lib.tile(dev, "utae", B=B)
+            sub["encoder"] = bench_lib.encoder(dev, frames=1024, min_seconds=args.sub_seconds)
         sub["sub_clocks"] = sub_clocks.summary()  # sampled over the sub-records (several seconds of load)
         if rank == 0 and world > 1:
             sub["topology"] = bench_lib.topology()

@@ -7,7 +7,8 @@
 //                        D[pixel, c_out] = sum_{tap, c} X[pixel + tap, c] * W[c_out, tap, c]      (bf16 x bf16 -> fp32)
 //     * one persistent CTA per SM walks over (frame, band of image rows) units; M = one image row of 128 pixels,
 //       N = 64 output channels, K = 9 taps x C_in;
-//     * the input row y of a frame is brought in ONCE: four producer warps read the NCHW rows (16-byte loads),
+//     * the input row y of a frame is brought in ONCE: four producer warps read the NCHW rows (16-byte loads, the next
+//       row's loads in flight while the current one is stored),
 //       transpose 8 channel x 8 pixel blocks in registers (PRMT) and store them pixel-major into a ring slot
 //       [130 pixels][64 channels] in the K-major 128-byte-swizzled layout tcgen05 reads (chunk ^ (row & 7); the two halo
 //       pixels are the reflected ones, so the padding costs nothing);
@@ -17,7 +18,7 @@
 //       filled at 1x the input bytes instead of 9x;
 //     * the prepared weights [64][9 * C_in] (bf16, K-major, 64-wide swizzled chunks) stay resident in shared memory;
 //     * one elected thread issues tcgen05.mma (M 128, N 64, K 16) into one of two TMEM accumulators; tcgen05.commit frees
-//       ring slots and hands the accumulator to four epilogue warps (tcgen05.ld), which add the bias, store the raw
+//       ring slots and hands the accumulator to eight epilogue warps (tcgen05.ld), which add the bias, store the raw
 //       (pre-normalisation) row as bf16 NCHW and keep the GroupNorm sums of their frame in registers (one atomic per warp
 //       and quarter of the channels per unit).
 //   c2s_group_stats      per-(frame, group) sum / sum of squares of a raw NCHW tensor (layers whose convolution ran elsewhere)
@@ -32,8 +33,9 @@ namespace {
 constexpr int kCW = 128;             // image width served by the tensor-core kernel = UMMA M
 constexpr int kCN = 64;              // output channels = UMMA N
 constexpr int kSlotBytes = 17408;    // 130 pixel rows x 128 B, rounded up to the 1024-byte swizzle atom
-constexpr int kRing = 6;             // input rows in flight
-constexpr int kConvThreads = 288;    // warp 0: MMA issuer, warps 1-4: producers, warps 5-8: epilogue
+constexpr int kRing = 8;             // input rows in flight
+constexpr int kAccBufs = 4;          // TMEM accumulators (64 columns each)
+constexpr int kConvThreads = 416;    // warp 0: MMA issuer, warps 1-4: producers, warps 5-12: epilogue (2 per TMEM lane quarter)
 constexpr int kStatQuarters = 4;     // statistics granularity of the tensor-core kernel: 16 channels
 
 struct ConvArgs {
@@ -72,11 +74,22 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// the same descriptor from its low word ((address >> 4) | leading byte offset 1 << 16); the high word is constant
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo) {
+  constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, descriptor version 1, SWIZZLE_128B
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp (the compiler then knows that exactly one thread issues the tcgen05 instructions)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -113,7 +126,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
   constexpr int NCHUNK = (9 * CK + 63) / 64;       // 64-wide K chunks of the resident weights
   constexpr int CB = CK / 8;                       // 8-channel blocks per pixel row
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[2 * kRing + 4];  // full[R], empty[R], tfull[2], tempty[2]
+  __shared__ __align__(8) unsigned long long bars[2 * kRing + 2 * kAccBufs];  // full[R], empty[R], tfull[A], tempty[A]
   __shared__ uint32_t tmem_s;
   __shared__ float s_bias[kCN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -125,15 +138,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (kRing + s); };
   auto tfull = [&](int b) { return bar0 + 8u * (2 * kRing + b); };
-  auto tempty = [&](int b) { return bar0 + 8u * (2 * kRing + 2 + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (2 * kRing + kAccBufs + b); };
 
   if (tid == 0) {
-    for (int s = 0; s < kRing; ++s) mbar_init(full(s), 128), mbar_init(empty(s), 1);
-    for (int b = 0; b < 2; ++b) mbar_init(tfull(b), 1), mbar_init(tempty(b), 128);
+    for (int s = 0; s < kRing; ++s) mbar_init(full(s), 4), mbar_init(empty(s), 1);      // one arrival per producer warp
+    for (int b = 0; b < kAccBufs; ++b) mbar_init(tfull(b), 1), mbar_init(tempty(b), 8);       // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s32(&tmem_s)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s32(&tmem_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid < kCN) s_bias[tid] = a.bias != nullptr ? a.bias[tid] : 0.f;
@@ -151,56 +164,80 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
 
   if (warp == 0) {
     // ---- MMA issuer ----------------------------------------------------------------------------------------------
-    if (lane == 0) {
+    // The issuing thread is the pipeline's clock: tcgen05.mma blocks it while the (shallow) queue is full, so every scalar
+    // instruction between the last product of a row and the first one of the next row is tensor-pipe idle time.  The
+    // bookkeeping is therefore incremental (no divisions, one barrier wait and one release per row in the steady state)
+    // and the tap loops stay rolled: the descriptor arithmetic of a tap sits between the products, not in front of them.
+    if (elect_one()) {
       uint32_t idesc = 0;
       idesc |= 1u << 4;                                  // D = fp32
       idesc |= 1u << 7;                                  // A = bf16
       idesc |= 1u << 10;                                 // B = bf16
       idesc |= static_cast<uint32_t>(kCN >> 3) << 17;    // N
       idesc |= static_cast<uint32_t>(kCW >> 4) << 24;    // M
-      unsigned g_base = 0, o = 0;
+      const uint32_t b_lo0 = ((base >> 4) & 0x3fffu) | (1u << 16);
+      uint32_t in_slot = 0, in_phase = 0;      // ring slot of the next input row to wait for; bit s = parity of slot s
+      uint32_t free_slot = 0;                  // ring slot of the next input row to release
+      uint32_t o = 0;                          // output rows issued
+      auto slot_lo = [&](uint32_t slot) { return (((ring + slot * kSlotBytes) >> 4) & 0x3fffu) | (1u << 16); };
+      auto take_row = [&]() {                  // wait for the next input row, return the descriptor word of its slot
+        mbar_wait(full(in_slot), (in_phase >> in_slot) & 1u);
+        const uint32_t lo = slot_lo(in_slot);
+        in_phase ^= 1u << in_slot;
+        in_slot = in_slot + 1 == kRing ? 0 : in_slot + 1;
+        return lo;
+      };
+      auto release_row = [&]() {               // the oldest resident input row is dead once the products issued so far are done
+        umma_commit(empty(free_slot));
+        free_slot = free_slot + 1 == kRing ? 0 : free_slot + 1;
+      };
       for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
         const Unit t = unit_of(a, u);
-        const int n_in = t.hi - t.lo + 1;
-        int have = 0, freed = 0;
+        // descriptor words of the slots holding rows y - 1, y, y + 1 (reflected at the frame edges, conv.py:76)
+        uint32_t dm, d0, dp;
+        int resident;                          // input rows of this unit waited for and not yet released
+        if (t.y0 == 0) {
+          d0 = take_row(), dp = take_row(), dm = dp, resident = 2;   // row -1 = row 1
+        } else {
+          dm = take_row(), d0 = take_row(), resident = 2;
+          if (t.y0 + 1 <= t.hi) dp = take_row(), ++resident;
+          else dp = dm;                                               // y0 = H - 1: row H = row H - 2
+        }
         for (int y = t.y0; y < t.y1; ++y) {
-          const int need = min(y + 1, a.H - 1) - t.lo + 1;
-          while (have < need) {
-            const unsigned gi = g_base + have;
-            mbar_wait(full(gi % kRing), (gi / kRing) & 1u);
-            ++have;
-          }
-          const unsigned buf = o & 1u;
-          if (o >= 2) mbar_wait(tempty(buf), ((o >> 1) - 1u) & 1u);
+          const uint32_t buf = o & (kAccBufs - 1);
+          if (o >= kAccBufs) mbar_wait(tempty(buf), ((o / kAccBufs) - 1u) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d_tmem = tacc + buf * kCN;
+          uint32_t b_lo = b_lo0;
+#pragma unroll 1
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            const uint32_t row_lo = dyi == 0 ? dm : (dyi == 1 ? d0 : dp);
+#pragma unroll 1
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              const uint32_t a_lo = row_lo + dxi * 8;   // pixel x + dx sits in row 1 + x + dx of the slot: start (1 + dx) * 128 B
+              if (KS == 4) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            int ry = y + dy;
-            ry = ry < 0 ? -ry : (ry >= a.H ? 2 * a.H - 2 - ry : ry);  // reflect (conv.py:76 padding_mode)
-            const unsigned gi = g_base + static_cast<unsigned>(ry - t.lo);
-            const uint32_t a0 = ring + (gi % kRing) * kSlotBytes + (1 + dx) * 128;
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              const int s = tap * KS + ks;
-              umma_bf16(tacc + buf * kCN, umma_desc_k_sw128(a0 + ks * 32),
-                        umma_desc_k_sw128(base + (s >> 2) * 8192 + (s & 3) * 32), idesc, s != 0);
+                for (int ks = 0; ks < KS; ++ks)
+                  umma_bf16(d_tmem, desc_from(a_lo + ks * 2), desc_from(b_lo + ks * 2), idesc, (dyi | dxi | ks) != 0);
+                b_lo += 512;                            // next tap = next 64-wide chunk of the weights (8192 B)
+              } else {                                  // CK = 16: four taps share a chunk
+                const int tap = dyi * 3 + dxi;
+                umma_bf16(d_tmem, desc_from(a_lo), desc_from(b_lo0 + (tap >> 2) * 512 + (tap & 3) * 2), idesc, tap != 0);
+              }
             }
           }
           umma_commit(tfull(buf));
           ++o;
-          // input rows below y are not needed by later output rows of this unit
-          const int free_to = y - t.lo;
-          while (freed < free_to) {
-            umma_commit(empty((g_base + freed) % kRing));
-            ++freed;
+          // row y - 1 is not needed by later output rows (the first output row of a frame has no row above it)
+          if (y > t.lo) release_row(), --resident;
+          // slide the window: rows y, y + 1, y + 2
+          if (y + 1 < t.y1) {
+            dm = d0, d0 = dp;
+            if (y + 2 <= t.hi) dp = take_row(), ++resident;
+            else dp = dm;                                             // y + 2 = H: reflected onto row H - 2 = the new row y - 1... see below
           }
         }
-        while (freed < n_in) {
-          umma_commit(empty((g_base + freed) % kRing));
-          ++freed;
-        }
-        g_base += n_in;
+        while (resident > 0) release_row(), --resident;
       }
     }
   } else if (warp <= 4) {
@@ -210,17 +247,46 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
     const bool active = pb < kCW / 8;
     unsigned g = 0;
     const size_t plane = static_cast<size_t>(a.H) * kCW;
+    auto load_row = [&](uint4 (&v)[8], int f, int r) {
+      const __nv_bfloat16* src = a.x + (static_cast<size_t>(f) * a.c_in + cb * 8) * plane + static_cast<size_t>(r) * kCW + pb * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = (active && cb * 8 + i < a.c_in) ? __ldg(reinterpret_cast<const uint4*>(src + i * plane)) : make_uint4(0, 0, 0, 0);
+    };
+    // (unit, row) cursor of the newest row whose loads are in flight: two rows ahead of the row being stored (one row of
+    // latency hiding was measured as not enough: the producers sat on the long scoreboard)
+    int nu = blockIdx.x, nr = 0;
+    Unit nt{};
+    auto advance = [&]() {  // next (unit, row) in the order every role walks
+      if (++nr > nt.hi) {
+        nu += gridDim.x;
+        if (nu < a.n_units) nt = unit_of(a, nu), nr = nt.lo;
+      }
+    };
+    uint4 vn0[8], vn1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vn0[i] = vn1[i] = make_uint4(0, 0, 0, 0);
+    if (nu < a.n_units) {
+      nt = unit_of(a, nu);
+      nr = nt.lo;
+      load_row(vn0, nt.f, nr);
+      advance();
+      if (nu < a.n_units) load_row(vn1, nt.f, nr);
+    }
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
       const Unit t = unit_of(a, u);
       for (int r = t.lo; r <= t.hi; ++r, ++g) {
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = vn0[i], vn0[i] = vn1[i];
+        // issue the loads of the row after next: they fly during two rows of waits and stores
+        if (nu < a.n_units) {
+          advance();
+          if (nu < a.n_units) load_row(vn1, nt.f, nr);
+        }
         const unsigned slot = g % kRing;
         if (g >= kRing) mbar_wait(empty(slot), ((g / kRing) - 1u) & 1u);
         if (active) {
-          uint4 v[8];
-          const __nv_bfloat16* src = a.x + (static_cast<size_t>(t.f) * a.c_in + cb * 8) * plane + static_cast<size_t>(r) * kCW + pb * 8;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            v[i] = (cb * 8 + i < a.c_in) ? __ldg(reinterpret_cast<const uint4*>(src + i * plane)) : make_uint4(0, 0, 0, 0);
           unsigned char* sl = ring_ptr + slot * kSlotBytes;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -241,48 +307,51 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> tensor-core (async proxy) reads
-        mbar_arrive(full(slot));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full(slot));  // hundreds of per-thread arrivals on one mbarrier cost ~1000 cycles per row
       }
     }
   } else {
-    // ---- epilogue: TMEM lanes 32 q .. 32 q + 31 = pixels of the row --------------------------------------------------
-    const int q = warp & 3;
+    // ---- epilogue: TMEM lanes 32 q .. 32 q + 31 = pixels of the row; the two warps of a quarter split the channels ------
+    const int q = warp & 3, half = (warp - 5) >> 2;
     const int x = q * 32 + lane;
+    float bias_r[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) bias_r[c] = s_bias[half * 32 + c];
     unsigned o = 0;
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
       const Unit t = unit_of(a, u);
-      float s1[kStatQuarters], s2[kStatQuarters];
-#pragma unroll
-      for (int k = 0; k < kStatQuarters; ++k) s1[k] = 0.f, s2[k] = 0.f;
+      float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};  // the two 16-channel quarters of this warp's 32 channels
       for (int y = t.y0; y < t.y1; ++y, ++o) {
-        const unsigned buf = o & 1u;
-        mbar_wait(tfull(buf), (o >> 1) & 1u);
+        const unsigned buf = o & (kAccBufs - 1);
+        mbar_wait(tfull(buf), (o / kAccBufs) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t r0[32], r1[32];
-        const uint32_t taddr = tacc + (static_cast<uint32_t>(q * 32) << 16) + buf * kCN;
-        tmem_ld32(taddr, r0);
-        tmem_ld32(taddr + 32, r1);
+        uint32_t r0[32];
+        tmem_ld32(tacc + (static_cast<uint32_t>(q * 32) << 16) + buf * kCN + half * 32, r0);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(tempty(buf));  // the accumulator is in registers: the next row but one may overwrite it
-        __nv_bfloat16* dst = a.y + (static_cast<size_t>(t.f) * kCN * a.H + y) * kCW + x;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(buf));  // the accumulator is in registers: the next row but one may overwrite it
+        // 2-byte stores, 64 contiguous bytes per warp instruction.  (Staging the tile in shared memory for 16-byte stores was
+        // measured and is SLOWER, 2.17 vs 1.56 ms: with N = 64 the products read 6 KB of shared memory per 48 cycles, i.e. they
+        // saturate its bandwidth, and every other shared-memory access -- the staging, even a bias read per channel -- is
+        // taken from them.  The bias therefore lives in registers.)
         const size_t cstride = static_cast<size_t>(a.H) * kCW;
+        __nv_bfloat16* dst = a.y + ((static_cast<size_t>(t.f) * kCN + half * 32) * a.H + y) * kCW + x;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float v0 = __uint_as_float(r0[c]) + s_bias[c], v1 = __uint_as_float(r1[c]) + s_bias[32 + c];
+          const float v0 = __uint_as_float(r0[c]) + bias_r[c];
           dst[c * cstride] = __float2bfloat16_rn(v0);
-          dst[(32 + c) * cstride] = __float2bfloat16_rn(v1);
           s1[c >> 4] += v0, s2[c >> 4] = fmaf(v0, v0, s2[c >> 4]);
-          s1[2 + (c >> 4)] += v1, s2[2 + (c >> 4)] = fmaf(v1, v1, s2[2 + (c >> 4)]);
         }
       }
       if (a.stats != nullptr) {
 #pragma unroll
-        for (int k = 0; k < kStatQuarters; ++k) {
+        for (int k = 0; k < 2; ++k) {
           const float t1 = warp_sum(s1[k]), t2 = warp_sum(s2[k]);
           if (lane == 0) {
-            atomicAdd(a.stats + (static_cast<size_t>(t.f) * kStatQuarters + k) * 2, t1);
-            atomicAdd(a.stats + (static_cast<size_t>(t.f) * kStatQuarters + k) * 2 + 1, t2);
+            atomicAdd(a.stats + (static_cast<size_t>(t.f) * kStatQuarters + half * 2 + k) * 2, t1);
+            atomicAdd(a.stats + (static_cast<size_t>(t.f) * kStatQuarters + half * 2 + k) * 2 + 1, t2);
           }
         }
       }
@@ -290,7 +359,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tacc) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tacc) : "memory");
 }
 
 // weight[c_out][c_in][3][3] fp32 -> wp[c_out][chunks * 64] bf16 with k = tap * CK + c (zero for c >= c_in and behind 9 CK)
@@ -343,26 +412,38 @@ struct NormArgs {
 template <typename T>
 __global__ void __launch_bounds__(256) group_norm_relu_kernel(const NormArgs a) {
   constexpr int VEC = Elem<T>::kVec;
+  __shared__ float s_sc[256], s_sh[256];  // scale / shift of the (at most 256) channels this block touches
   const int f = blockIdx.y;
   const size_t per_frame = static_cast<size_t>(a.C) * a.hw;
-  const size_t e = (static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x) * VEC;
-  if (e >= per_frame) return;
-  const int c = static_cast<int>(e / a.hw);  // hw % VEC == 0: the vector stays inside one channel
-  const int cpg = a.C / a.n_groups, g = c / cpg, spg = a.n_sub / a.n_groups;
-  double t1 = 0.0, t2 = 0.0;
-  for (int k = 0; k < spg; ++k) {
-    t1 += a.stats[(static_cast<size_t>(f) * a.n_sub + g * spg + k) * 2];
-    t2 += a.stats[(static_cast<size_t>(f) * a.n_sub + g * spg + k) * 2 + 1];
+  const size_t e0 = static_cast<size_t>(blockIdx.x) * 256 * VEC;
+  const int c_first = static_cast<int>(e0 / a.hw);
+  size_t e_last = e0 + 256 * VEC - 1;
+  e_last = e_last < per_frame ? e_last : per_frame - 1;
+  const int n_ch = static_cast<int>(e_last / a.hw) - c_first + 1;  // hw >= VEC: at most 256 channels
+  if (static_cast<int>(threadIdx.x) < n_ch) {
+    const int c = c_first + threadIdx.x;
+    const int cpg = a.C / a.n_groups, g = c / cpg, spg = a.n_sub / a.n_groups;
+    double t1 = 0.0, t2 = 0.0;
+    for (int k = 0; k < spg; ++k) {
+      t1 += a.stats[(static_cast<size_t>(f) * a.n_sub + g * spg + k) * 2];
+      t2 += a.stats[(static_cast<size_t>(f) * a.n_sub + g * spg + k) * 2 + 1];
+    }
+    const double n = static_cast<double>(cpg) * a.hw;
+    const double mean = t1 / n;
+    double var = t2 / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float sc = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps))) * a.gamma[c];
+    s_sc[threadIdx.x] = sc;
+    s_sh[threadIdx.x] = a.beta[c] - static_cast<float>(mean) * sc;
   }
-  const double n = static_cast<double>(cpg) * a.hw;
-  const double mean = t1 / n;
-  double var = t2 / n - mean * mean;
-  var = var < 0.0 ? 0.0 : var;
-  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
-  const float sc = rstd * a.gamma[c], sh = a.beta[c] - static_cast<float>(mean) * sc;
+  __syncthreads();
+  const size_t e = e0 + static_cast<size_t>(threadIdx.x) * VEC;
+  if (e >= per_frame) return;
+  const int ci = static_cast<int>(e / a.hw) - c_first;  // hw % VEC == 0: the vector stays inside one channel
+  const float sc = s_sc[ci], sh = s_sh[ci];
   const size_t off = static_cast<size_t>(f) * per_frame + e;
   float v[VEC];
-  Elem<T>::unpack(*reinterpret_cast<const uint4*>(static_cast<const T*>(a.x) + off), v);
+  Elem<T>::unpack(*reinterpret_cast<const uint4*>(static_cast<const T*>(a.x) + off), v);  // plain load: out may alias x
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     v[i] = fmaf(v[i], sc, sh);
@@ -370,7 +451,7 @@ __global__ void __launch_bounds__(256) group_norm_relu_kernel(const NormArgs a) 
   }
   if (a.residual != nullptr) {
     float rv[VEC];
-    Elem<T>::unpack(*reinterpret_cast<const uint4*>(static_cast<const T*>(a.residual) + off), rv);
+    Elem<T>::unpack(ld_stream_v4(static_cast<const T*>(a.residual) + off), rv);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) v[i] += rv[i];
   }

@@ -225,6 +225,47 @@ def training(dev, local_rank, B=16, min_seconds=1.0, seed=1234, ddp=False):
     return rec
 
 
+# ------------------------------------------------------------------------------------------------ section 8f rank 4
+def encoder(dev, frames=1024, min_seconds=1.0, seed=1234):
+    """Shared conv encoder slice: U-TAE's ``in_conv`` = ConvBlock([10, 64, 64], GroupNorm)
+    on ``frames`` packed valid frames of [10, 128, 128] (bf16), both convolutions on the tcgen05 implicit-GEMM kernel, and
+    the 64 -> 64 convolution alone against the measured dense bf16 tensor-core peak."""
+    from crop2seg_b200 import conv as cc
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    blk = c2s.ConvBlock([10, 64, 64], pad_value=0, norm="group").to(dev).eval()
+    x = torch.randn((frames, 10, 128, 128), device=dev, generator=gen).to(torch.bfloat16)
+    with torch.no_grad():
+        ms, steps, launches = timed(lambda: blk(x), dev, min_seconds)
+    world = _world()
+    flops = 2.0 * frames * 128 * 128 * 64 * (10 + 64) * 9
+    peaks = {}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        peaks = json.load(open(path))
+    tpeak = float(peaks.get("bf16_tflops", 1637.8))
+    rec = {"workload": "in_conv = ConvBlock([10,64,64], norm='group') on packed frames (utae.py:128-136)",
+           "value": world * frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "ms_per_step": ms, "steps": steps,
+           "timed_s": ms * steps * 1e-3, "frames_per_gpu": frames, "dtype": "bf16", "tflops": flops / ms * 1e-9,
+           "gpu_launches_per_step": launches,
+           "note": "two 3x3 reflect convolutions (tcgen05 implicit GEMM, raw bf16 output + GroupNorm sums) and two "
+                   "normalisation passes; forward only"}
+    x64 = torch.randn((frames, 64, 128, 128), device=dev, generator=gen).to(torch.bfloat16)
+    conv = blk.conv.conv[3]
+    ms2, steps2, _ = timed(lambda: cc.conv2d_reflect_forward(x64, conv.weight, conv.bias), dev, min_seconds)
+    f2 = 2.0 * frames * 128 * 128 * 64 * 64 * 9
+    rec["conv64"] = {"kernel": "conv3x3_reflect<tcgen05> 64 -> 64 at 128^2", "ms": ms2, "steps": steps2,
+                     "roofline": {"bound": "tensor", "achieved": f2 / ms2 * 1e-9, "peak": tpeak, "unit": "TFLOP/s",
+                                  "frac": f2 / ms2 * 1e-9 / tpeak,
+                                  "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if peaks else "fallback",
+                                  "note": "M 128 x N 64 x K 16 products read 6 KB of shared memory each: 48 cycles against "
+                                          "a 32-cycle tensor floor (tools/ubench/umma_rowshift.cu), i.e. at most 0.67 of "
+                                          "the nominal rate with 64 output channels"}}
+    del x, x64
+    torch.cuda.empty_cache()
+    return rec
+
+
 # ------------------------------------------------------------------------------------------------ configs[4]
 def tile(dev, placement="timeunet", B=64, tiles=1, seed=1234, with_edges=True):
     """Webapp-style full Sentinel-2 tile (BASELINE configs[4]): 10980^2 -> zero-pad to 11008^2 -> 86 x 86 = 7396 patches of

@@ -100,7 +100,81 @@ __global__ void __launch_bounds__(128, 1) test_kernel(const __nv_bfloat16* a, co
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tacc) : "memory");
 }
 
+
+// throughput: `reps` back-to-back K = 64 products (4 instructions each) from one thread, A start shifted by `shift` rows
+template <int N>
+__global__ void __launch_bounds__(128, 1) rate_kernel(int shift, int reps, long long* cycles) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_s;
+  const uint32_t base = (s32(smem_raw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (kRowsA * 128 + 256 * 128) / 16; i += 128) reinterpret_cast<uint4*>(smem_raw + (base - s32(smem_raw)))[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s32(&tmem_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tacc = tmem_s;
+  if (warp == 0) {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    if (pred) {
+      uint32_t idesc = 0;
+      idesc |= 1u << 4, idesc |= 1u << 7, idesc |= 1u << 10;
+      idesc |= static_cast<uint32_t>(N >> 3) << 17;
+      idesc |= static_cast<uint32_t>(kM >> 4) << 24;
+      const uint64_t da = desc_k_sw128(base + shift * 128, 0);
+      const uint64_t db = desc_k_sw128(base + kRowsA * 128, 0);
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tacc),
+                       "l"(da + 2 * k), "l"(db + 2 * k), "r"(idesc), "r"(1u)
+                       : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar)) : "memory");
+      uint32_t done;
+      do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(s32(&bar))
+                     : "memory");
+      } while (!done);
+      *cycles = clock64() - t0;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tacc) : "memory");
+}
+
+template <int N>
+void rate(int shift) {
+  long long* dc;
+  cudaMalloc(&dc, 8);
+  const int smem = kRowsA * 128 + 256 * 128 + 1024, reps = 2000;
+  cudaFuncSetAttribute(rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  rate_kernel<N><<<1, 128, smem>>>(shift, reps, dc);
+  cudaDeviceSynchronize();
+  long long c = 0;
+  cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+  printf("M 128 N %3d K 16, A start + %d rows: %.1f cycles per instruction (floor N/2 = %d) %s\n", N, shift, double(c) / (reps * 4), N / 2,
+         cudaGetErrorString(cudaGetLastError()));
+  cudaFree(dc);
+}
+
 int main() {
+  for (int sh = 0; sh <= 2; ++sh) rate<64>(sh), rate<128>(sh), rate<256>(sh);
+
   std::vector<__nv_bfloat16> ha(kRowsA * kK), hb(kN * kK);
   std::vector<float> fa(kRowsA * kK), fb(kN * kK);
   srand(3);
