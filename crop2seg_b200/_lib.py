@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 9
+C2S_ABI_VERSION = 10
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -106,6 +106,11 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("frames", "c_in", "c_out", "H", "W", "kernel", "stride", "padding", "dtype")]
 
 
+class ConvInputNorm(ctypes.Structure):
+    _fields_ = [("stats", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                ("n_groups", ctypes.c_int32), ("n_sub", ctypes.c_int32), ("relu", ctypes.c_int32), ("eps", ctypes.c_float)]
+
+
 class C2SError(RuntimeError):
     """A C-ABI call returned a non-zero status (message from ``c2s_last_error``)."""
 
@@ -198,7 +203,7 @@ def load() -> ctypes.CDLL:
         lib.c2s_conv2d_workspace_bytes.restype = sz
         lib.c2s_conv2d_workspace_bytes.argtypes = [ctypes.POINTER(ConvDesc)]
         lib.c2s_conv2d_forward.restype = i32
-        lib.c2s_conv2d_forward.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, sz, vp]
+        lib.c2s_conv2d_forward.argtypes = [ctypes.POINTER(ConvDesc), vp, ctypes.POINTER(ConvInputNorm), vp, vp, vp, vp, vp, sz, vp]
         lib.c2s_group_stats.restype = i32
         lib.c2s_group_stats.argtypes = [vp, i32, ctypes.c_int64, i32, ctypes.c_int64, i32, vp, vp]
         lib.c2s_group_norm_relu.restype = i32

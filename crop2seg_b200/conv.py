@@ -14,7 +14,9 @@ What runs where (``forward`` / ``smart_forward``, eval mode, CUDA tensors):
   ``csrc/c2s_conv.cu``).  Every other layer (4x4 / stride 2, the 64^2 ... 16^2 levels, 128 channels) calls
   ``torch.nn.functional.conv2d`` on a reflect-padded bf16 tensor -- a plain cuDNN library convolution, stated here and in
   DESIGN.md as NOT part of the hand-written path -- followed by ``c2s_group_stats``;
-* GroupNorm + ReLU (+ the residual of ``DownConvBlock``): ``c2s_group_norm_relu``, one element-wise pass, fp32 statistics.
+* GroupNorm + ReLU (+ the residual of ``DownConvBlock``): ``c2s_group_norm_relu``, one element-wise pass, fp32 statistics;
+  between two tensor-core stages of one ``ConvLayer`` the pass is skipped: the next convolution normalises its input on
+  the fly while it stages it (``c2s_conv_input_norm``).
 
 Training mode, other norms and the experimental conv types raise ``NotImplementedError``: the reference classes remain
 the training path.
@@ -53,9 +55,12 @@ def conv2d_supported(x: torch.Tensor, conv: nn.Conv2d) -> bool:
 
 
 def conv2d_reflect_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], *, kernel: int = 3,
-                           stride: int = 1, padding: int = 1, with_stats: bool = True):
+                           stride: int = 1, padding: int = 1, with_stats: bool = True, in_norm=None):
     """``c2s_conv2d_forward``: raw convolution output [frames, c_out, H, W] (bf16) and the GroupNorm sums
-    [frames, 4, 2] (float32; quarter-of-the-channels granularity) of its fp32 values."""
+    [frames, 4, 2] (float32; quarter-of-the-channels granularity) of its fp32 values.
+
+    ``in_norm = (stats, group_norm_module, relu)``: x is the RAW output of the previous stage and the kernel reads
+    ``relu(GroupNorm(x))`` on the fly (the previous stage's normalisation pass is skipped)."""
     _require_cuda(x, "x")
     x = x.contiguous()
     dev = x.device
@@ -67,11 +72,18 @@ def conv2d_reflect_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional
     bs = None if bias is None else bias.detach().to(device=dev, dtype=torch.float32).contiguous()
     y = torch.empty((n, c_out, h, w), dtype=x.dtype, device=dev)
     stats = torch.empty((n, 4, 2), dtype=torch.float32, device=dev) if with_stats else None
+    inn, keep = None, []
+    if in_norm is not None:
+        st, norm, relu = in_norm
+        keep = [st.contiguous(), norm.weight.detach().to(device=dev, dtype=torch.float32).contiguous(),
+                norm.bias.detach().to(device=dev, dtype=torch.float32).contiguous()]
+        inn = ctypes.byref(_lib.ConvInputNorm(stats=keep[0].data_ptr(), gamma=keep[1].data_ptr(), beta=keep[2].data_ptr(),
+                                              n_groups=norm.num_groups, n_sub=st.shape[1], relu=int(relu), eps=float(norm.eps)))
     lib = _lib.load()
     with torch.cuda.device(dev):
         ws_bytes = lib.c2s_conv2d_workspace_bytes(ctypes.byref(d))
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-        status = lib.c2s_conv2d_forward(ctypes.byref(d), x.data_ptr(), wt.data_ptr(), _ptr(bs), y.data_ptr(), _ptr(stats),
+        status = lib.c2s_conv2d_forward(ctypes.byref(d), x.data_ptr(), inn, wt.data_ptr(), _ptr(bs), y.data_ptr(), _ptr(stats),
                                         ws.data_ptr(), ws_bytes, _stream(dev))
     _lib.check(status, "c2s_conv2d_forward")
     return y, stats
@@ -145,19 +157,27 @@ class ConvLayer(nn.Module):
         dtype = input.dtype
         x = input.to(torch.bfloat16).contiguous()
         first = x
+        pending = None  # (raw, stats, norm, relu) of a stage whose normalisation pass has not run yet
         for n_stage, (ci, ni, relu) in enumerate(self._plan):
             conv, norm = self.conv[ci], self.conv[ni]
-            if conv2d_supported(x, conv):
-                raw, stats = conv2d_reflect_forward(x, conv.weight, conv.bias, kernel=conv.kernel_size[0],
-                                                    stride=conv.stride[0], padding=conv.padding[0])
+            last = n_stage == len(self._plan) - 1
+            src = pending[0] if pending is not None else x
+            if conv2d_supported(src, conv):
+                # the tensor-core kernel normalises its input on the fly: the previous stage's pass never touches memory
+                raw, stats = conv2d_reflect_forward(src, conv.weight, conv.bias, kernel=conv.kernel_size[0],
+                                                    stride=conv.stride[0], padding=conv.padding[0],
+                                                    in_norm=None if pending is None else pending[1:])
             else:  # library convolution (cuDNN through torch), see the module docstring
+                if pending is not None:
+                    x = group_norm_relu(pending[0], pending[1], pending[2], relu=pending[3], out=pending[0])
                 pad = conv.padding[0]
                 xp = F.pad(x, (pad, pad, pad, pad), mode=conv.padding_mode) if pad else x
                 raw = F.conv2d(xp, conv.weight.to(torch.bfloat16), None if conv.bias is None else conv.bias.to(torch.bfloat16),
                                stride=conv.stride)
                 stats = group_stats(raw, norm.num_groups)
-            last = n_stage == len(self._plan) - 1
-            x = group_norm_relu(raw, stats, norm, relu=relu, residual=first if (residual_last and last) else None, out=raw)
+            pending = (raw, stats, norm, relu)
+            if last:
+                x = group_norm_relu(raw, stats, norm, relu=relu, residual=first if residual_last else None, out=raw)
         return x.to(dtype)
 
 

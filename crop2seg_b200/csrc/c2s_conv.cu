@@ -45,6 +45,13 @@ struct ConvArgs {
   float* stats;              // [frames][4][2] sum, sum of squares per 16-channel quarter (accumulated), or nullptr
   const __nv_bfloat16* wp;   // [64][chunks * 64] prepared weights, k = tap * CK + c
   int frames, c_in, H, rows_per_unit, units_per_frame, n_units;
+  // optional normalisation of the INPUT on the fly: x is the raw output of the previous layer, the producers apply
+  // relu(GroupNorm(x)) while they transpose it (the previous layer's second pass never touches HBM)
+  const float* in_stats;     // [frames][in_sub][2] or nullptr
+  const float* in_gamma;
+  const float* in_beta;
+  int in_groups, in_sub, in_relu;
+  float in_eps;
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -120,7 +127,7 @@ __device__ __forceinline__ Unit unit_of(const ConvArgs& a, int u) {
   return t;
 }
 
-template <int CK>
+template <int CK, bool NORM>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvArgs a) {
   constexpr int KS = CK / 16;                      // k-steps (MMA instructions) per tap
   constexpr int NCHUNK = (9 * CK + 63) / 64;       // 64-wide K chunks of the resident weights
@@ -273,12 +280,50 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
       advance();
       if (nu < a.n_units) load_row(vn1, nt.f, nr);
     }
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc[i] = 1.f, sh[i] = 0.f;
+    int norm_f = -1;
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
       const Unit t = unit_of(a, u);
+      if (NORM && t.f != norm_f && active) {  // scale / shift of this thread's 8 channels in frame t.f
+        norm_f = t.f;
+        const int cpg = a.c_in / a.in_groups, spg = a.in_sub / a.in_groups;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = cb * 8 + i;
+          if (c >= a.c_in) continue;
+          const int grp = c / cpg;
+          double t1 = 0.0, t2 = 0.0;
+          for (int k = 0; k < spg; ++k) {
+            t1 += a.in_stats[(static_cast<size_t>(t.f) * a.in_sub + grp * spg + k) * 2];
+            t2 += a.in_stats[(static_cast<size_t>(t.f) * a.in_sub + grp * spg + k) * 2 + 1];
+          }
+          const double n = static_cast<double>(cpg) * a.H * kCW;
+          const double mean = t1 / n;
+          double var = t2 / n - mean * mean;
+          var = var < 0.0 ? 0.0 : var;
+          sc[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.in_eps))) * a.in_gamma[c];
+          sh[i] = a.in_beta[c] - static_cast<float>(mean) * sc[i];
+        }
+      }
       for (int r = t.lo; r <= t.hi; ++r, ++g) {
         uint4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = vn0[i], vn0[i] = vn1[i];
+        if (NORM) {  // the same arithmetic as group_norm_relu_kernel: fma in fp32, ReLU, round to bf16
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float f[8];
+            Elem<__nv_bfloat16>::unpack(v[i], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[e] = fmaf(f[e], sc[i], sh[i]);
+              if (a.in_relu) f[e] = fmaxf(f[e], 0.f);
+            }
+            v[i] = Elem<__nv_bfloat16>::pack(f);
+          }
+        }
         // issue the loads of the row after next: they fly during two rows of waits and stores
         if (nu < a.n_units) {
           advance();
@@ -477,8 +522,8 @@ size_t c2s_conv2d_workspace_bytes(const c2s_conv_desc* d) {
   return static_cast<size_t>(c2s::kCN) * c2s::conv_chunks(c2s::conv_ck(d->c_in)) * 64 * sizeof(__nv_bfloat16);
 }
 
-int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const float* weight, const float* bias, void* y, float* stats,
-                       void* workspace, size_t workspace_bytes, void* stream_ptr) {
+int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_input_norm* in_norm, const float* weight,
+                       const float* bias, void* y, float* stats, void* workspace, size_t workspace_bytes, void* stream_ptr) {
   using namespace c2s;
   C2S_CHECK_ARG(desc != nullptr && x != nullptr && weight != nullptr && y != nullptr, "c2s_conv2d_forward: NULL argument");
   const c2s_conv_desc& d = *desc;
@@ -504,6 +549,14 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const float* we
   ConvArgs a{};
   a.x = static_cast<const __nv_bfloat16*>(x), a.y = static_cast<__nv_bfloat16*>(y), a.bias = bias, a.stats = stats, a.wp = wp;
   a.frames = d.frames, a.c_in = d.c_in, a.H = d.H;
+  if (in_norm != nullptr) {
+    C2S_CHECK_ARG(in_norm->stats != nullptr && in_norm->gamma != nullptr && in_norm->beta != nullptr && in_norm->n_groups > 0 &&
+                      d.c_in % in_norm->n_groups == 0 && in_norm->n_sub > 0 && in_norm->n_sub % in_norm->n_groups == 0,
+                  "c2s_conv2d_forward: bad input normalisation (groups=%d, sub-groups=%d, c_in=%d)", in_norm->n_groups,
+                  in_norm->n_sub, d.c_in);
+    a.in_stats = in_norm->stats, a.in_gamma = in_norm->gamma, a.in_beta = in_norm->beta;
+    a.in_groups = in_norm->n_groups, a.in_sub = in_norm->n_sub, a.in_relu = in_norm->relu, a.in_eps = in_norm->eps;
+  }
   // whole frames per unit when there are enough of them to balance the SMs, bands of rows otherwise
   a.rows_per_unit = d.H;
   while (a.rows_per_unit > 16 && static_cast<long long>(d.frames) * ceil_div(d.H, a.rows_per_unit) < 4LL * sms) a.rows_per_unit /= 2;
@@ -511,12 +564,16 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const float* we
   a.n_units = d.frames * a.units_per_frame;
   const int grid = a.n_units < sms ? a.n_units : sms;
   const size_t smem = static_cast<size_t>(chunks) * 8192 + static_cast<size_t>(kRing) * kSlotBytes + 1024;
-  if (ck == 16) {
-    C2S_SMEM_ATTR(conv3x3_tc_kernel<16>, smem);
-    conv3x3_tc_kernel<16><<<grid, kConvThreads, smem, stream>>>(a);
+  if (ck == 16) {  // the first layer of a block reads the model input: no normalisation on the fly
+    C2S_CHECK_ARG(in_norm == nullptr, "c2s_conv2d_forward: input normalisation needs c_in = 64");
+    C2S_SMEM_ATTR((conv3x3_tc_kernel<16, false>), smem);
+    conv3x3_tc_kernel<16, false><<<grid, kConvThreads, smem, stream>>>(a);
+  } else if (in_norm != nullptr) {
+    C2S_SMEM_ATTR((conv3x3_tc_kernel<64, true>), smem);
+    conv3x3_tc_kernel<64, true><<<grid, kConvThreads, smem, stream>>>(a);
   } else {
-    C2S_SMEM_ATTR(conv3x3_tc_kernel<64>, smem);
-    conv3x3_tc_kernel<64><<<grid, kConvThreads, smem, stream>>>(a);
+    C2S_SMEM_ATTR((conv3x3_tc_kernel<64, false>), smem);
+    conv3x3_tc_kernel<64, false><<<grid, kConvThreads, smem, stream>>>(a);
   }
   C2S_LAUNCH_CHECK("conv3x3_reflect<tcgen05>");
   return C2S_OK;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 9
+#define C2S_ABI_VERSION 10
 
 enum c2s_status {
   C2S_OK = 0,
@@ -397,13 +397,24 @@ typedef struct c2s_conv_desc {
 int c2s_conv2d_supported(const c2s_conv_desc* desc);
 size_t c2s_conv2d_workspace_bytes(const c2s_conv_desc* desc); /* prepared bf16 weights */
 
-/* y[f, o, y, x] = bias[o] + sum_{c, ky, kx} weight[o, c, ky, kx] * x[f, c, reflect(y + ky - 1), reflect(x + kx - 1)]
- *   x      : [frames, c_in, H, W] bf16          weight : float32 [c_out, c_in, 3, 3] (nn.Conv2d.weight), bias float32 [c_out] | NULL
+/* Optional normalisation of the convolution's INPUT on the fly: x is then the RAW output of the previous ConvLayer stage
+ * and the kernel reads relu(GroupNorm(x)) -- the previous stage's normalisation pass never touches memory. */
+typedef struct c2s_conv_input_norm {
+  const float* stats;   /* [frames][n_sub][2] sums of the previous stage (c2s_conv2d_forward: n_sub = 4)       */
+  const float* gamma;   /* nn.GroupNorm.weight [c_in]                                                          */
+  const float* beta;    /* nn.GroupNorm.bias   [c_in]                                                          */
+  int32_t n_groups, n_sub, relu;
+  float eps;
+} c2s_conv_input_norm;
+
+/* y[f, o, y, x] = bias[o] + sum_{c, ky, kx} weight[o, c, ky, kx] * x'[f, c, reflect(y + ky - 1), reflect(x + kx - 1)]
+ *   x      : [frames, c_in, H, W] bf16;  x' = x, or relu(GroupNorm(x)) rounded to bf16 when in_norm is given
+ *   weight : float32 [c_out, c_in, 3, 3] (nn.Conv2d.weight), bias float32 [c_out] | NULL
  *   y      : [frames, c_out, H, W] bf16, the RAW convolution output (GroupNorm needs the whole frame first)
  *   stats  : float32 [frames][4][2] = (sum, sum of squares) of the fp32 outputs per frame and quarter of the channels
- *            (written, not accumulated), for c2s_group_norm_relu with n_sub = 4; or NULL */
-int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const float* weight, const float* bias, void* y,
-                       float* stats, void* workspace, size_t workspace_bytes, void* stream);
+ *            (written, not accumulated), for c2s_group_norm_relu / c2s_conv_input_norm with n_sub = 4; or NULL */
+int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_input_norm* in_norm, const float* weight,
+                       const float* bias, void* y, float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
 /* stats[f][g] = (sum, sum of squares) over the channels of group g and the hw pixels of frame f of x[frames, C, hw]. */
 int c2s_group_stats(const void* x, int32_t dtype, int64_t frames, int32_t channels, int64_t hw, int32_t n_groups,

@@ -140,5 +140,31 @@ def test_in_conv_runs_on_the_tensor_core_kernel():
     with torch.no_grad():
         blk(x)
     torch.cuda.synchronize()
-    # per layer: weight preparation, convolution, normalisation pass (the statistics come out of the convolution)
-    assert c2s.ops._lib.launch_count() == 6
+    # weight preparation + convolution per layer, ONE normalisation pass: the second convolution normalises its input on the
+    # fly (c2s_conv_input_norm), the statistics come out of the convolutions
+    assert c2s.ops._lib.launch_count() == 5
+
+
+@pytest.mark.gpu
+def test_input_normalisation_on_the_fly_equals_the_separate_pass():
+    """conv2(relu(GroupNorm(raw1))) with the normalisation inside the second convolution's producers against the same with
+    c2s_group_norm_relu in between: the arithmetic is the same (fp32 fma, ReLU, round to bf16), so are the bits."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    blk = c2s.ConvBlock([10, 64, 64], pad_value=0, norm="group").cuda().eval()
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, torch.nn.GroupNorm):
+                m.weight.copy_(1 + 0.3 * torch.randn(64, device="cuda", generator=g))
+                m.bias.copy_(0.2 * torch.randn(64, device="cuda", generator=g))
+    x = torch.randn((3, 10, 21, 128), device="cuda", generator=g).to(torch.bfloat16)
+    seq = blk.conv.conv
+    with torch.no_grad():
+        fused = blk(x)
+        raw1, st1 = c2s_conv.conv2d_reflect_forward(x, seq[0].weight, seq[0].bias)
+        a1 = c2s_conv.group_norm_relu(raw1, st1, seq[1], relu=True)
+        raw2, st2 = c2s_conv.conv2d_reflect_forward(a1, seq[3].weight, seq[3].bias)
+        ref = c2s_conv.group_norm_relu(raw2, st2, seq[4], relu=True)
+    # the GroupNorm sums are accumulated with float atomics (order-dependent last bits): compare within bf16 rounding
+    assert _rel(fused.float().cpu().numpy(), ref.float().cpu().numpy()) < 8e-3
+    raw2f, _ = c2s_conv.conv2d_reflect_forward(raw1, seq[3].weight, seq[3].bias, in_norm=(st1, seq[1], True))
+    assert torch.equal(raw2f, raw2)  # same statistics tensor in both paths: bit-exact
