@@ -30,9 +30,9 @@
 namespace c2s {
 namespace {
 
-constexpr int kCW = 128;             // image width served by the tensor-core kernel = UMMA M
 constexpr int kCN = 64;              // output channels = UMMA N
-constexpr int kSlotBytes = 17408;    // 130 pixel rows x 128 B, rounded up to the 1024-byte swizzle atom
+// one ring slot = one image row [W + 2 pixels][128 B], rounded up to the 1024-byte swizzle atom (W = 128: 17408, W = 64: 9216)
+__host__ __device__ constexpr int slot_bytes(int w) { return ((w + 2) * 128 + 1023) / 1024 * 1024; }
 constexpr int kRing = 8;             // input rows in flight
 constexpr int kAccBufs = 4;          // TMEM accumulators (64 columns each)
 constexpr int kConvThreads = 416;    // warp 0: MMA issuer, warps 1-4: producers, warps 5-12: epilogue (2 per TMEM lane quarter)
@@ -127,8 +127,12 @@ __device__ __forceinline__ Unit unit_of(const ConvArgs& a, int u) {
   return t;
 }
 
-template <int CK, bool NORM>
+// W = image width = UMMA M: 128 (one accumulator row per TMEM lane) or 64 (an M = 64 accumulator lives in lanes 0-15 of every
+// 32-lane quarter, tools/ubench/umma_rowshift.cu)
+template <int CK, bool NORM, int W>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvArgs a) {
+  constexpr int kCW = W;
+  constexpr int kSlotBytes = slot_bytes(W);
   constexpr int KS = CK / 16;                      // k-steps (MMA instructions) per tap
   constexpr int NCHUNK = (9 * CK + 63) / 64;       // 64-wide K chunks of the resident weights
   constexpr int CB = CK / 8;                       // 8-channel blocks per pixel row
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
             const int row = pb * 8 + j + 1;
             *reinterpret_cast<uint4*>(sl + row * 128 + ((cb ^ (row & 7)) << 4)) = w;
             if (pb == 0 && j == 1) *reinterpret_cast<uint4*>(sl + ((cb ^ 0) << 4)) = w;                       // pixel -1 = pixel 1
-            if (pb == kCW / 8 - 1 && j == 6) *reinterpret_cast<uint4*>(sl + 129 * 128 + ((cb ^ (129 & 7)) << 4)) = w;  // pixel 128 = pixel 126
+            if (pb == kCW / 8 - 1 && j == 6) *reinterpret_cast<uint4*>(sl + (kCW + 1) * 128 + ((cb ^ ((kCW + 1) & 7)) << 4)) = w;  // pixel W = pixel W - 2
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> tensor-core (async proxy) reads
@@ -359,7 +363,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
   } else {
     // ---- epilogue: TMEM lanes 32 q .. 32 q + 31 = pixels of the row; the two warps of a quarter split the channels ------
     const int q = warp & 3, half = (warp - 5) >> 2;
-    const int x = q * 32 + lane;
+    const bool valid = kCW == 128 || lane < 16;                    // M = 64: rows 16 q .. 16 q + 15 in lanes 0-15
+    const int x = kCW == 128 ? q * 32 + lane : q * 16 + (lane & 15);
     float bias_r[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) bias_r[c] = s_bias[half * 32 + c];
@@ -385,8 +390,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
         __nv_bfloat16* dst = a.y + ((static_cast<size_t>(t.f) * kCN + half * 32) * a.H + y) * kCW + x;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float v0 = __uint_as_float(r0[c]) + bias_r[c];
-          dst[c * cstride] = __float2bfloat16_rn(v0);
+          const float v0 = valid ? __uint_as_float(r0[c]) + bias_r[c] : 0.f;
+          if (valid) dst[c * cstride] = __float2bfloat16_rn(v0);
           s1[c >> 4] += v0, s2[c >> 4] = fmaf(v0, v0, s2[c >> 4]);
         }
       }
@@ -513,7 +518,7 @@ extern "C" {
 
 int c2s_conv2d_supported(const c2s_conv_desc* d) {
   if (d == nullptr) return 0;
-  return d->kernel == 3 && d->stride == 1 && d->padding == 1 && d->W == c2s::kCW && d->H >= 2 && d->c_out == c2s::kCN &&
+  return d->kernel == 3 && d->stride == 1 && d->padding == 1 && (d->W == 128 || d->W == 64) && d->H >= 2 && d->c_out == c2s::kCN &&
          (d->c_in <= 16 || d->c_in == 64) && d->c_in >= 1 && d->dtype == C2S_BF16 && d->frames > 0;
 }
 
@@ -528,7 +533,7 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_
   C2S_CHECK_ARG(desc != nullptr && x != nullptr && weight != nullptr && y != nullptr, "c2s_conv2d_forward: NULL argument");
   const c2s_conv_desc& d = *desc;
   if (!c2s_conv2d_supported(desc))
-    C2S_UNSUPPORTED("c2s_conv2d_forward: serves 3x3 / stride 1 / reflect padding 1, W = 128, c_out = 64, c_in <= 16 or 64, bf16 "
+    C2S_UNSUPPORTED("c2s_conv2d_forward: serves 3x3 / stride 1 / reflect padding 1, W = 128 or 64, c_out = 64, c_in <= 16 or 64, bf16 "
                     "(got k=%d s=%d p=%d W=%d c_in=%d c_out=%d dtype=%d)", d.kernel, d.stride, d.padding, d.W, d.c_in, d.c_out,
                     d.dtype);
   C2S_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0,
@@ -563,18 +568,24 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_
   a.units_per_frame = ceil_div(d.H, a.rows_per_unit);
   a.n_units = d.frames * a.units_per_frame;
   const int grid = a.n_units < sms ? a.n_units : sms;
-  const size_t smem = static_cast<size_t>(chunks) * 8192 + static_cast<size_t>(kRing) * kSlotBytes + 1024;
-  if (ck == 16) {  // the first layer of a block reads the model input: no normalisation on the fly
+  const size_t smem = static_cast<size_t>(chunks) * 8192 + static_cast<size_t>(kRing) * slot_bytes(d.W) + 1024;
+  if (ck == 16)  // the first layer of a block reads the model input: no normalisation on the fly
     C2S_CHECK_ARG(in_norm == nullptr, "c2s_conv2d_forward: input normalisation needs c_in = 64");
-    C2S_SMEM_ATTR((conv3x3_tc_kernel<16, false>), smem);
-    conv3x3_tc_kernel<16, false><<<grid, kConvThreads, smem, stream>>>(a);
-  } else if (in_norm != nullptr) {
-    C2S_SMEM_ATTR((conv3x3_tc_kernel<64, true>), smem);
-    conv3x3_tc_kernel<64, true><<<grid, kConvThreads, smem, stream>>>(a);
+#define C2S_CONV_LAUNCH(CK_, NORM_, W_)                                                   \
+  do {                                                                                    \
+    C2S_SMEM_ATTR((conv3x3_tc_kernel<CK_, NORM_, W_>), smem);                             \
+    conv3x3_tc_kernel<CK_, NORM_, W_><<<grid, kConvThreads, smem, stream>>>(a);           \
+  } while (0)
+  if (d.W == 128) {
+    if (ck == 16) C2S_CONV_LAUNCH(16, false, 128);
+    else if (in_norm != nullptr) C2S_CONV_LAUNCH(64, true, 128);
+    else C2S_CONV_LAUNCH(64, false, 128);
   } else {
-    C2S_SMEM_ATTR((conv3x3_tc_kernel<64, false>), smem);
-    conv3x3_tc_kernel<64, false><<<grid, kConvThreads, smem, stream>>>(a);
+    if (ck == 16) C2S_CONV_LAUNCH(16, false, 64);
+    else if (in_norm != nullptr) C2S_CONV_LAUNCH(64, true, 64);
+    else C2S_CONV_LAUNCH(64, false, 64);
   }
+#undef C2S_CONV_LAUNCH
   C2S_LAUNCH_CHECK("conv3x3_reflect<tcgen05>");
   return C2S_OK;
 }

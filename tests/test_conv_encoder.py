@@ -71,10 +71,12 @@ def _torch_conv(x, w, b):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("frames,c_in,h", [(3, 64, 12), (2, 10, 7), (1, 64, 2), (5, 3, 33), (150, 64, 16), (20, 64, 128)])
-def test_tensor_core_convolution_matches_torch(frames, c_in, h):
+@pytest.mark.parametrize("frames,c_in,h,w", [(3, 64, 12, 128), (2, 10, 7, 128), (1, 64, 2, 128), (5, 3, 33, 128),
+                                             (150, 64, 16, 128), (20, 64, 128, 128),
+                                             (3, 64, 64, 64), (7, 64, 5, 64), (2, 10, 9, 64), (300, 64, 64, 64)])
+def test_tensor_core_convolution_matches_torch(frames, c_in, h, w):
     g = torch.Generator(device="cuda").manual_seed(frames * 131 + c_in)
-    x = torch.randn((frames, c_in, h, 128), device="cuda", generator=g).to(torch.bfloat16)
+    x = torch.randn((frames, c_in, h, w), device="cuda", generator=g).to(torch.bfloat16)
     w = torch.randn((64, c_in, 3, 3), device="cuda", generator=g) * (1.0 / (3.0 * c_in ** 0.5))
     b = torch.randn(64, device="cuda", generator=g) * 0.1
     conv = torch.nn.Conv2d(c_in, 64, 3, padding=1, padding_mode="reflect")

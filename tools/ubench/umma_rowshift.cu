@@ -172,7 +172,86 @@ void rate(int shift) {
   cudaFree(dc);
 }
 
+// Where do the 64 rows of an M = 64 accumulator live in tensor memory?  D[m][n] = m + 1 for all n; every lane is dumped.
+__global__ void __launch_bounds__(128, 1) m64_kernel(float* d) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_s;
+  const uint32_t base = (s32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* sm = smem_raw + (base - s32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (64 * 128 + 64 * 128) / 2; i += 128) reinterpret_cast<uint16_t*>(sm)[i] = 0;
+  __syncthreads();
+  if (tid < 64) {  // A[m][k = 0] = m + 1 (bf16 exact up to 256), B[n][k = 0] = 1; logical chunk 0 sits at chunk (r & 7)
+    reinterpret_cast<__nv_bfloat16*>(sm + tid * 128 + ((0 ^ (tid & 7)) << 4))[0] = __float2bfloat16(float(tid + 1));
+    reinterpret_cast<__nv_bfloat16*>(sm + 64 * 128 + tid * 128 + ((0 ^ (tid & 7)) << 4))[0] = __float2bfloat16(1.f);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(s32(&tmem_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tacc = tmem_s;
+  if (tid == 0) {
+    uint32_t idesc = 0;
+    idesc |= 1u << 4, idesc |= 1u << 7, idesc |= 1u << 10;
+    idesc |= static_cast<uint32_t>(64 >> 3) << 17;
+    idesc |= static_cast<uint32_t>(64 >> 4) << 24;
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tacc),
+                 "l"(desc_k_sw128(base, 0)), "l"(desc_k_sw128(base + 64 * 128, 0)), "r"(idesc), "r"(0u)
+                 : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar)) : "memory");
+  }
+  uint32_t done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(s32(&bar))
+                 : "memory");
+  } while (!done);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(tacc + (static_cast<uint32_t>(warp * 32) << 16)));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  d[tid] = __uint_as_float(r[0]);
+  d[128 + tid] = __uint_as_float(r[5]);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tacc) : "memory");
+}
+
+void m64_layout() {
+  float* dd;
+  cudaMalloc(&dd, 256 * 4);
+  cudaMemset(dd, 0, 256 * 4);
+  const int smem = 2 * 64 * 128 + 1024;
+  m64_kernel<<<1, 128, smem>>>(dd);
+  cudaDeviceSynchronize();
+  float h[256];
+  cudaMemcpy(h, dd, sizeof(h), cudaMemcpyDeviceToHost);
+  printf("M = 64 accumulator: value (= row + 1) seen by TMEM lane 0..127, column 0 [%s]\n", cudaGetErrorString(cudaGetLastError()));
+  for (int l = 0; l < 128; ++l) printf("%g%s", h[l], (l & 31) == 31 ? "\n" : " ");
+  printf("column 5:\n");
+  for (int l = 0; l < 128; ++l) printf("%g%s", h[128 + l], (l & 31) == 31 ? "\n" : " ");
+  cudaFree(dd);
+}
+
 int main() {
+  m64_layout();
   for (int sh = 0; sh <= 2; ++sh) rate<64>(sh), rate<128>(sh), rate<256>(sh);
 
   std::vector<__nv_bfloat16> ha(kRowsA * kK), hb(kN * kK);
