@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 10
+C2S_ABI_VERSION = 11
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -19,7 +19,7 @@ AGG_ATT_GROUP, AGG_ATT_MEAN, AGG_MEAN = 0, 1, 2
 PE_NONE, PE_SINUSOID, PE_SINUSOID_LINEAR, PE_DOY_TABLE = 0, 1, 2, 3
 LTAE_ATTN_ONLY, LTAE_SKIP_ATTN_STORE, LTAE_ZERO_PADDED, LTAE_BN_BATCH_STATS, LTAE_REUSE_FOLDED = 1, 2, 4, 8, 16
 # enum c2s_option / c2s_ltae_kernel (kernel-selection switches for parity tests and A/B measurements)
-OPT_LTAE_KERNEL, OPT_AGG_KERNEL, OPT_AGG_TAPS = 0, 1, 2
+OPT_LTAE_KERNEL, OPT_AGG_KERNEL, OPT_AGG_TAPS, OPT_LTAE_BWD_KERNEL = 0, 1, 2, 3
 LTAE_KERNEL_AUTO, LTAE_KERNEL_GENERAL, LTAE_KERNEL_SLAB, LTAE_KERNEL_TEAM = 0, 1, 2, 3
 
 EXPORTS = (

@@ -12,10 +12,10 @@ thread_local char g_error[512] = "";
 char g_kernel[128] = "";
 char g_ltae_kernel[128] = "";
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_options[3] = {{0}, {0}, {0}};
+std::atomic<int> g_options[4] = {{0}, {0}, {0}, {0}};
 }  // namespace
 
-int option(int which) { return (which >= 0 && which < 3) ? g_options[which].load(std::memory_order_relaxed) : 0; }
+int option(int which) { return (which >= 0 && which < 4) ? g_options[which].load(std::memory_order_relaxed) : 0; }
 
 // cudaFuncSetAttribute is a per-device setting: `done` holds one flag per device ordinal for one kernel.
 int set_max_dynamic_smem(const void* func, int bytes, std::atomic<unsigned long long>* done) {
@@ -87,8 +87,8 @@ int64_t c2s_launch_count(void) { return c2s::g_launches.load(); }
 void c2s_reset_launch_count(void) { c2s::g_launches.store(0); }
 
 int c2s_set_option(int option, int value) {
-  const int max_value[3] = {C2S_LTAE_KERNEL_TEAM, 1, 1};
-  if (option < 0 || option >= 3 || value < 0 || value > max_value[option]) {
+  const int max_value[4] = {C2S_LTAE_KERNEL_TEAM, 1, 1, 1};
+  if (option < 0 || option >= 4 || value < 0 || value > max_value[option]) {
     c2s::set_error("c2s_set_option: unknown option %d / value %d", option, value);
     return C2S_ERR_BAD_ARGUMENT;
   }
@@ -96,7 +96,7 @@ int c2s_set_option(int option, int value) {
   return C2S_OK;
 }
 
-int c2s_get_option(int option) { return (option >= 0 && option < 3) ? c2s::g_options[option].load() : -1; }
+int c2s_get_option(int option) { return (option >= 0 && option < 4) ? c2s::g_options[option].load() : -1; }
 
 const char* c2s_last_kernel(void) { return c2s::g_kernel; }
 const char* c2s_last_ltae_kernel(void) { return c2s::g_ltae_kernel; }

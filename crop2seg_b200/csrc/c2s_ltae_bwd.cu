@@ -21,7 +21,7 @@
 // One CTA = 8 consecutive pixels of one sample, fp32 math on the CUDA cores, fp32 or bf16 features (the general
 // counterpart of ltae_forward_kernel; the training placements have N = B*256 pixel rows, where this is far from any
 // hardware limit).  x is swept five times by the same CTA; all sweeps but the first hit L2.
-#include "c2s_ltae_prep.cuh"
+#include "c2s_ltae_fa.cuh"
 
 namespace c2s {
 namespace {
@@ -673,6 +673,20 @@ int c2s_ltae_backward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const 
   if (status != C2S_OK) return status;
 
   const int hw = d.H * d.W;
+  if (option(C2S_OPT_LTAE_BWD_KERNEL) == 0 && ltae_bwd_tc_eligible(d, x, io)) {  // bf16 shipped shapes: tensor-core kernel
+    BwdTcArgs t{};
+    t.x = static_cast<const __nv_bfloat16*>(x);
+    t.g_o = io.grad_o, t.g_attn = io.grad_attn;
+    t.u = ws + lay.u, t.cpos = ws + lay.cpos, t.wct = ws + lay.wct, t.wb = ws + lay.wb;
+    t.pe = d.pe_mode != C2S_PE_NONE ? ws + lay.pe : nullptr;
+    t.gamma = p.in_norm_weight, t.beta = p.in_norm_bias;
+    t.pad = pad_mask, t.attn_keep = p.attn_keep, t.attn_keep_scale = d.attn_keep_scale;
+    t.g_u = io.grad_u, t.g_cpos = io.grad_cpos, t.g_gamma = io.grad_gamma, t.g_beta = io.grad_beta;
+    t.zn_rows = io.zn_rows, t.sa_rows = io.sa_rows;
+    t.B = d.B, t.T = d.T, t.hw = hw;
+    t.gn_eps = d.gn_eps;
+    return ltae_bwd_tc_launch(d, t, io.grad_x, stream);
+  }
   BwdArgs a{};
   a.x = x, a.pad = pad_mask, a.g_o = io.grad_o, a.g_attn = io.grad_attn;
   a.u = ws + lay.u, a.cpos = ws + lay.cpos, a.wct = ws + lay.wct, a.bc = p.inconv_bias;

@@ -183,6 +183,33 @@ __device__ __forceinline__ float ex2(float v) {
 
 }  // namespace
 
+// c2s_ltae_bwd_tc.cu: stage A of the backward on the tensor cores
+struct BwdTcArgs {
+  const __nv_bfloat16* x;
+  const float* g_o;     // [N][256]
+  const float* g_attn;  // [16][B][T][hw] or nullptr
+  const float* u;       // [C][16]  (in_norm.weight folded in)
+  const float* cpos;    // [B][T][16]
+  const float* wct;     // [C][256]
+  const float* wb;      // [256]  bc + Wc beta
+  const float* pe;      // [B][T][256] or nullptr (the 16 columns of a head repeat)
+  const float* gamma;
+  const float* beta;
+  const uint8_t* pad;
+  const uint8_t* attn_keep;
+  float attn_keep_scale;
+  float* g_u;
+  float* g_cpos;
+  float* g_gamma;
+  float* g_beta;
+  float* zn_rows;
+  float* sa_rows;
+  int B, T, hw, tiles_per_b, n_tiles;
+  float gn_eps;
+};
+bool ltae_bwd_tc_eligible(const c2s_ltae_desc& d, const void* x, const c2s_ltae_bwd_io& io);
+int ltae_bwd_tc_launch(const c2s_ltae_desc& d, const BwdTcArgs& a, void* grad_x, cudaStream_t stream);
+
 // c2s_ltae_team.cu
 bool ltae_team_eligible(int C, const FaArgs& a);
 int ltae_team_launch(int C, const CUtensorMap& map16, const CUtensorMap& map4, const CUtensorMap& map1, const FaArgs& a,

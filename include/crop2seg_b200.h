@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 10
+#define C2S_ABI_VERSION 11
 
 enum c2s_status {
   C2S_OK = 0,
@@ -438,7 +438,8 @@ void c2s_reset_launch_count(void);
 enum c2s_option {
   C2S_OPT_LTAE_KERNEL = 0, /* enum c2s_ltae_kernel: which kernel serves c2s_ltae_forward                       */
   C2S_OPT_AGG_KERNEL = 1,  /* 0 = automatic, 1 = register-streaming aggregator kernels (no bulk-copy pipeline) */
-  C2S_OPT_AGG_TAPS = 2     /* 0 = automatic, 1 = bilinear taps read from global memory (no staged rows)        */
+  C2S_OPT_AGG_TAPS = 2,    /* 0 = automatic, 1 = bilinear taps read from global memory (no staged rows)        */
+  C2S_OPT_LTAE_BWD_KERNEL = 3 /* 0 = automatic (tensor-core kernel where eligible), 1 = fp32 CUDA-core kernel     */
 };
 enum c2s_ltae_kernel {
   C2S_LTAE_KERNEL_AUTO = 0,

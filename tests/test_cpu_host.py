@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(LIB_PATH)
     for sym in declared:
         assert hasattr(raw, sym), sym
-    assert lib.c2s_abi_version() == _lib.C2S_ABI_VERSION == 10
+    assert lib.c2s_abi_version() == _lib.C2S_ABI_VERSION == 11
 
 
 def test_header_compiles_as_plain_c(tmp_path):

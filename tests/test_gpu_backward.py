@@ -271,3 +271,79 @@ def test_encoder_without_inconv_raises_in_backward():
     out, attn = m(to_dev(x).requires_grad_(True), batch_positions=to_dev(pos), pad_mask=to_dev(pad))  # forward is served
     with pytest.raises(_lib.C2SError, match="no torch fallback"):
         out.sum().backward()
+
+
+@pytest.mark.parametrize("c_in,variant,lengths", [
+    (128, "sinusoid", [61, 27, 5]), (64, "sinusoid", [61, 33, 0]), (128, "doy", [40, 17, 40]), (64, "abs_rel", [13, 13, 2]),
+    (128, "no_pe", [61, 61, 61]), (64, "sinusoid_T64", [64, 64, 1]), (128, "sinusoid", [48, 30, 1]),
+    (128, "sinusoid_wide", [61, 40, 27]), (64, "sinusoid_wide", [33, 61, 27, 50])])
+def test_ltae_tensor_core_backward_matches_the_general_kernel_and_the_oracle(c_in, variant, lengths):
+    """Stage A on the tensor cores (``ltae_backward<tc,C=..>``: bf16 features, shipped head layout) against the fp32
+    CUDA-core kernel on the same call (every output of ``c2s_ltae_backward``) and, through the module in training mode
+    with an injected dropout realisation, against autograd of the torch-CPU oracle: ragged series up to T = 61 / 64,
+    an all-padded series, every positional variant the kernel serves."""
+    extra = {"sinusoid": {}, "sinusoid_T64": {}, "sinusoid_wide": {}, "doy": dict(use_doy=True),
+             "abs_rel": dict(use_abs_rel_enc=True), "no_pe": dict(positional_encoding=False)}[variant]
+    kw = dict(in_channels=c_in, n_head=16, d_k=4, mlp=[256, 64], d_model=256, **extra)
+    m, rng = _ltae(kw, 7 + c_in + len(variant))
+    m.train()
+    m.assume_zero_padded = True
+    # "wide": more pixel tiles (192 / 256) than SMs, so the persistent CTAs walk over several tiles
+    b, t, (h, w) = len(lengths), max(lengths), ((32, 16) if variant == "sinusoid_wide" else (4, 4))
+    x, pos, pad = synth_inputs(rng, b, t, c_in, h, w, lengths, doy=variant == "doy", abs_rel=variant == "abs_rel")
+    x = bf16_round(x + 0.3 * rng.standard_normal(x.shape).astype(np.float32) * (~pad)[:, :, None, None, None])
+    pos = None if variant == "no_pe" else pos
+    attn_keep = (rng.uniform(size=(16, b, t, h, w)) >= 0.1).astype(np.uint8)
+    mlp_keep = (rng.uniform(size=(b, 64, h, w)) >= 0.2).astype(np.uint8)
+    wo, wa = _loss_weights(rng, (b, 64, h, w), (16, b, t, h, w))
+
+    def run(general):
+        for p_ in m.parameters():
+            p_.grad = None
+        xd = to_dev(x, dtype=torch.bfloat16).requires_grad_(True)
+        with _lib.option(_lib.OPT_LTAE_BWD_KERNEL, 1 if general else 0):
+            with c2s.modules.injected_dropout(to_dev(attn_keep), to_dev(mlp_keep)):
+                out, attn = m(xd, batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+            kernels = []
+            orig = ops.ltae_backward
+
+            def spy(*a_, **k_):
+                r = orig(*a_, **k_)
+                kernels.append(_lib.last_kernel())
+                return r
+            ops.ltae_backward = spy
+            try:
+                ((out.float() * to_dev(wo)).sum() + (attn * to_dev(wa)).sum()).backward()
+            finally:
+                ops.ltae_backward = orig
+        return xd.grad.float().cpu().numpy(), {n_: p_.grad.cpu().numpy().copy() for n_, p_ in m.named_parameters()}, kernels
+
+    gx_tc, gp_tc, k_tc = run(False)
+    gx_gen, gp_gen, k_gen = run(True)
+    # learnable positional tables (day of year) need grad_pe, which only the CUDA-core kernel forms
+    served = "ltae_backward<general>" if variant in ("doy", "abs_rel") else f"ltae_backward<tc,C={c_in}>"
+    assert k_tc == [served] and k_gen == ["ltae_backward<general>"]
+    assert np.isfinite(gx_tc).all()
+    assert rel_err(gx_tc, gx_gen) < 1.5e-2  # both round grad_x to bf16; the tensor-core operands are bf16 (measured <= 9e-3)
+    gmax = max(float(np.abs(v).max()) for v in gp_gen.values())
+    for name, ref in gp_gen.items():
+        diff = float(np.abs(gp_tc[name] - ref).max())
+        # the outputs of the kernel itself agree to < 1e-2 (tools/experiments/bwd_tc_errors.py); stage F then takes
+        # differences of them (in_norm.bias: direct term against the folded ones), hence the oracle's bf16 criterion
+        assert diff <= 3e-2 * max(float(np.abs(ref).max()), 1e-3 * gmax), (name, diff)
+    # the oracle's autograd on the same rounded features and the same dropout realisation
+    cfg = {"kind": "ltae", "kwargs": kw}
+    inp = {"positions": pos if pos is not None else np.zeros((b, t), np.int64), "pad_mask": pad, "attn_keep": attn_keep,
+           "mlp_keep": mlp_keep, "w_out": wo, "w_attn": wa}
+    if variant == "no_pe" or 0 in lengths:
+        # _oracle_training_step always passes positions; an all-padded series is all zeros, its GroupNorm has rstd =
+        # eps^-1/2 = 316 and turns the bf16 rounding of grad_x into O(1) differences: the comparison with the fp32
+        # kernel above covers both
+        return
+    _, ref_g = _oracle_training_step(cfg, inp, {k_: v for k_, v in oracle_params(m).items()}, x)
+    assert rel_err(gx_tc, ref_g["x"]) < 2e-2
+    gmax = max(float(np.abs(v).max()) for k_, v in ref_g.items() if k_ != "x")
+    for name, g_ in gp_tc.items():
+        ref = ref_g[name]
+        diff = float(np.abs(g_ - ref).max())
+        assert diff <= 3e-2 * max(float(np.abs(ref).max()), 1e-3 * gmax), (name, diff)

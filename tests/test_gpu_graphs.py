@@ -104,7 +104,9 @@ def test_training_step_replays_in_one_graph():
         assert np.isfinite(l_graph) and abs(l_graph - l_eager) <= 1e-3 * max(abs(l_eager), 1e-6)
         for k in p_eager:
             err = float((p_eager[k] - p_graph[k]).abs().max() / p_eager[k].abs().max().clamp_min(1e-12))
-            assert err < 2e-3, (k, err)  # float atomics reorder between runs; Adam normalises the step size
+            # float atomics reorder between runs and Adam normalises the step size: an element whose gradient sits at
+            # that noise level moves by +-lr per step whatever its sign does (3 steps of 1e-3 on weights of ~0.25)
+            assert err < 1e-2, (k, err)
     finally:
         c2s.modules.ATTENTION_DROPOUT = old
 
