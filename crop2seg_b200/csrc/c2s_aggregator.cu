@@ -31,6 +31,7 @@ struct AggArgs {
   const void* x;
   const float* attn;  // [n_heads, B, T, ha, wa] or nullptr (uniform weights)
   const uint8_t* pad;  // [B, T] or nullptr
+  const int* order;    // [B] samples by decreasing number of valid frames (pipelined kernel) or nullptr
   void* out;
   int B, T, C, H, W;
   int n_heads, ha, wa;
@@ -317,6 +318,24 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   return r;
 }
 
+// The CTAs of a sample do work proportional to its number of valid frames (27 .. 61 in the benchmark) and the hardware
+// hands CTAs out in grid order, so the kernel's tail is whatever the last samples happen to be.  One small CTA sorts the
+// samples by decreasing length (rank by counting, stable) and the pipelined kernel walks the grid's y dimension through
+// that permutation: longest-processing-time-first, the tail is made of the shortest series.
+__global__ void __launch_bounds__(1024) agg_order_kernel(const uint8_t* __restrict__ pad, int* __restrict__ order, int B, int T) {
+  __shared__ short len[1024];
+  const int i = threadIdx.x;
+  int n = 0;
+  if (i < B)
+    for (int t = 0; t < T; ++t) n += pad[i * T + t] == 0;
+  len[i] = static_cast<short>(i < B ? n : -1);
+  __syncthreads();
+  if (i >= B) return;
+  int rank = 0;
+  for (int q = 0; q < B; ++q) rank += (len[q] > n) || (len[q] == n && q < i);
+  order[rank] = i;
+}
+
 // TAPS: the attention rows a pixel block needs (a contiguous slice of the low-resolution map, at most a few hundred
 // floats) ride along with every frame as one more bulk copy into the stage, and the consumers read their bilinear taps
 // from shared memory.  Without it every consumer thread issues 2 * NCOL global loads per frame for them -- measured as
@@ -332,7 +351,7 @@ __global__ void __launch_bounds__(kPipeMaxConsumers + 32, (S >= 4 && sizeof(T) =
   __shared__ int n_frames_s;
   __shared__ __align__(8) unsigned long long bars[2 * 16];  // full[0..15], empty[0..15]
 
-  const int b = blockIdx.y;
+  const int b = a.order != nullptr ? a.order[blockIdx.y] : blockIdx.y;  // longest series first: the last wave is the short ones
   const int cchunk = blockIdx.x / pblocks;
   const int pblk = blockIdx.x - cchunk * pblocks;
   const int c0 = cchunk * kPipeCPT;
@@ -553,6 +572,9 @@ int launch_cpt(const AggArgs& a, int cpt, int s, cudaStream_t stream) {
     default: return launch_scale<T, VEC, 1>(a, s, stream);
   }
 }
+
+// the sample order of the pipelined kernel sits behind the pooled / averaged attention maps in the workspace
+inline size_t order_offset(size_t map_bytes) { return (map_bytes + 15) & ~static_cast<size_t>(15); }
 
 size_t attn_elems(const c2s_agg_desc* d, int heads, int h, int w) {
   return static_cast<size_t>(heads) * d->B * d->T * h * w;
@@ -882,7 +904,7 @@ size_t c2s_agg_workspace_bytes(const c2s_agg_desc* d) {
     const int k = d->wa / (d->H > 0 ? d->H : 1);
     if (k >= 1) n = c2s::attn_elems(d, d->n_heads, d->ha / k, d->wa / k);
   }
-  return n * sizeof(float);
+  return c2s::order_offset(n * sizeof(float)) + static_cast<size_t>(d->B > 0 ? d->B : 0) * sizeof(int);
 }
 
 int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, const uint8_t* pad_mask, void* out,
@@ -908,6 +930,7 @@ int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, con
   a.B = d->B, a.T = d->T, a.C = d->C, a.H = d->H, a.W = d->W;
   a.hw = d->H * d->W;
   int scale_class = 0;
+  size_t map_bytes = 0;  // workspace bytes taken by the averaged / pooled attention maps
 
   if (d->mode == C2S_AGG_MEAN) {
     a.attn = nullptr;
@@ -928,6 +951,7 @@ int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, con
       head_mean_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(attn, static_cast<float*>(workspace), heads, n);
       C2S_LAUNCH_CHECK("head_mean");
       amap = static_cast<const float*>(workspace);
+      map_bytes = n * sizeof(float);
       heads = 1;
     } else if (uses_pool(d)) {
       const int k = d->wa / d->H;
@@ -944,6 +968,7 @@ int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, con
                                                               k, n);
         C2S_LAUNCH_CHECK("avg_pool");
         amap = static_cast<const float*>(workspace);
+        map_bytes = n * sizeof(float);
       }
       ha = ho, wa = wo;
     }
@@ -973,6 +998,15 @@ int c2s_agg_forward(const c2s_agg_desc* d, const void* x, const float* attn, con
     if (n_consumers >= 64 && n_consumers % 32 == 0 && vecs % n_consumers == 0) {
       int n_stages = bf16 ? 3 : 4;  // 16 KB stages; bf16: 3 (x8: three CTAs per SM = 144 KB, the rest stays L1 for the attention taps: 0.927 vs 0.967 ms with 4)
       while (static_cast<size_t>(n_stages) * kPipeCPT * n_consumers * 16 > 12 * 16384) --n_stages;
+      // ragged series: walk the samples longest first (one 1-CTA launch; skipped when the caller gave no room for it)
+      const size_t off = order_offset(map_bytes);
+      if (pad_mask != nullptr && d->B > 1 && d->B <= 1024 && workspace != nullptr &&
+          workspace_bytes >= off + static_cast<size_t>(d->B) * sizeof(int)) {
+        int* order = reinterpret_cast<int*>(static_cast<char*>(workspace) + off);
+        agg_order_kernel<<<1, 1024, 0, stream>>>(pad_mask, order, d->B, d->T);
+        C2S_LAUNCH_CHECK("agg_order");
+        a.order = order;
+      }
       return bf16 ? launch_pipe<__nv_bfloat16>(a, scale_class, n_consumers, n_stages, stream)
                   : launch_pipe<float>(a, scale_class, n_consumers, n_stages, stream);
     }

@@ -15,7 +15,7 @@
 //     the N dimension of one product per head (two heads per warp), the result lands in shared memory [pixel][h][c];
 //   * grad_x replaces x in the slab (same fragment positions), is transposed back and leaves as four TMA stores (the
 //     frame dimension of the 4-D tensor map clips t >= T);
-//   * the sums over pixels (grad_U, direct gamma / beta terms, grad_cpos) collect in shared memory; grad_U and the
+//   * the sums over pixels (grad_U, direct gamma / beta terms, grad_cpos) collect in shared memory (fp32); grad_U and the
 //     gamma / beta terms are flushed once per CTA, grad_cpos once per tile.
 // 64 HBM bytes per (pixel, frame, 16 channels) are read and written once; at the training placement (4 096 pixels) the
 // kernel is latency-bound, the point is the instruction count: ~4 k warp instructions per pixel against ~77 k of the
@@ -35,7 +35,7 @@ struct BtSmem {
   static constexpr int kSlab = kTP * kFB;
   static constexpr int kGzRow = (C + 8) * 2;          // one head row of gzn (bf16), bytes
   static constexpr int kGzPix = kH * kGzRow + 16;     // pixel blocks 4 banks apart
-  static constexpr int kGuP = 20;                     // pitch of the grad_U / grad_cpos accumulators (bank spread)
+  static constexpr int kGuP = 20;                     // pitch of the grad_U accumulators (bank spread)
   static constexpr int kPeRowB = 48;                  // positional rows [t][16 + 8] bf16
   static constexpr int oSlab = 0;
   static constexpr int oGz = oSlab + kSlab;
@@ -80,6 +80,18 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t v) {
   return r;
 }
 __device__ __forceinline__ float2 ldg_f2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+// global loads that must be ISSUED where they are written (the compiler sinks plain loads to their first use, which puts a
+// full L2 latency on the critical path)
+__device__ __forceinline__ float ldg_f32_now(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_u8_now(const uint8_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 
 template <int C>
 __global__ void __launch_bounds__(256, 1)
@@ -212,6 +224,43 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       go2 = ldg_f2(gor + 16 * g + 2 * j + 8), go3 = ldg_f2(gor + 16 * (g + 8) + 2 * j + 8);
     }
 
+    // the gradient of the returned attention is the initial value of the g_at accumulators, the dropout realisation two
+    // bit masks (rows g / g + 8, bit 2 nt + e <-> frame 8 nt + 2 j + e): requested now, they travel during the phases below
+    float gacc[8][4];
+    uint32_t km0 = 0xffffffffu, km1 = 0xffffffffu;
+    {
+      const size_t h8 = static_cast<size_t>(8) * a.B * a.T * a.hw;
+      const size_t at0 = ((static_cast<size_t>(g) * a.B + b) * a.T) * a.hw + pix0 + p;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int t = nt * 8 + 2 * j + e;
+          float v0 = 0.f, v1 = 0.f;
+          if (a.g_attn != nullptr && t < a.T) {
+            const float* ga = a.g_attn + at0 + static_cast<size_t>(t) * a.hw;
+            v0 = ldg_f32_now(ga), v1 = ldg_f32_now(ga + h8);
+          }
+          gacc[nt][e] = v0, gacc[nt][2 + e] = v1;
+        }
+      if (a.attn_keep != nullptr) {
+        uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int t = nt * 8 + 2 * j + e;
+            if (t < a.T) {
+              const uint8_t* kp = a.attn_keep + at0 + static_cast<size_t>(t) * a.hw;
+              m0 |= (ldg_u8_now(kp) != 0u ? 1u : 0u) << (2 * nt + e);
+              m1 |= (ldg_u8_now(kp + h8) != 0u ? 1u : 0u) << (2 * nt + e);
+            }
+          }
+        km0 = m0, km1 = m1;
+      }
+    }
+    const float keep_scale = a.attn_keep != nullptr ? a.attn_keep_scale : 1.f;
+
     // ---- gzn[pixel][h][c] = sum_i Wc[16 h + i][c] grad_o[pixel][16 h + i]: heads 2 warp, 2 warp + 1; M = c, N = pixel -----
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
@@ -313,23 +362,13 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     __syncwarp();
 
     // ---- scores S[h, t] (hi + lo weights) and g_at[h, t] = sum_c (gamma gzn r)[h, c] x[t, c] + ... in one sweep ------------
-    float sacc[8][4], gacc[8][4], cacc[4] = {0.f, 0.f, 0.f, 0.f};
+    float sacc[8][4], cacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int t = nt * 8 + 2 * j;
       const float2 c0 = *reinterpret_cast<const float2*>(s_cpos + g * kAP + t);
       const float2 c1 = *reinterpret_cast<const float2*>(s_cpos + (g + 8) * kAP + t);
       sacc[nt][0] = c0.x, sacc[nt][1] = c0.y, sacc[nt][2] = c1.x, sacc[nt][3] = c1.y;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float v0 = 0.f, v1 = 0.f;
-        if (a.g_attn != nullptr && t + e < a.T) {
-          const float* ga = a.g_attn + ((static_cast<size_t>(g) * a.B + b) * a.T + t + e) * a.hw + pix0 + p;
-          v0 = __ldg(ga);
-          v1 = __ldg(ga + static_cast<size_t>(8) * a.B * a.T * a.hw);
-        }
-        gacc[nt][e] = v0, gacc[nt][2 + e] = v1;
-      }
     }
     const uint32_t xbase = slab + ((p ^ mr) << 4) + (mat & 1) * 128 + ((mat >> 1) * 8 + mr) * FB;
     const uint32_t gz_frag = s32(gz_ptr) + ((mat & 1) * 8 + mr) * S::kGzRow + (mat >> 1) * 16;
@@ -442,23 +481,12 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
       const float inv0 = 1.f / d0, inv1 = 1.f / d1;  // T >= 1: the maximum contributes exp2(0) = 1
       // a = e inv; g_a = g_at keep; at = a keep
-      float kacc[8][4];
       float dot0 = 0.f, dot1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int t = nt * 8 + 2 * j + e;
-          float k0 = 1.f, k1 = 1.f;
-          if (a.attn_keep != nullptr) {
-            k0 = 0.f, k1 = 0.f;
-            if (t < a.T) {
-              const uint8_t* kp = a.attn_keep + ((static_cast<size_t>(g) * a.B + b) * a.T + t) * a.hw + pix0 + p;
-              k0 = kp[0] ? a.attn_keep_scale : 0.f;
-              k1 = kp[static_cast<size_t>(8) * a.B * a.T * a.hw] ? a.attn_keep_scale : 0.f;
-            }
-          }
-          kacc[nt][e] = k0, kacc[nt][2 + e] = k1;
+          const float k0 = ((km0 >> (2 * nt + e)) & 1u) ? keep_scale : 0.f, k1 = ((km1 >> (2 * nt + e)) & 1u) ? keep_scale : 0.f;
           const float a0 = sacc[nt][e] * inv0, a1 = sacc[nt][2 + e] * inv1;
           sacc[nt][e] = a0, sacc[nt][2 + e] = a1;
           const float ga0 = (gacc[nt][e] + gsa0) * k0, ga1 = (gacc[nt][2 + e] + gsa1) * k1;
@@ -477,12 +505,12 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         for (int e = 0; e < 2; ++e) {
           gs[e] = sacc[nt][e] * (gacc[nt][e] - dot0);
           gs[2 + e] = sacc[nt][2 + e] * (gacc[nt][2 + e] - dot1);
-          at[e] = sacc[nt][e] * kacc[nt][e];
-          at[2 + e] = sacc[nt][2 + e] * kacc[nt][2 + e];
+          at[e] = ((km0 >> (2 * nt + e)) & 1u) ? sacc[nt][e] * keep_scale : 0.f;
+          at[2 + e] = ((km1 >> (2 * nt + e)) & 1u) ? sacc[nt][2 + e] * keep_scale : 0.f;
           sgs0 += gs[e], sgs1 += gs[2 + e], sa0 += at[e], sa1 += at[2 + e];
           const int t = nt * 8 + 2 * j + e;
-          atomicAdd(s_gc + t * GP + g, gs[e]);  // grad_cpos[b][t][h] += gs, summed over the pixels of the tile
-          atomicAdd(s_gc + t * GP + g + 8, gs[2 + e]);
+          atomicAdd(s_gc + t * GP + g, gs[e]);  // grad_cpos[b][t][h] += gs, summed over the pixels of the tile (fp32: the
+          atomicAdd(s_gc + t * GP + g + 8, gs[2 + e]);  // sum over t is analytically zero and must stay at rounding level)
         }
         gsp[nt][0] = pack_bf16(gs[0], gs[1]), gsp[nt][1] = pack_bf16(gs[2], gs[3]);
         atp[nt][0] = pack_bf16(at[0], at[1]), atp[nt][1] = pack_bf16(at[2], at[3]);

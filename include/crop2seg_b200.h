@@ -71,8 +71,9 @@ typedef struct c2s_agg_desc {
   int32_t dtype;         /* enum c2s_dtype of x and out; attn is always float32               */
 } c2s_agg_desc;
 
-/* Scratch bytes needed by c2s_agg_forward for this descriptor (0 for the shipped models:
- * only att_mean and the AvgPool2d branch stage a reduced attention map). */
+/* Scratch bytes c2s_agg_forward can use for this descriptor: the reduced attention map of att_mean / the AvgPool2d
+ * branch (required there) followed by B int32 for the sample order of the pipelined kernel (longest series first;
+ * optional: with a smaller or NULL workspace the samples are walked in index order, same results). */
 size_t c2s_agg_workspace_bytes(const c2s_agg_desc* desc);
 
 /* out[B,C,H,W] = sum_t resize(attn)[c // (C/n_heads), b, t] * (pad ? 0 : 1) * x[b,t,c]
