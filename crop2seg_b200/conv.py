@@ -70,7 +70,8 @@ def conv2d_reflect_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional
                       dtype=_code(x.dtype))
     wt = weight.detach().to(device=dev, dtype=torch.float32).contiguous()
     bs = None if bias is None else bias.detach().to(device=dev, dtype=torch.float32).contiguous()
-    y = torch.empty((n, c_out, h, w), dtype=x.dtype, device=dev)
+    ho, wo = (h + 2 * padding - kernel) // stride + 1, (w + 2 * padding - kernel) // stride + 1
+    y = torch.empty((n, c_out, ho, wo), dtype=x.dtype, device=dev)
     stats = torch.empty((n, 4, 2), dtype=torch.float32, device=dev) if with_stats else None
     inn, keep = None, []
     if in_norm is not None:

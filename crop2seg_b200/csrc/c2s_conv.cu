@@ -412,15 +412,259 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tacc) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 4x4 / stride 2 / reflect padding 1 (the strided layer of DownConvBlock, conv.py:252-263) from 128-pixel rows, 64 -> 64:
+//     y[o, Y, X] = b[o] + sum_{c, ky, kx} W[o, c, ky, kx] x[c, reflect(2 Y + ky - 1), reflect(2 X + kx - 1)]
+// The same machinery with three changes:
+//   * an input row is stored PARITY-SPLIT: even pixels [0, 2, .., 126, 126'] and odd pixels [1', 1, 3, .., 127] in two
+//     halves of the slot (primes: the reflected halo pixels 128 -> 126, -1 -> 1).  Output pixel X reads input pixel
+//     2 X + kx - 1, i.e. row X (kx = 0, 1) or X + 1 (kx = 2, 3) of the odd (kx even) / even (kx odd) half: the 16 taps are
+//     again start addresses, M = 64 output pixels per product;
+//   * the loop is INPUT-stationary: every input row is used by two output rows (three at the reflected frame edges), so a
+//     row's 32 products are issued when it arrives -- into the accumulators of those output rows -- and the row is
+//     released at once.  The ring needs 5 rows instead of the 6+ an output-stationary order would hold, which is what lets
+//     the 128 KB of weights (16 taps x 64 x 64 bf16) stay resident beside it;
+//   * an accumulator is handed to the epilogue when the last input row of its output row (2 Y + 2, or H - 1) is through.
+constexpr int kDSub = 9216;        // one parity half: 65 pixel rows x 128 B, rounded up to the 1024-byte swizzle atom
+constexpr int kDSlot = 2 * kDSub;  // [even | odd]
+constexpr int kDRing = 5;
+constexpr int kDChunks = 16;       // 16 taps x 64 channels, 64-wide K chunks
+constexpr int kDW = 128, kDWo = 64;
+
+__device__ __forceinline__ Unit dunit_of(const ConvArgs& a, int u) {  // a.H = input rows; output rows [y0, y1), input rows [lo, hi]
+  Unit t;
+  t.f = u / a.units_per_frame;
+  const int band = u - t.f * a.units_per_frame;
+  t.y0 = band * a.rows_per_unit;
+  t.y1 = min(t.y0 + a.rows_per_unit, a.H >> 1);
+  t.lo = max(2 * t.y0 - 1, 0);
+  t.hi = min(2 * t.y1, a.H - 1);
+  return t;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const ConvArgs a) {
+  constexpr int CB = 8;  // 8-channel blocks per pixel
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * kDRing + 2 * kAccBufs];  // full[R], empty[R], tfull[A], tempty[A]
+  __shared__ uint32_t tmem_s;
+  __shared__ float s_bias[kCN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (s32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* sm = smem_raw + (base - s32(smem_raw));
+  const uint32_t ring = base + kDChunks * 8192;
+  unsigned char* ring_ptr = sm + kDChunks * 8192;
+  const uint32_t bar0 = s32(&bars[0]);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kDRing + s); };
+  auto tfull = [&](int b) { return bar0 + 8u * (2 * kDRing + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (2 * kDRing + kAccBufs + b); };
+  const int Ho = a.H >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kDRing; ++s) mbar_init(full(s), 4), mbar_init(empty(s), 1);
+    for (int b = 0; b < kAccBufs; ++b) mbar_init(tfull(b), 1), mbar_init(tempty(b), 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s32(&tmem_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < kCN) s_bias[tid] = a.bias != nullptr ? a.bias[tid] : 0.f;
+  for (int i = tid; i < kCN * kDChunks * 8; i += kConvThreads) {  // resident weights, as in conv3x3_tc_kernel
+    const int c16 = i & 7, j = (i >> 3) % kDChunks, n = i / (8 * kDChunks);
+    const uint4 v = *reinterpret_cast<const uint4*>(a.wp + static_cast<size_t>(n) * (kDChunks * 64) + j * 64 + c16 * 8);
+    *reinterpret_cast<uint4*>(sm + j * 8192 + n * 128 + ((c16 ^ (n & 7)) << 4)) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tacc = tmem_s;
+
+  if (warp == 0) {
+    // ---- MMA issuer ----------------------------------------------------------------------------------------------
+    if (elect_one()) {
+      uint32_t idesc = 0;
+      idesc |= 1u << 4, idesc |= 1u << 7, idesc |= 1u << 10;  // D = fp32, A = B = bf16
+      idesc |= static_cast<uint32_t>(kCN >> 3) << 17;          // N = 64
+      idesc |= static_cast<uint32_t>(kDWo >> 4) << 24;         // M = 64
+      const uint32_t b_lo0 = ((base >> 4) & 0x3fffu) | (1u << 16);
+      uint32_t in_slot = 0, in_phase = 0;
+      uint32_t o = 0;  // output rows handed out so far (accumulator = o & 3)
+      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        const Unit t = dunit_of(a, u);
+        const uint32_t obase = o;
+        int started = 0;  // output rows of this unit that have received their first product
+        for (int r = t.lo; r <= t.hi; ++r) {
+          mbar_wait(full(in_slot), (in_phase >> in_slot) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t row_lo = (((ring + in_slot * kDSlot) >> 4) & 0x3fffu) | (1u << 16);
+          // the output rows fed by input row v (v = r, or the row r stands in for at a reflected frame edge)
+          auto contribute = [&](int v) {
+#pragma unroll 1
+            for (int ky = 0; ky < 4; ++ky) {
+              const int num = v + 1 - ky;  // = 2 Y
+              if (num & 1) continue;
+              const int Y = num >> 1;
+              if (Y < t.y0 || Y >= t.y1) continue;
+              const int rel = Y - t.y0;
+              const uint32_t oi = obase + rel, buf = oi & (kAccBufs - 1);
+              const bool fresh = rel == started;
+              if (fresh) {
+                ++started;
+                if (oi >= kAccBufs) mbar_wait(tempty(buf), ((oi / kAccBufs) - 1u) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              }
+              const uint32_t d_tmem = tacc + buf * kCN;
+#pragma unroll 1
+              for (int kx = 0; kx < 4; ++kx) {
+                // input pixel 2 X + kx - 1: odd half for even kx, even half for odd kx; row X (+ 1 for kx >= 2)
+                const uint32_t a_lo = row_lo + ((kx & 1) ? 0u : static_cast<uint32_t>(kDSub >> 4)) + (kx >> 1) * 8;
+                const uint32_t b_lo = b_lo0 + (ky * 4 + kx) * 512;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d_tmem, desc_from(a_lo + ks * 2), desc_from(b_lo + ks * 2), idesc, !(fresh && kx == 0 && ks == 0));
+              }
+            }
+          };
+          contribute(r);
+          if (r == 1) contribute(-1);           // row -1 = row 1
+          if (r == a.H - 2) contribute(a.H);    // row H = row H - 2
+          umma_commit(empty(in_slot));          // the row is dead once the products issued so far are done
+          in_phase ^= 1u << in_slot;
+          in_slot = in_slot + 1 == kDRing ? 0 : in_slot + 1;
+          // output rows whose last input row this was
+          if (!(r & 1) && r >= 2) {
+            const int yc = (r - 2) >> 1;
+            if (yc >= t.y0 && yc < t.y1) umma_commit(tfull((obase + yc - t.y0) & (kAccBufs - 1)));
+          }
+          if (r == a.H - 1 && t.y1 == Ho) umma_commit(tfull((obase + Ho - 1 - t.y0) & (kAccBufs - 1)));
+        }
+        o += t.y1 - t.y0;
+      }
+    }
+  } else if (warp <= 4) {
+    // ---- producers: one 8 channel x 8 pixel block per thread and input row, stored parity-split ---------------------------
+    const int ptid = tid - 32;
+    const int cb = ptid % CB, pb = ptid / CB;  // 8 x 16 blocks = 128 threads
+    unsigned g = 0;
+    const size_t plane = static_cast<size_t>(a.H) * kDW;
+    auto load_row = [&](uint4 (&v)[8], int f, int r) {
+      const __nv_bfloat16* src = a.x + (static_cast<size_t>(f) * a.c_in + cb * 8) * plane + static_cast<size_t>(r) * kDW + pb * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(src + i * plane));
+    };
+    int nu = blockIdx.x, nr = 0;
+    Unit nt{};
+    auto advance = [&]() {
+      if (++nr > nt.hi) {
+        nu += gridDim.x;
+        if (nu < a.n_units) nt = dunit_of(a, nu), nr = nt.lo;
+      }
+    };
+    uint4 vn0[8], vn1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vn0[i] = vn1[i] = make_uint4(0, 0, 0, 0);
+    if (nu < a.n_units) {
+      nt = dunit_of(a, nu);
+      nr = nt.lo;
+      load_row(vn0, nt.f, nr);
+      advance();
+      if (nu < a.n_units) load_row(vn1, nt.f, nr);
+    }
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+      const Unit t = dunit_of(a, u);
+      for (int r = t.lo; r <= t.hi; ++r, ++g) {
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = vn0[i], vn0[i] = vn1[i];
+        if (nu < a.n_units) {
+          advance();
+          if (nu < a.n_units) load_row(vn1, nt.f, nr);
+        }
+        const unsigned slot = g % kDRing;
+        if (g >= kDRing) mbar_wait(empty(slot), ((g / kDRing) - 1u) & 1u);
+        unsigned char* sl = ring_ptr + slot * kDSlot;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+          auto word = [&](int i) -> uint32_t {
+            return (j >> 1) == 0 ? v[i].x : ((j >> 1) == 1 ? v[i].y : ((j >> 1) == 2 ? v[i].z : v[i].w));
+          };
+          uint4 w;
+          w.x = __byte_perm(word(0), word(1), sel);
+          w.y = __byte_perm(word(2), word(3), sel);
+          w.z = __byte_perm(word(4), word(5), sel);
+          w.w = __byte_perm(word(6), word(7), sel);
+          // pixel 8 pb + j: even -> row (8 pb + j) / 2 of the even half, odd -> row (8 pb + j + 1) / 2 of the odd half
+          const int row = 4 * pb + ((j + 1) >> 1);
+          unsigned char* half = sl + ((j & 1) ? kDSub : 0);
+          *reinterpret_cast<uint4*>(half + row * 128 + ((cb ^ (row & 7)) << 4)) = w;
+          if (pb == 0 && j == 1) *reinterpret_cast<uint4*>(sl + kDSub + ((cb ^ 0) << 4)) = w;                    // pixel -1 = pixel 1
+          if (pb == kDW / 8 - 1 && j == 6) *reinterpret_cast<uint4*>(sl + 64 * 128 + ((cb ^ (64 & 7)) << 4)) = w;  // pixel 128 = pixel 126
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full(slot));
+      }
+    }
+  } else {
+    // ---- epilogue: an M = 64 accumulator keeps rows 16 q .. 16 q + 15 in lanes 0-15 of TMEM quarter q ---------------------
+    const int q = warp & 3, half = (warp - 5) >> 2;
+    const bool valid = lane < 16;
+    const int x = q * 16 + (lane & 15);
+    float bias_r[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) bias_r[c] = s_bias[half * 32 + c];
+    unsigned o = 0;
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+      const Unit t = dunit_of(a, u);
+      float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+      for (int y = t.y0; y < t.y1; ++y, ++o) {
+        const unsigned buf = o & (kAccBufs - 1);
+        mbar_wait(tfull(buf), (o / kAccBufs) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t r0[32];
+        tmem_ld32(tacc + (static_cast<uint32_t>(q * 32) << 16) + buf * kCN + half * 32, r0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(buf));
+        const size_t cstride = static_cast<size_t>(Ho) * kDWo;
+        __nv_bfloat16* dst = a.y + ((static_cast<size_t>(t.f) * kCN + half * 32) * Ho + y) * kDWo + x;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float v0 = valid ? __uint_as_float(r0[c]) + bias_r[c] : 0.f;
+          if (valid) dst[c * cstride] = __float2bfloat16_rn(v0);
+          s1[c >> 4] += v0, s2[c >> 4] = fmaf(v0, v0, s2[c >> 4]);
+        }
+      }
+      if (a.stats != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float t1 = warp_sum(s1[k]), t2 = warp_sum(s2[k]);
+          if (lane == 0) {
+            atomicAdd(a.stats + (static_cast<size_t>(t.f) * kStatQuarters + half * 2 + k) * 2, t1);
+            atomicAdd(a.stats + (static_cast<size_t>(t.f) * kStatQuarters + half * 2 + k) * 2 + 1, t2);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tacc) : "memory");
+}
+
 // weight[c_out][c_in][3][3] fp32 -> wp[c_out][chunks * 64] bf16 with k = tap * CK + c (zero for c >= c_in and behind 9 CK)
 __global__ void conv_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int ck,
-                                        int k_total) {
+                                        int k_total, int taps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c_out * k_total) return;
   const int n = i / k_total, k = i - n * k_total;
   const int tap = k / ck, c = k - tap * ck;
   float v = 0.f;
-  if (tap < 9 && c < c_in) v = w[(static_cast<size_t>(n) * c_in + c) * 9 + tap];
+  if (tap < taps && c < c_in) v = w[(static_cast<size_t>(n) * c_in + c) * taps + tap];
   wp[i] = __float2bfloat16_rn(v);
 }
 
@@ -510,6 +754,11 @@ __global__ void __launch_bounds__(256) group_norm_relu_kernel(const NormArgs a) 
 
 int conv_ck(int c_in) { return c_in <= 16 ? 16 : 64; }
 int conv_chunks(int ck) { return (9 * ck + 63) / 64; }
+// the strided layer of DownConvBlock on the tensor cores: 4x4 / stride 2 / padding 1 from 128-pixel rows, 64 -> 64 channels
+bool conv_is_down(const c2s_conv_desc& d) {
+  return d.kernel == 4 && d.stride == 2 && d.padding == 1 && d.W == kDW && d.H >= 4 && d.H % 2 == 0 && d.c_in == 64 &&
+         d.c_out == kCN && d.dtype == C2S_BF16 && d.frames > 0;
+}
 
 }  // namespace
 }  // namespace c2s
@@ -518,12 +767,14 @@ extern "C" {
 
 int c2s_conv2d_supported(const c2s_conv_desc* d) {
   if (d == nullptr) return 0;
+  if (c2s::conv_is_down(*d)) return 1;
   return d->kernel == 3 && d->stride == 1 && d->padding == 1 && (d->W == 128 || d->W == 64) && d->H >= 2 && d->c_out == c2s::kCN &&
          (d->c_in <= 16 || d->c_in == 64) && d->c_in >= 1 && d->dtype == C2S_BF16 && d->frames > 0;
 }
 
 size_t c2s_conv2d_workspace_bytes(const c2s_conv_desc* d) {
   if (!c2s_conv2d_supported(d)) return 0;
+  if (c2s::conv_is_down(*d)) return static_cast<size_t>(c2s::kCN) * c2s::kDChunks * 64 * sizeof(__nv_bfloat16);
   return static_cast<size_t>(c2s::kCN) * c2s::conv_chunks(c2s::conv_ck(d->c_in)) * 64 * sizeof(__nv_bfloat16);
 }
 
@@ -533,7 +784,8 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_
   C2S_CHECK_ARG(desc != nullptr && x != nullptr && weight != nullptr && y != nullptr, "c2s_conv2d_forward: NULL argument");
   const c2s_conv_desc& d = *desc;
   if (!c2s_conv2d_supported(desc))
-    C2S_UNSUPPORTED("c2s_conv2d_forward: serves 3x3 / stride 1 / reflect padding 1, W = 128 or 64, c_out = 64, c_in <= 16 or 64, bf16 "
+    C2S_UNSUPPORTED("c2s_conv2d_forward: serves 3x3 / stride 1 / reflect padding 1, W = 128 or 64, c_out = 64, c_in <= 16 or 64, "
+                    "and 4x4 / stride 2 / padding 1, W = 128, even H, 64 -> 64 channels; bf16 "
                     "(got k=%d s=%d p=%d W=%d c_in=%d c_out=%d dtype=%d)", d.kernel, d.stride, d.padding, d.W, d.c_in, d.c_out,
                     d.dtype);
   C2S_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0,
@@ -544,9 +796,10 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_
   int status = check_device();
   if (status != C2S_OK) return status;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_ptr);
-  const int ck = conv_ck(d.c_in), chunks = conv_chunks(ck), k_total = chunks * 64;
+  const bool down = conv_is_down(d);
+  const int ck = conv_ck(d.c_in), chunks = down ? kDChunks : conv_chunks(ck), k_total = chunks * 64;
   __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(workspace);
-  conv_weight_prep_kernel<<<ceil_div(kCN * k_total, 256), 256, 0, stream>>>(weight, wp, kCN, d.c_in, ck, k_total);
+  conv_weight_prep_kernel<<<ceil_div(kCN * k_total, 256), 256, 0, stream>>>(weight, wp, kCN, d.c_in, ck, k_total, down ? 16 : 9);
   C2S_LAUNCH_CHECK("conv_weight_prep");
   if (stats != nullptr) C2S_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(d.frames) * kStatQuarters * 2 * sizeof(float), stream));
   int sms = 148, dev = 0;
@@ -561,6 +814,20 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_
                   in_norm->n_sub, d.c_in);
     a.in_stats = in_norm->stats, a.in_gamma = in_norm->gamma, a.in_beta = in_norm->beta;
     a.in_groups = in_norm->n_groups, a.in_sub = in_norm->n_sub, a.in_relu = in_norm->relu, a.in_eps = in_norm->eps;
+  }
+  if (down) {  // units are bands of OUTPUT rows
+    C2S_CHECK_ARG(in_norm == nullptr, "c2s_conv2d_forward: the strided layer reads a normalised input (no in_norm)");
+    const int ho = d.H / 2;
+    a.rows_per_unit = ho;
+    while (a.rows_per_unit > 8 && static_cast<long long>(d.frames) * ceil_div(ho, a.rows_per_unit) < 4LL * sms) a.rows_per_unit /= 2;
+    a.units_per_frame = ceil_div(ho, a.rows_per_unit);
+    a.n_units = d.frames * a.units_per_frame;
+    const int grid_d = a.n_units < sms ? a.n_units : sms;
+    const size_t smem_d = static_cast<size_t>(kDChunks) * 8192 + static_cast<size_t>(kDRing) * kDSlot + 1024;
+    C2S_SMEM_ATTR(conv4x4s2_tc_kernel, smem_d);
+    conv4x4s2_tc_kernel<<<grid_d, kConvThreads, smem_d, stream>>>(a);
+    C2S_LAUNCH_CHECK("conv4x4s2_reflect<tcgen05>");
+    return C2S_OK;
   }
   // whole frames per unit when there are enough of them to balance the SMs, bands of rows otherwise
   a.rows_per_unit = d.H;

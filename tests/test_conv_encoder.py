@@ -96,6 +96,32 @@ def test_tensor_core_convolution_matches_torch(frames, c_in, h, w):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("frames,h", [(2, 128), (3, 4), (5, 10), (1, 6), (37, 32), (200, 128), (9, 64)])
+def test_tensor_core_strided_convolution_matches_torch(frames, h):
+    """The strided layer of DownConvBlock (conv.py:252-263): 4x4 / stride 2 / reflect padding 1, 64 -> 64 channels from
+    128-pixel rows -- parity-split rows, input-stationary products -- against a plain fp32 torch convolution of the same
+    bf16 operands: whole frames and bands per unit, the reflected rows at both frame edges, several units per CTA."""
+    g = torch.Generator(device="cuda").manual_seed(frames * 17 + h)
+    x = torch.randn((frames, 64, h, 128), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((64, 64, 4, 4), device="cuda", generator=g) * (1.0 / 32.0)
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    conv = torch.nn.Conv2d(64, 64, 4, stride=2, padding=1, padding_mode="reflect")
+    assert c2s_conv.conv2d_supported(x, conv)
+    y, stats = c2s_conv.conv2d_reflect_forward(x, w, b, kernel=4, stride=2, padding=1)
+    torch.cuda.synchronize()
+    assert c2s.ops._lib.load().c2s_last_kernel().decode() == "conv4x4s2_reflect<tcgen05>"
+    xp = torch.nn.functional.pad(x.float(), (1, 1, 1, 1), mode="reflect")
+    ref = torch.nn.functional.conv2d(xp, w.to(torch.bfloat16).float(), b, stride=2)
+    assert y.shape == ref.shape == (frames, 64, h // 2, 64) and y.dtype == torch.bfloat16
+    err = (y.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 6e-3, err
+    q = ref.view(frames, 4, -1)
+    s1, s2 = q.sum(-1), (q * q).sum(-1)
+    assert torch.allclose(stats[..., 0], s1, rtol=2e-3, atol=2e-3 * s1.abs().max().item())
+    assert torch.allclose(stats[..., 1], s2, rtol=2e-3)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("residual", [False, True])
 def test_group_norm_relu_matches_torch(dtype, residual):

@@ -105,6 +105,24 @@ def main():
         ms = timed(lambda: refb(x), args.seconds)
     print(json.dumps({"record": "the same layers, torch eager bf16 (cuDNN)", "ms": ms, "frames_per_s": n / ms * 1e3,
                       "tflops": flops / ms * 1e-9}), flush=True)
+    del x, xf
+    # first down block of U-TAE (utae.py:137-149): 4x4 / stride 2 layer 128^2 -> 64^2, then two 3x3 layers at 64^2
+    x64 = torch.randn((n, 64, 64, 64), device=dev).to(torch.bfloat16)
+    conv = torch.nn.Conv2d(64, 64, 3, padding=1, padding_mode="reflect").to(dev)
+    flops = 2.0 * n * 64 * 64 * 64 * 64 * 9
+    ms = timed(lambda: cc.conv2d_reflect_forward(x64, conv.weight, conv.bias), args.seconds)
+    print(json.dumps({"record": "conv3x3_reflect<tcgen05> c_in=64 at 64^2 (M = 64 products)", "frames": n, "ms": ms,
+                      "tflops": flops / ms * 1e-9, "tensor_frac": flops / ms * 1e-9 / float(peaks.get("bf16_tflops", 1637.8))}),
+          flush=True)
+    del x64
+    down = c2s.DownConvBlock(64, 64, 4, 2, 1, pad_value=0, norm="group").to(dev).eval()
+    x = torch.randn((n, 64, H, W), device=dev).to(torch.bfloat16)
+    with torch.no_grad():
+        ms = timed(lambda: down(x), args.seconds)
+        ms_down = timed(lambda: down.down(x), args.seconds)
+    flops = 2.0 * n * 64 * 64 * 64 * 64 * (16 + 9 + 9)
+    print(json.dumps({"record": "DownConvBlock(64, 64, 4, 2, 1) on packed frames 128^2 -> 64^2", "frames": n, "ms": ms,
+                      "ms_strided_layer": ms_down, "frames_per_s": n / ms * 1e3, "tflops": flops / ms * 1e-9}), flush=True)
 
 
 if __name__ == "__main__":
