@@ -9,11 +9,12 @@ What runs where (``forward`` / ``smart_forward``, eval mode, CUDA tensors):
 
 * frames: ``smart_forward`` packs the valid frames with the device-side frame index (no ``nonzero`` sync, no dummy
   forward; ``staging.py``), runs the block in bf16 on the packed frames and scatters the result back;
-* convolution: 3x3 / stride 1 layers at the full resolution (W = 128, 64 output channels: the two layers of ``in_conv``,
-  47 % of the encoder's multiply-adds) run as a hand-written tcgen05 implicit GEMM (``c2s_conv2d_forward``,
-  ``csrc/c2s_conv.cu``).  Every other layer (4x4 / stride 2, the 64^2 ... 16^2 levels, 128 channels) calls
-  ``torch.nn.functional.conv2d`` on a reflect-padded bf16 tensor -- a plain cuDNN library convolution, stated here and in
-  DESIGN.md as NOT part of the hand-written path -- followed by ``c2s_group_stats``;
+* convolution: every layer with 64 input (or <= 16, the model input) and 64 output channels runs as a hand-written tcgen05
+  implicit GEMM (``c2s_conv2d_forward``, ``csrc/c2s_conv.cu``): the 3x3 / stride 1 layers on rows of 128, 64 or 32 pixels
+  and the strided 4x4 layer of ``DownConvBlock`` from rows of 128, 64 or 32 pixels -- 96 % of the multiply-adds of U-TAE's
+  spatial encoder.  The two 128-channel layers of the last block (16 x 16 pixels) call ``torch.nn.functional.conv2d`` on a
+  reflect-padded bf16 tensor -- a plain cuDNN library convolution, stated here and in DESIGN.md as NOT part of the
+  hand-written path -- followed by ``c2s_group_stats``;
 * GroupNorm + ReLU (+ the residual of ``DownConvBlock``): ``c2s_group_norm_relu``, one element-wise pass, fp32 statistics;
   between two tensor-core stages of one ``ConvLayer`` the pass is skipped: the next convolution normalises its input on
   the fly while it stages it (``c2s_conv_input_norm``).

@@ -127,11 +127,14 @@ __device__ __forceinline__ Unit unit_of(const ConvArgs& a, int u) {
   return t;
 }
 
-// W = image width = UMMA M: 128 (one accumulator row per TMEM lane) or 64 (an M = 64 accumulator lives in lanes 0-15 of every
-// 32-lane quarter, tools/ubench/umma_rowshift.cu)
+// W = image width: 128 = UMMA M (one accumulator row per TMEM lane), 64 (an M = 64 accumulator lives in lanes 0-15 of every
+// 32-lane quarter, tools/ubench/umma_rowshift.cu) or 32 (M = 64 products whose rows 32-63 read whatever follows the slot --
+// the rows of a product are independent, their accumulator lanes are never stored; the tensor pipe is not what limits
+// these kernels, the issue rate of the products is)
 template <int CK, bool NORM, int W>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvArgs a) {
   constexpr int kCW = W;
+  constexpr int kM = W < 64 ? 64 : W;              // UMMA M
   constexpr int kSlotBytes = slot_bytes(W);
   constexpr int KS = CK / 16;                      // k-steps (MMA instructions) per tap
   constexpr int NCHUNK = (9 * CK + 63) / 64;       // 64-wide K chunks of the resident weights
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
       idesc |= 1u << 7;                                  // A = bf16
       idesc |= 1u << 10;                                 // B = bf16
       idesc |= static_cast<uint32_t>(kCN >> 3) << 17;    // N
-      idesc |= static_cast<uint32_t>(kCW >> 4) << 24;    // M
+      idesc |= static_cast<uint32_t>(kM >> 4) << 24;     // M
       const uint32_t b_lo0 = ((base >> 4) & 0x3fffu) | (1u << 16);
       uint32_t in_slot = 0, in_phase = 0;      // ring slot of the next input row to wait for; bit s = parity of slot s
       uint32_t free_slot = 0;                  // ring slot of the next input row to release
@@ -363,8 +366,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
   } else {
     // ---- epilogue: TMEM lanes 32 q .. 32 q + 31 = pixels of the row; the two warps of a quarter split the channels ------
     const int q = warp & 3, half = (warp - 5) >> 2;
-    const bool valid = kCW == 128 || lane < 16;                    // M = 64: rows 16 q .. 16 q + 15 in lanes 0-15
-    const int x = kCW == 128 ? q * 32 + lane : q * 16 + (lane & 15);
+    const int x = kM == 128 ? q * 32 + lane : q * 16 + (lane & 15);  // M = 64: rows 16 q .. 16 q + 15 in lanes 0-15
+    const bool valid = (kM == 128 || lane < 16) && x < kCW;
     float bias_r[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) bias_r[c] = s_bias[half * 32 + c];
@@ -425,11 +428,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
 //     released at once.  The ring needs 5 rows instead of the 6+ an output-stationary order would hold, which is what lets
 //     the 128 KB of weights (16 taps x 64 x 64 bf16) stay resident beside it;
 //   * an accumulator is handed to the epilogue when the last input row of its output row (2 Y + 2, or H - 1) is through.
-constexpr int kDSub = 9216;        // one parity half: 65 pixel rows x 128 B, rounded up to the 1024-byte swizzle atom
-constexpr int kDSlot = 2 * kDSub;  // [even | odd]
+// Input rows of 64 or 32 pixels (the second and third down block) run the same M = 64 products with 32 / 16 live rows.
+__host__ __device__ constexpr int dsub_bytes(int win) { return ((win / 2 + 1) * 128 + 1023) / 1024 * 1024; }  // one parity half
 constexpr int kDRing = 5;
 constexpr int kDChunks = 16;       // 16 taps x 64 channels, 64-wide K chunks
-constexpr int kDW = 128, kDWo = 64;
 
 __device__ __forceinline__ Unit dunit_of(const ConvArgs& a, int u) {  // a.H = input rows; output rows [y0, y1), input rows [lo, hi]
   Unit t;
@@ -442,7 +444,11 @@ __device__ __forceinline__ Unit dunit_of(const ConvArgs& a, int u) {  // a.H = i
   return t;
 }
 
+template <int WIN>
 __global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const ConvArgs a) {
+  constexpr int kDW = WIN, kDWo = WIN / 2;
+  constexpr int kDSub = dsub_bytes(WIN);  // WIN = 128: 65 pixel rows x 128 B -> 9216
+  constexpr int kDSlot = 2 * kDSub;       // [even | odd]
   constexpr int CB = 8;  // 8-channel blocks per pixel
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bars[2 * kDRing + 2 * kAccBufs];  // full[R], empty[R], tfull[A], tempty[A]
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const Con
       uint32_t idesc = 0;
       idesc |= 1u << 4, idesc |= 1u << 7, idesc |= 1u << 10;  // D = fp32, A = B = bf16
       idesc |= static_cast<uint32_t>(kCN >> 3) << 17;          // N = 64
-      idesc |= static_cast<uint32_t>(kDWo >> 4) << 24;         // M = 64
+      idesc |= static_cast<uint32_t>(64 >> 4) << 24;           // M = 64 (kDWo live rows)
       const uint32_t b_lo0 = ((base >> 4) & 0x3fffu) | (1u << 16);
       uint32_t in_slot = 0, in_phase = 0;
       uint32_t o = 0;  // output rows handed out so far (accumulator = o & 3)
@@ -547,12 +553,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const Con
     // ---- producers: one 8 channel x 8 pixel block per thread and input row, stored parity-split ---------------------------
     const int ptid = tid - 32;
     const int cb = ptid % CB, pb = ptid / CB;  // 8 x 16 blocks = 128 threads
+    const bool active = pb < kDW / 8;
     unsigned g = 0;
     const size_t plane = static_cast<size_t>(a.H) * kDW;
     auto load_row = [&](uint4 (&v)[8], int f, int r) {
       const __nv_bfloat16* src = a.x + (static_cast<size_t>(f) * a.c_in + cb * 8) * plane + static_cast<size_t>(r) * kDW + pb * 8;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(src + i * plane));
+      for (int i = 0; i < 8; ++i) v[i] = active ? __ldg(reinterpret_cast<const uint4*>(src + i * plane)) : make_uint4(0, 0, 0, 0);
     };
     int nu = blockIdx.x, nr = 0;
     Unit nt{};
@@ -585,23 +592,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const Con
         const unsigned slot = g % kDRing;
         if (g >= kDRing) mbar_wait(empty(slot), ((g / kDRing) - 1u) & 1u);
         unsigned char* sl = ring_ptr + slot * kDSlot;
+        if (active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
-          auto word = [&](int i) -> uint32_t {
-            return (j >> 1) == 0 ? v[i].x : ((j >> 1) == 1 ? v[i].y : ((j >> 1) == 2 ? v[i].z : v[i].w));
-          };
-          uint4 w;
-          w.x = __byte_perm(word(0), word(1), sel);
-          w.y = __byte_perm(word(2), word(3), sel);
-          w.z = __byte_perm(word(4), word(5), sel);
-          w.w = __byte_perm(word(6), word(7), sel);
-          // pixel 8 pb + j: even -> row (8 pb + j) / 2 of the even half, odd -> row (8 pb + j + 1) / 2 of the odd half
-          const int row = 4 * pb + ((j + 1) >> 1);
-          unsigned char* half = sl + ((j & 1) ? kDSub : 0);
-          *reinterpret_cast<uint4*>(half + row * 128 + ((cb ^ (row & 7)) << 4)) = w;
-          if (pb == 0 && j == 1) *reinterpret_cast<uint4*>(sl + kDSub + ((cb ^ 0) << 4)) = w;                    // pixel -1 = pixel 1
-          if (pb == kDW / 8 - 1 && j == 6) *reinterpret_cast<uint4*>(sl + 64 * 128 + ((cb ^ (64 & 7)) << 4)) = w;  // pixel 128 = pixel 126
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+            auto word = [&](int i) -> uint32_t {
+              return (j >> 1) == 0 ? v[i].x : ((j >> 1) == 1 ? v[i].y : ((j >> 1) == 2 ? v[i].z : v[i].w));
+            };
+            uint4 w;
+            w.x = __byte_perm(word(0), word(1), sel);
+            w.y = __byte_perm(word(2), word(3), sel);
+            w.z = __byte_perm(word(4), word(5), sel);
+            w.w = __byte_perm(word(6), word(7), sel);
+            // pixel 8 pb + j: even -> row (8 pb + j) / 2 of the even half, odd -> row (8 pb + j + 1) / 2 of the odd half
+            const int row = 4 * pb + ((j + 1) >> 1);
+            unsigned char* half = sl + ((j & 1) ? kDSub : 0);
+            *reinterpret_cast<uint4*>(half + row * 128 + ((cb ^ (row & 7)) << 4)) = w;
+            if (pb == 0 && j == 1) *reinterpret_cast<uint4*>(sl + kDSub + ((cb ^ 0) << 4)) = w;  // pixel -1 = pixel 1
+            if (pb == kDW / 8 - 1 && j == 6)                                                       // pixel W = pixel W - 2
+              *reinterpret_cast<uint4*>(sl + kDWo * 128 + ((cb ^ (kDWo & 7)) << 4)) = w;
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -611,8 +621,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const Con
   } else {
     // ---- epilogue: an M = 64 accumulator keeps rows 16 q .. 16 q + 15 in lanes 0-15 of TMEM quarter q ---------------------
     const int q = warp & 3, half = (warp - 5) >> 2;
-    const bool valid = lane < 16;
     const int x = q * 16 + (lane & 15);
+    const bool valid = lane < 16 && x < kDWo;
     float bias_r[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) bias_r[c] = s_bias[half * 32 + c];
@@ -756,7 +766,7 @@ int conv_ck(int c_in) { return c_in <= 16 ? 16 : 64; }
 int conv_chunks(int ck) { return (9 * ck + 63) / 64; }
 // the strided layer of DownConvBlock on the tensor cores: 4x4 / stride 2 / padding 1 from 128-pixel rows, 64 -> 64 channels
 bool conv_is_down(const c2s_conv_desc& d) {
-  return d.kernel == 4 && d.stride == 2 && d.padding == 1 && d.W == kDW && d.H >= 4 && d.H % 2 == 0 && d.c_in == 64 &&
+  return d.kernel == 4 && d.stride == 2 && d.padding == 1 && (d.W == 128 || d.W == 64 || d.W == 32) && d.H >= 4 && d.H % 2 == 0 && d.c_in == 64 &&
          d.c_out == kCN && d.dtype == C2S_BF16 && d.frames > 0;
 }
 
@@ -768,7 +778,7 @@ extern "C" {
 int c2s_conv2d_supported(const c2s_conv_desc* d) {
   if (d == nullptr) return 0;
   if (c2s::conv_is_down(*d)) return 1;
-  return d->kernel == 3 && d->stride == 1 && d->padding == 1 && (d->W == 128 || d->W == 64) && d->H >= 2 && d->c_out == c2s::kCN &&
+  return d->kernel == 3 && d->stride == 1 && d->padding == 1 && (d->W == 128 || d->W == 64 || d->W == 32) && d->H >= 2 && d->c_out == c2s::kCN &&
          (d->c_in <= 16 || d->c_in == 64) && d->c_in >= 1 && d->dtype == C2S_BF16 && d->frames > 0;
 }
 
@@ -784,8 +794,8 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_
   C2S_CHECK_ARG(desc != nullptr && x != nullptr && weight != nullptr && y != nullptr, "c2s_conv2d_forward: NULL argument");
   const c2s_conv_desc& d = *desc;
   if (!c2s_conv2d_supported(desc))
-    C2S_UNSUPPORTED("c2s_conv2d_forward: serves 3x3 / stride 1 / reflect padding 1, W = 128 or 64, c_out = 64, c_in <= 16 or 64, "
-                    "and 4x4 / stride 2 / padding 1, W = 128, even H, 64 -> 64 channels; bf16 "
+    C2S_UNSUPPORTED("c2s_conv2d_forward: serves 3x3 / stride 1 / reflect padding 1, W = 128, 64 or 32, c_out = 64, c_in <= 16 or 64, "
+                    "and 4x4 / stride 2 / padding 1, W = 128, 64 or 32, even H, 64 -> 64 channels; bf16 "
                     "(got k=%d s=%d p=%d W=%d c_in=%d c_out=%d dtype=%d)", d.kernel, d.stride, d.padding, d.W, d.c_in, d.c_out,
                     d.dtype);
   C2S_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0,
@@ -823,9 +833,19 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_
     a.units_per_frame = ceil_div(ho, a.rows_per_unit);
     a.n_units = d.frames * a.units_per_frame;
     const int grid_d = a.n_units < sms ? a.n_units : sms;
-    const size_t smem_d = static_cast<size_t>(kDChunks) * 8192 + static_cast<size_t>(kDRing) * kDSlot + 1024;
-    C2S_SMEM_ATTR(conv4x4s2_tc_kernel, smem_d);
-    conv4x4s2_tc_kernel<<<grid_d, kConvThreads, smem_d, stream>>>(a);
+    // narrow rows: the M = 64 products read 65 pixel rows from a half of 33 / 17; the ring is followed by what they run into
+    const size_t smem_d = static_cast<size_t>(kDChunks) * 8192 + static_cast<size_t>(kDRing) * 2 * dsub_bytes(d.W) + 1024 +
+                          (d.W == 128 ? 0 : 8192);
+    if (d.W == 128) {
+      C2S_SMEM_ATTR(conv4x4s2_tc_kernel<128>, smem_d);
+      conv4x4s2_tc_kernel<128><<<grid_d, kConvThreads, smem_d, stream>>>(a);
+    } else if (d.W == 64) {
+      C2S_SMEM_ATTR(conv4x4s2_tc_kernel<64>, smem_d);
+      conv4x4s2_tc_kernel<64><<<grid_d, kConvThreads, smem_d, stream>>>(a);
+    } else {
+      C2S_SMEM_ATTR(conv4x4s2_tc_kernel<32>, smem_d);
+      conv4x4s2_tc_kernel<32><<<grid_d, kConvThreads, smem_d, stream>>>(a);
+    }
     C2S_LAUNCH_CHECK("conv4x4s2_reflect<tcgen05>");
     return C2S_OK;
   }
@@ -835,7 +855,8 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_
   a.units_per_frame = ceil_div(d.H, a.rows_per_unit);
   a.n_units = d.frames * a.units_per_frame;
   const int grid = a.n_units < sms ? a.n_units : sms;
-  const size_t smem = static_cast<size_t>(chunks) * 8192 + static_cast<size_t>(kRing) * slot_bytes(d.W) + 1024;
+  // W = 32: the products read 66 pixel rows from a slot of 40; the ring is followed by what the last slot's reads run into
+  const size_t smem = static_cast<size_t>(chunks) * 8192 + static_cast<size_t>(kRing) * slot_bytes(d.W) + 1024 + (d.W == 32 ? 4096 : 0);
   if (ck == 16)  // the first layer of a block reads the model input: no normalisation on the fly
     C2S_CHECK_ARG(in_norm == nullptr, "c2s_conv2d_forward: input normalisation needs c_in = 64");
 #define C2S_CONV_LAUNCH(CK_, NORM_, W_)                                                   \
@@ -847,10 +868,14 @@ int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_
     if (ck == 16) C2S_CONV_LAUNCH(16, false, 128);
     else if (in_norm != nullptr) C2S_CONV_LAUNCH(64, true, 128);
     else C2S_CONV_LAUNCH(64, false, 128);
-  } else {
+  } else if (d.W == 64) {
     if (ck == 16) C2S_CONV_LAUNCH(16, false, 64);
     else if (in_norm != nullptr) C2S_CONV_LAUNCH(64, true, 64);
     else C2S_CONV_LAUNCH(64, false, 64);
+  } else {
+    if (ck == 16) C2S_CONV_LAUNCH(16, false, 32);
+    else if (in_norm != nullptr) C2S_CONV_LAUNCH(64, true, 32);
+    else C2S_CONV_LAUNCH(64, false, 32);
   }
 #undef C2S_CONV_LAUNCH
   C2S_LAUNCH_CHECK("conv3x3_reflect<tcgen05>");

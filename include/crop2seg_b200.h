@@ -393,8 +393,10 @@ typedef struct c2s_conv_desc {
   int32_t dtype;                   /* enum c2s_dtype of x and y                                  */
 } c2s_conv_desc;
 
-/* 1 when c2s_conv2d_forward serves the layer on the tensor cores: 3x3, stride 1, padding 1, W = 128, c_out = 64,
- * c_in <= 16 or c_in = 64, bf16 (U-TAE's in_conv: utae.py:128-136).  Other layers are the caller's business. */
+/* 1 when c2s_conv2d_forward serves the layer on the tensor cores (bf16, c_out = 64):
+ *   3x3, stride 1, padding 1, W = 128 / 64 / 32, c_in <= 16 or c_in = 64   (in_conv, conv1 / conv2 of the down blocks)
+ *   4x4, stride 2, padding 1, W = 128 / 64 / 32, even H, c_in = 64         (the strided layer of DownConvBlock, conv.py:252-263)
+ * Other layers (128 channels) are the caller's business. */
 int c2s_conv2d_supported(const c2s_conv_desc* desc);
 size_t c2s_conv2d_workspace_bytes(const c2s_conv_desc* desc); /* prepared bf16 weights */
 
@@ -408,10 +410,10 @@ typedef struct c2s_conv_input_norm {
   float eps;
 } c2s_conv_input_norm;
 
-/* y[f, o, y, x] = bias[o] + sum_{c, ky, kx} weight[o, c, ky, kx] * x'[f, c, reflect(y + ky - 1), reflect(x + kx - 1)]
- *   x      : [frames, c_in, H, W] bf16;  x' = x, or relu(GroupNorm(x)) rounded to bf16 when in_norm is given
- *   weight : float32 [c_out, c_in, 3, 3] (nn.Conv2d.weight), bias float32 [c_out] | NULL
- *   y      : [frames, c_out, H, W] bf16, the RAW convolution output (GroupNorm needs the whole frame first)
+/* y[f, o, y, x] = bias[o] + sum_{c, ky, kx} weight[o, c, ky, kx] * x'[f, c, reflect(s y + ky - 1), reflect(s x + kx - 1)]
+ *   x      : [frames, c_in, H, W] bf16;  x' = x, or relu(GroupNorm(x)) rounded to bf16 when in_norm is given (3x3 only)
+ *   weight : float32 [c_out, c_in, k, k] (nn.Conv2d.weight), bias float32 [c_out] | NULL
+ *   y      : [frames, c_out, H / s, W / s] bf16, the RAW convolution output (GroupNorm needs the whole frame first)
  *   stats  : float32 [frames][4][2] = (sum, sum of squares) of the fp32 outputs per frame and quarter of the channels
  *            (written, not accumulated), for c2s_group_norm_relu / c2s_conv_input_norm with n_sub = 4; or NULL */
 int c2s_conv2d_forward(const c2s_conv_desc* desc, const void* x, const c2s_conv_input_norm* in_norm, const float* weight,

@@ -73,7 +73,8 @@ def _torch_conv(x, w, b):
 @pytest.mark.gpu
 @pytest.mark.parametrize("frames,c_in,h,w", [(3, 64, 12, 128), (2, 10, 7, 128), (1, 64, 2, 128), (5, 3, 33, 128),
                                              (150, 64, 16, 128), (20, 64, 128, 128),
-                                             (3, 64, 64, 64), (7, 64, 5, 64), (2, 10, 9, 64), (300, 64, 64, 64)])
+                                             (3, 64, 64, 64), (7, 64, 5, 64), (2, 10, 9, 64), (300, 64, 64, 64),
+                                             (3, 64, 32, 32), (5, 10, 7, 32), (1, 64, 2, 32), (700, 64, 32, 32)])
 def test_tensor_core_convolution_matches_torch(frames, c_in, h, w):
     g = torch.Generator(device="cuda").manual_seed(frames * 131 + c_in)
     x = torch.randn((frames, c_in, h, w), device="cuda", generator=g).to(torch.bfloat16)
@@ -96,13 +97,15 @@ def test_tensor_core_convolution_matches_torch(frames, c_in, h, w):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("frames,h", [(2, 128), (3, 4), (5, 10), (1, 6), (37, 32), (200, 128), (9, 64)])
-def test_tensor_core_strided_convolution_matches_torch(frames, h):
+@pytest.mark.parametrize("frames,h,w_in", [(2, 128, 128), (3, 4, 128), (5, 10, 128), (1, 6, 128), (37, 32, 128), (200, 128, 128),
+                                            (9, 64, 128), (3, 64, 64), (5, 6, 64), (400, 64, 64), (3, 32, 32), (2, 4, 32),
+                                            (900, 32, 32)])
+def test_tensor_core_strided_convolution_matches_torch(frames, h, w_in):
     """The strided layer of DownConvBlock (conv.py:252-263): 4x4 / stride 2 / reflect padding 1, 64 -> 64 channels from
-    128-pixel rows -- parity-split rows, input-stationary products -- against a plain fp32 torch convolution of the same
-    bf16 operands: whole frames and bands per unit, the reflected rows at both frame edges, several units per CTA."""
+    128 / 64 / 32-pixel rows -- parity-split rows, input-stationary products -- against a plain fp32 torch convolution of
+    the same bf16 operands: whole frames and bands per unit, the reflected rows at both frame edges, several units per CTA."""
     g = torch.Generator(device="cuda").manual_seed(frames * 17 + h)
-    x = torch.randn((frames, 64, h, 128), device="cuda", generator=g).to(torch.bfloat16)
+    x = torch.randn((frames, 64, h, w_in), device="cuda", generator=g).to(torch.bfloat16)
     w = torch.randn((64, 64, 4, 4), device="cuda", generator=g) * (1.0 / 32.0)
     b = torch.randn(64, device="cuda", generator=g) * 0.1
     conv = torch.nn.Conv2d(64, 64, 4, stride=2, padding=1, padding_mode="reflect")
@@ -112,7 +115,7 @@ def test_tensor_core_strided_convolution_matches_torch(frames, h):
     assert c2s.ops._lib.load().c2s_last_kernel().decode() == "conv4x4s2_reflect<tcgen05>"
     xp = torch.nn.functional.pad(x.float(), (1, 1, 1, 1), mode="reflect")
     ref = torch.nn.functional.conv2d(xp, w.to(torch.bfloat16).float(), b, stride=2)
-    assert y.shape == ref.shape == (frames, 64, h // 2, 64) and y.dtype == torch.bfloat16
+    assert y.shape == ref.shape == (frames, 64, h // 2, w_in // 2) and y.dtype == torch.bfloat16
     err = (y.float() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 6e-3, err
     q = ref.view(frames, 4, -1)

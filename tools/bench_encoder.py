@@ -123,6 +123,29 @@ def main():
     flops = 2.0 * n * 64 * 64 * 64 * 64 * (16 + 9 + 9)
     print(json.dumps({"record": "DownConvBlock(64, 64, 4, 2, 1) on packed frames 128^2 -> 64^2", "frames": n, "ms": ms,
                       "ms_strided_layer": ms_down, "frames_per_s": n / ms * 1e3, "tflops": flops / ms * 1e-9}), flush=True)
+    del x
+    full_encoder(n, args.seconds)
+
+
+def full_encoder(n, seconds):
+    """U-TAE's spatial encoder (utae.py:128-149, widths [64, 64, 64, 128]) block by block on n packed frames."""
+    dev = torch.device("cuda", 0)
+    blocks = [("in_conv 10->64->64 @128", c2s.ConvBlock([10, 64, 64], pad_value=0, norm="group"), (10, 128)),
+              ("down1 64->64 @128->64", c2s.DownConvBlock(64, 64, 4, 2, 1, pad_value=0, norm="group"), (64, 128)),
+              ("down2 64->64 @64->32", c2s.DownConvBlock(64, 64, 4, 2, 1, pad_value=0, norm="group"), (64, 64)),
+              ("down3 64->128 @32->16", c2s.DownConvBlock(64, 128, 4, 2, 1, pad_value=0, norm="group"), (64, 32))]
+    total = 0.0
+    for name, blk, (c, r) in blocks:
+        blk = blk.to(dev).eval()
+        x = torch.randn((n, c, r, r), device=dev).to(torch.bfloat16)
+        with torch.no_grad():
+            ms = timed(lambda: blk(x), seconds)
+        total += ms
+        print(json.dumps({"record": "encoder block " + name, "frames": n, "ms": ms}), flush=True)
+        del x
+    macs = 128 * 128 * 64 * 9 * 74 + 64 * 64 * 64 * 64 * 34 + 32 * 32 * 64 * 64 * 34 + 16 * 16 * (64 * 64 * 16 + 9 * 64 * 128 + 9 * 128 * 128)
+    print(json.dumps({"record": "U-TAE spatial encoder, four blocks", "frames": n, "ms": total, "frames_per_s": n / total * 1e3,
+                      "tflops": 2.0 * n * macs / total * 1e-9}), flush=True)
 
 
 if __name__ == "__main__":

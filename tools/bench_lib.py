@@ -262,6 +262,26 @@ def encoder(dev, frames=1024, min_seconds=1.0, seed=1234):
                                           "a 32-cycle tensor floor (tools/ubench/umma_rowshift.cu), i.e. at most 0.67 of "
                                           "the nominal rate with 64 output channels"}}
     del x, x64
+    # the four blocks of the spatial encoder one after the other (utae.py:128-149): every 64 -> 64 layer runs on the
+    # tensor-core kernels (3x3 with 128 / 64 / 32-pixel rows, strided 4x4 with parity-split rows); the two 128-channel layers
+    # of the last block (3.8 % of the multiply-adds) are library convolutions, said so in conv.py
+    blocks = [("in_conv", blk, (10, 128)),
+              ("down1", c2s.DownConvBlock(64, 64, 4, 2, 1, pad_value=0, norm="group").to(dev).eval(), (64, 128)),
+              ("down2", c2s.DownConvBlock(64, 64, 4, 2, 1, pad_value=0, norm="group").to(dev).eval(), (64, 64)),
+              ("down3", c2s.DownConvBlock(64, 128, 4, 2, 1, pad_value=0, norm="group").to(dev).eval(), (64, 32))]
+    per, total = {}, 0.0
+    for name, b, (c, r) in blocks:
+        xb = torch.randn((frames, c, r, r), device=dev, generator=gen).to(torch.bfloat16)
+        with torch.no_grad():
+            m, _, _ = timed(lambda: b(xb), dev, min_seconds / 4)
+        per[name] = m
+        total += m
+        del xb
+    macs = 128 * 128 * 64 * 9 * 74 + 64 * 64 * 64 * 64 * 34 + 32 * 32 * 64 * 64 * 34 + 16 * 16 * (64 * 64 * 16 + 9 * 64 * 128 + 9 * 128 * 128)
+    rec["spatial_encoder"] = {"workload": "U-TAE spatial encoder (in_conv + 3 DownConvBlock, widths [64,64,64,128]) on packed frames, "
+                                          "block by block", "ms_per_block": per, "ms": total,
+                              "frames_per_s": world * frames / (total * 1e-3), "tflops": 2.0 * frames * macs / total * 1e-9,
+                              "hand_written_share_of_macs": 1.0 - 16 * 16 * (9 * 64 * 128 + 9 * 128 * 128) / macs}
     torch.cuda.empty_cache()
     return rec
 
