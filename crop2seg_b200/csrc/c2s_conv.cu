@@ -194,8 +194,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
       uint32_t free_slot = 0;                  // ring slot of the next input row to release
       uint32_t o = 0;                          // output rows issued
       auto slot_lo = [&](uint32_t slot) { return (((ring + slot * kSlotBytes) >> 4) & 0x3fffu) | (1u << 16); };
+#ifdef C2S_CONV_TIMING
+      long long dbg_full = 0, dbg_tempty = 0, dbg_mma = 0, dbg_rows = 0;
+      const long long dbg_start = clock64();
+#endif
       auto take_row = [&]() {                  // wait for the next input row, return the descriptor word of its slot
+#ifdef C2S_CONV_TIMING
+        const long long dbg_t = clock64();
+#endif
         mbar_wait(full(in_slot), (in_phase >> in_slot) & 1u);
+#ifdef C2S_CONV_TIMING
+        dbg_full += clock64() - dbg_t;
+#endif
         const uint32_t lo = slot_lo(in_slot);
         in_phase ^= 1u << in_slot;
         in_slot = in_slot + 1 == kRing ? 0 : in_slot + 1;
@@ -219,7 +229,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
         }
         for (int y = t.y0; y < t.y1; ++y) {
           const uint32_t buf = o & (kAccBufs - 1);
+#ifdef C2S_CONV_TIMING
+          const long long dbg_t0 = clock64();
+#endif
           if (o >= kAccBufs) mbar_wait(tempty(buf), ((o / kAccBufs) - 1u) & 1u);
+#ifdef C2S_CONV_TIMING
+          const long long dbg_t1 = clock64();
+          dbg_tempty += dbg_t1 - dbg_t0;
+#endif
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d_tmem = tacc + buf * kCN;
           uint32_t b_lo = b_lo0;
@@ -241,6 +258,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
             }
           }
           umma_commit(tfull(buf));
+#ifdef C2S_CONV_TIMING
+          dbg_mma += clock64() - dbg_t1, ++dbg_rows;
+#endif
           ++o;
           // row y - 1 is not needed by later output rows (the first output row of a frame has no row above it)
           if (y > t.lo) release_row(), --resident;
@@ -253,6 +273,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
         }
         while (resident > 0) release_row(), --resident;
       }
+#ifdef C2S_CONV_TIMING
+      if (blockIdx.x == 0)
+        printf("[conv3x3 W=%d CK=%d] issuer of CTA 0: %lld rows, %lld cycles total; per row: wait full %lld, wait tempty %lld, "
+               "issue %lld\n", kCW, CK, dbg_rows, clock64() - dbg_start, dbg_full / dbg_rows, dbg_tempty / dbg_rows, dbg_mma / dbg_rows);
+#endif
     }
   } else if (warp <= 4) {
     // ---- producers: one 8 channel x 8 pixel block per thread and input row -------------------------------------------
@@ -497,12 +522,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const Con
       const uint32_t b_lo0 = ((base >> 4) & 0x3fffu) | (1u << 16);
       uint32_t in_slot = 0, in_phase = 0;
       uint32_t o = 0;  // output rows handed out so far (accumulator = o & 3)
+#ifdef C2S_CONV_TIMING
+      long long dbg_full = 0, dbg_tempty = 0, dbg_rows = 0;
+      const long long dbg_start = clock64();
+#endif
       for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
         const Unit t = dunit_of(a, u);
         const uint32_t obase = o;
         int started = 0;  // output rows of this unit that have received their first product
         for (int r = t.lo; r <= t.hi; ++r) {
+#ifdef C2S_CONV_TIMING
+          const long long dbg_t = clock64();
+#endif
           mbar_wait(full(in_slot), (in_phase >> in_slot) & 1u);
+#ifdef C2S_CONV_TIMING
+          dbg_full += clock64() - dbg_t, ++dbg_rows;
+#endif
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t row_lo = (((ring + in_slot * kDSlot) >> 4) & 0x3fffu) | (1u << 16);
           // the output rows fed by input row v (v = r, or the row r stands in for at a reflected frame edge)
@@ -518,7 +553,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const Con
               const bool fresh = rel == started;
               if (fresh) {
                 ++started;
+#ifdef C2S_CONV_TIMING
+                const long long dbg_t2 = clock64();
+#endif
                 if (oi >= kAccBufs) mbar_wait(tempty(buf), ((oi / kAccBufs) - 1u) & 1u);
+#ifdef C2S_CONV_TIMING
+                dbg_tempty += clock64() - dbg_t2;
+#endif
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               }
               const uint32_t d_tmem = tacc + buf * kCN;
@@ -548,6 +589,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const Con
         }
         o += t.y1 - t.y0;
       }
+#ifdef C2S_CONV_TIMING
+      if (blockIdx.x == 0)
+        printf("[conv4x4s2 W=%d] issuer of CTA 0: %lld input rows, %lld cycles total = %lld per row; per row: wait full %lld, "
+               "wait tempty %lld\n", kDW, dbg_rows, clock64() - dbg_start, (clock64() - dbg_start) / dbg_rows, dbg_full / dbg_rows,
+               dbg_tempty / dbg_rows);
+#endif
     }
   } else if (warp <= 4) {
     // ---- producers: one 8 channel x 8 pixel block per thread and input row, stored parity-split ---------------------------
