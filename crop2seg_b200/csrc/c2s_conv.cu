@@ -155,7 +155,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
   auto tempty = [&](int b) { return bar0 + 8u * (2 * kRing + kAccBufs + b); };
 
   if (tid == 0) {
-    for (int s = 0; s < kRing; ++s) mbar_init(full(s), 4), mbar_init(empty(s), 1);      // one arrival per producer warp
+    constexpr int kRowBlocks = (CK / 8) * (W / 8);  // producer threads of a row (see the producer role): whole warps -> groups
+    constexpr int kRowWarps = (kRowBlocks < 128 && kRowBlocks % 32 == 0) ? kRowBlocks / 32 : 4;
+    for (int s = 0; s < kRing; ++s) mbar_init(full(s), kRowWarps), mbar_init(empty(s), 1);   // one arrival per warp serving the row
     for (int b = 0; b < kAccBufs; ++b) mbar_init(tfull(b), 1), mbar_init(tempty(b), 8);       // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -281,65 +283,186 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
     }
   } else if (warp <= 4) {
     // ---- producers: one 8 channel x 8 pixel block per thread and input row -------------------------------------------
-    const int ptid = tid - 32;
-    const int cb = ptid % CB, pb = ptid / CB;
-    const bool active = pb < kCW / 8;
-    unsigned g = 0;
-    const size_t plane = static_cast<size_t>(a.H) * kCW;
-    auto load_row = [&](uint4 (&v)[8], int f, int r) {
-      const __nv_bfloat16* src = a.x + (static_cast<size_t>(f) * a.c_in + cb * 8) * plane + static_cast<size_t>(r) * kCW + pb * 8;
+    // A row has BPR = CB * W / 8 blocks.  When that is a whole number of warps below 128 threads (64- and 32-pixel rows, the
+    // 16-channel first layer), the 128 producer threads form NG = 128 / BPR groups that take the rows of the (unit, row)
+    // sequence in turn, each filling its own ring slots; otherwise all four warps serve every row (spare threads idle).
+    constexpr int BPR0 = CB * (kCW / 8);
+    constexpr int NG = (BPR0 < 128 && BPR0 % 32 == 0) ? 128 / BPR0 : 1;
+    constexpr int BPR = NG > 1 ? BPR0 : 128;
+    if constexpr (NG == 1) {
+      // every producer thread serves every row (the nested unit / row loops schedule measurably better than the cursor
+      // form below when there is nothing to skip: 2.25 vs 2.96 ms for the 64 -> 64 layer with the input normalisation)
+      const int ptid = tid - 32;
+      const int cb = ptid % CB, pb = ptid / CB;
+      const bool active = pb < kCW / 8;
+      unsigned g = 0;
+      const size_t plane = static_cast<size_t>(a.H) * kCW;
+      auto load_row = [&](uint4 (&v)[8], int f, int r) {
+        const __nv_bfloat16* src = a.x + (static_cast<size_t>(f) * a.c_in + cb * 8) * plane + static_cast<size_t>(r) * kCW + pb * 8;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        v[i] = (active && cb * 8 + i < a.c_in) ? __ldg(reinterpret_cast<const uint4*>(src + i * plane)) : make_uint4(0, 0, 0, 0);
-    };
-    // (unit, row) cursor of the newest row whose loads are in flight: two rows ahead of the row being stored (one row of
-    // latency hiding was measured as not enough: the producers sat on the long scoreboard)
-    int nu = blockIdx.x, nr = 0;
-    Unit nt{};
-    auto advance = [&]() {  // next (unit, row) in the order every role walks
-      if (++nr > nt.hi) {
-        nu += gridDim.x;
-        if (nu < a.n_units) nt = unit_of(a, nu), nr = nt.lo;
+        for (int i = 0; i < 8; ++i)
+          v[i] = (active && cb * 8 + i < a.c_in) ? __ldg(reinterpret_cast<const uint4*>(src + i * plane)) : make_uint4(0, 0, 0, 0);
+      };
+      // (unit, row) cursor of the newest row whose loads are in flight: two rows ahead of the row being stored (one row of
+      // latency hiding was measured as not enough: the producers sat on the long scoreboard)
+      int nu = blockIdx.x, nr = 0;
+      Unit nt{};
+      auto advance = [&]() {  // next (unit, row) in the order every role walks
+        if (++nr > nt.hi) {
+          nu += gridDim.x;
+          if (nu < a.n_units) nt = unit_of(a, nu), nr = nt.lo;
+        }
+      };
+      uint4 vn0[8], vn1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vn0[i] = vn1[i] = make_uint4(0, 0, 0, 0);
+      if (nu < a.n_units) {
+        nt = unit_of(a, nu);
+        nr = nt.lo;
+        load_row(vn0, nt.f, nr);
+        advance();
+        if (nu < a.n_units) load_row(vn1, nt.f, nr);
       }
-    };
-    uint4 vn0[8], vn1[8];
+      float sc[8], sh[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) vn0[i] = vn1[i] = make_uint4(0, 0, 0, 0);
-    if (nu < a.n_units) {
-      nt = unit_of(a, nu);
-      nr = nt.lo;
-      load_row(vn0, nt.f, nr);
-      advance();
-      if (nu < a.n_units) load_row(vn1, nt.f, nr);
-    }
-    float sc[8], sh[8];
+      for (int i = 0; i < 8; ++i) sc[i] = 1.f, sh[i] = 0.f;
+      int norm_f = -1;
+      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        const Unit t = unit_of(a, u);
+        if (NORM && t.f != norm_f && active) {  // scale / shift of this thread's 8 channels in frame t.f
+          norm_f = t.f;
+          const int cpg = a.c_in / a.in_groups, spg = a.in_sub / a.in_groups;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sc[i] = 1.f, sh[i] = 0.f;
-    int norm_f = -1;
-    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
-      const Unit t = unit_of(a, u);
-      if (NORM && t.f != norm_f && active) {  // scale / shift of this thread's 8 channels in frame t.f
-        norm_f = t.f;
-        const int cpg = a.c_in / a.in_groups, spg = a.in_sub / a.in_groups;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = cb * 8 + i;
-          if (c >= a.c_in) continue;
-          const int grp = c / cpg;
-          double t1 = 0.0, t2 = 0.0;
-          for (int k = 0; k < spg; ++k) {
-            t1 += a.in_stats[(static_cast<size_t>(t.f) * a.in_sub + grp * spg + k) * 2];
-            t2 += a.in_stats[(static_cast<size_t>(t.f) * a.in_sub + grp * spg + k) * 2 + 1];
+          for (int i = 0; i < 8; ++i) {
+            const int c = cb * 8 + i;
+            if (c >= a.c_in) continue;
+            const int grp = c / cpg;
+            double t1 = 0.0, t2 = 0.0;
+            for (int k = 0; k < spg; ++k) {
+              t1 += a.in_stats[(static_cast<size_t>(t.f) * a.in_sub + grp * spg + k) * 2];
+              t2 += a.in_stats[(static_cast<size_t>(t.f) * a.in_sub + grp * spg + k) * 2 + 1];
+            }
+            const double n = static_cast<double>(cpg) * a.H * kCW;
+            const double mean = t1 / n;
+            double var = t2 / n - mean * mean;
+            var = var < 0.0 ? 0.0 : var;
+            sc[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.in_eps))) * a.in_gamma[c];
+            sh[i] = a.in_beta[c] - static_cast<float>(mean) * sc[i];
           }
-          const double n = static_cast<double>(cpg) * a.H * kCW;
-          const double mean = t1 / n;
-          double var = t2 / n - mean * mean;
-          var = var < 0.0 ? 0.0 : var;
-          sc[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.in_eps))) * a.in_gamma[c];
-          sh[i] = a.in_beta[c] - static_cast<float>(mean) * sc[i];
+        }
+        for (int r = t.lo; r <= t.hi; ++r, ++g) {
+          uint4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = vn0[i], vn0[i] = vn1[i];
+          if (NORM) {  // the same arithmetic as group_norm_relu_kernel: fma in fp32, ReLU, round to bf16
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float f[8];
+              Elem<__nv_bfloat16>::unpack(v[i], f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                f[e] = fmaf(f[e], sc[i], sh[i]);
+                if (a.in_relu) f[e] = fmaxf(f[e], 0.f);
+              }
+              v[i] = Elem<__nv_bfloat16>::pack(f);
+            }
+          }
+          // issue the loads of the row after next: they fly during two rows of waits and stores
+          if (nu < a.n_units) {
+            advance();
+            if (nu < a.n_units) load_row(vn1, nt.f, nr);
+          }
+          const unsigned slot = g % kRing;
+          if (g >= kRing) mbar_wait(empty(slot), ((g / kRing) - 1u) & 1u);
+          if (active) {
+            unsigned char* sl = ring_ptr + slot * kSlotBytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+              // word j / 2 of channel i holds pixels (j & ~1, j | 1) of that channel
+              auto word = [&](int i) -> uint32_t {
+                return (j >> 1) == 0 ? v[i].x : ((j >> 1) == 1 ? v[i].y : ((j >> 1) == 2 ? v[i].z : v[i].w));
+              };
+              uint4 w;
+              w.x = __byte_perm(word(0), word(1), sel);
+              w.y = __byte_perm(word(2), word(3), sel);
+              w.z = __byte_perm(word(4), word(5), sel);
+              w.w = __byte_perm(word(6), word(7), sel);
+              const int row = pb * 8 + j + 1;
+              *reinterpret_cast<uint4*>(sl + row * 128 + ((cb ^ (row & 7)) << 4)) = w;
+              if (pb == 0 && j == 1) *reinterpret_cast<uint4*>(sl + ((cb ^ 0) << 4)) = w;                       // pixel -1 = pixel 1
+              if (pb == kCW / 8 - 1 && j == 6) *reinterpret_cast<uint4*>(sl + (kCW + 1) * 128 + ((cb ^ ((kCW + 1) & 7)) << 4)) = w;  // pixel W = pixel W - 2
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> tensor-core (async proxy) reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full(slot));  // hundreds of per-thread arrivals on one mbarrier cost ~1000 cycles per row
         }
       }
-      for (int r = t.lo; r <= t.hi; ++r, ++g) {
+    } else {
+      const int ptid = tid - 32;
+      const int grp = ptid / BPR, btid = ptid % BPR;
+      const int cb = btid % CB, pb = btid / CB;
+      const bool active = pb < kCW / 8;
+      const size_t plane = static_cast<size_t>(a.H) * kCW;
+      auto load_row = [&](uint4 (&v)[8], int f, int r) {
+        const __nv_bfloat16* src = a.x + (static_cast<size_t>(f) * a.c_in + cb * 8) * plane + static_cast<size_t>(r) * kCW + pb * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[i] = (active && cb * 8 + i < a.c_in) ? __ldg(reinterpret_cast<const uint4*>(src + i * plane)) : make_uint4(0, 0, 0, 0);
+      };
+      // cursors over the (unit, row) sequence every role walks: `cs` the row being stored, `cl` the newest row whose loads
+      // are in flight -- two of this group's rows ahead (one row of latency hiding was measured as not enough)
+      struct Cursor {
+        int u, r, hi, f;  // unit, row, last row of the unit, frame; u >= n_units: behind the end
+      };
+      auto enter = [&](Cursor& c) {
+        if (c.u < a.n_units) {
+          const Unit t = unit_of(a, c.u);
+          c.r = t.lo, c.hi = t.hi, c.f = t.f;
+        }
+      };
+      auto step = [&](Cursor& c, int n) {
+        for (int i = 0; i < n && c.u < a.n_units; ++i)
+          if (++c.r > c.hi) c.u += gridDim.x, enter(c);
+      };
+      Cursor cs{};
+      cs.u = blockIdx.x;
+      enter(cs);
+      step(cs, grp);
+      Cursor cl = cs;
+      uint4 vn0[8], vn1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vn0[i] = vn1[i] = make_uint4(0, 0, 0, 0);
+      if (cl.u < a.n_units) load_row(vn0, cl.f, cl.r);
+      step(cl, NG);
+      if (cl.u < a.n_units) load_row(vn1, cl.f, cl.r);
+      float sc[8], sh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sc[i] = 1.f, sh[i] = 0.f;
+      int norm_f = -1;
+      for (unsigned g = grp; cs.u < a.n_units; g += NG, step(cs, NG)) {
+        if (NORM && cs.f != norm_f && active) {  // scale / shift of this thread's 8 channels in frame cs.f
+          norm_f = cs.f;
+          const int cpg = a.c_in / a.in_groups, spg = a.in_sub / a.in_groups;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = cb * 8 + i;
+            if (c >= a.c_in) continue;
+            const int gq = c / cpg;
+            double t1 = 0.0, t2 = 0.0;
+            for (int k = 0; k < spg; ++k) {
+              t1 += a.in_stats[(static_cast<size_t>(norm_f) * a.in_sub + gq * spg + k) * 2];
+              t2 += a.in_stats[(static_cast<size_t>(norm_f) * a.in_sub + gq * spg + k) * 2 + 1];
+            }
+            const double n = static_cast<double>(cpg) * a.H * kCW;
+            const double mean = t1 / n;
+            double var = t2 / n - mean * mean;
+            var = var < 0.0 ? 0.0 : var;
+            sc[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.in_eps))) * a.in_gamma[c];
+            sh[i] = a.in_beta[c] - static_cast<float>(mean) * sc[i];
+          }
+        }
         uint4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = vn0[i], vn0[i] = vn1[i];
@@ -356,11 +479,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const ConvA
             v[i] = Elem<__nv_bfloat16>::pack(f);
           }
         }
-        // issue the loads of the row after next: they fly during two rows of waits and stores
-        if (nu < a.n_units) {
-          advance();
-          if (nu < a.n_units) load_row(vn1, nt.f, nr);
-        }
+        // issue the loads of this group's row after next: they fly during two rows of waits and stores
+        step(cl, NG);
+        if (cl.u < a.n_units) load_row(vn1, cl.f, cl.r);
         const unsigned slot = g % kRing;
         if (g >= kRing) mbar_wait(empty(slot), ((g / kRing) - 1u) & 1u);
         if (active) {
@@ -563,14 +684,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv4x4s2_tc_kernel(const Con
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               }
               const uint32_t d_tmem = tacc + buf * kCN;
-#pragma unroll 1
+              // 16 products with compile-time offsets from three bases (even half, odd half, the tap row of the weights):
+              // input pixel 2 X + kx - 1 = odd half for even kx, even half for odd kx; row X (+ 1 for kx >= 2)
+              const uint32_t a_even = row_lo, a_odd = row_lo + static_cast<uint32_t>(kDSub >> 4);
+              const uint32_t b_row = b_lo0 + ky * 2048;
+#pragma unroll
               for (int kx = 0; kx < 4; ++kx) {
-                // input pixel 2 X + kx - 1: odd half for even kx, even half for odd kx; row X (+ 1 for kx >= 2)
-                const uint32_t a_lo = row_lo + ((kx & 1) ? 0u : static_cast<uint32_t>(kDSub >> 4)) + (kx >> 1) * 8;
-                const uint32_t b_lo = b_lo0 + (ky * 4 + kx) * 512;
+                const uint32_t a_lo = ((kx & 1) ? a_even : a_odd) + (kx >> 1) * 8;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16(d_tmem, desc_from(a_lo + ks * 2), desc_from(b_lo + ks * 2), idesc, !(fresh && kx == 0 && ks == 0));
+                  umma_bf16(d_tmem, desc_from(a_lo + ks * 2), desc_from(b_row + kx * 512 + ks * 2), idesc,
+                            (kx | ks) != 0 ? 1u : (fresh ? 0u : 1u));
               }
             }
           };
