@@ -884,17 +884,19 @@ struct NormArgs {
   float eps;
 };
 
-template <typename T>
+// kNormItems 16-byte vectors per thread: four independent loads in flight, 16 KB (bf16) per block; 1 for tiny planes
+template <typename T, int kNormItems>
 __global__ void __launch_bounds__(256) group_norm_relu_kernel(const NormArgs a) {
   constexpr int VEC = Elem<T>::kVec;
-  __shared__ float s_sc[256], s_sh[256];  // scale / shift of the (at most 256) channels this block touches
+  constexpr int SPAN = 256 * kNormItems * VEC;  // elements per block
+  __shared__ float s_sc[256], s_sh[256];  // scale / shift of the channels this block touches (the host checks <= 256)
   const int f = blockIdx.y;
   const size_t per_frame = static_cast<size_t>(a.C) * a.hw;
-  const size_t e0 = static_cast<size_t>(blockIdx.x) * 256 * VEC;
+  const size_t e0 = static_cast<size_t>(blockIdx.x) * SPAN;
   const int c_first = static_cast<int>(e0 / a.hw);
-  size_t e_last = e0 + 256 * VEC - 1;
+  size_t e_last = e0 + SPAN - 1;
   e_last = e_last < per_frame ? e_last : per_frame - 1;
-  const int n_ch = static_cast<int>(e_last / a.hw) - c_first + 1;  // hw >= VEC: at most 256 channels
+  const int n_ch = static_cast<int>(e_last / a.hw) - c_first + 1;
   if (static_cast<int>(threadIdx.x) < n_ch) {
     const int c = c_first + threadIdx.x;
     const int cpg = a.C / a.n_groups, g = c / cpg, spg = a.n_sub / a.n_groups;
@@ -911,26 +913,40 @@ __global__ void __launch_bounds__(256) group_norm_relu_kernel(const NormArgs a) 
     s_sc[threadIdx.x] = sc;
     s_sh[threadIdx.x] = a.beta[c] - static_cast<float>(mean) * sc;
   }
+  // the loads go out before the barrier: they travel while the scale / shift of the block is formed
+  const size_t base = static_cast<size_t>(f) * per_frame;
+  uint4 xv[kNormItems], rv[kNormItems];
+  size_t e[kNormItems];
+#pragma unroll
+  for (int k = 0; k < kNormItems; ++k) {
+    e[k] = e0 + (static_cast<size_t>(k) * 256 + threadIdx.x) * VEC;
+    xv[k] = rv[k] = make_uint4(0, 0, 0, 0);
+    if (e[k] < per_frame) {
+      xv[k] = *reinterpret_cast<const uint4*>(static_cast<const T*>(a.x) + base + e[k]);  // plain load: out may alias x
+      if (a.residual != nullptr) rv[k] = ld_stream_v4(static_cast<const T*>(a.residual) + base + e[k]);
+    }
+  }
   __syncthreads();
-  const size_t e = e0 + static_cast<size_t>(threadIdx.x) * VEC;
-  if (e >= per_frame) return;
-  const int ci = static_cast<int>(e / a.hw) - c_first;  // hw % VEC == 0: the vector stays inside one channel
-  const float sc = s_sc[ci], sh = s_sh[ci];
-  const size_t off = static_cast<size_t>(f) * per_frame + e;
-  float v[VEC];
-  Elem<T>::unpack(*reinterpret_cast<const uint4*>(static_cast<const T*>(a.x) + off), v);  // plain load: out may alias x
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    v[i] = fmaf(v[i], sc, sh);
-    if (a.relu) v[i] = fmaxf(v[i], 0.f);
-  }
-  if (a.residual != nullptr) {
-    float rv[VEC];
-    Elem<T>::unpack(ld_stream_v4(static_cast<const T*>(a.residual) + off), rv);
+  for (int k = 0; k < kNormItems; ++k) {
+    if (e[k] >= per_frame) continue;
+    const int ci = static_cast<int>(e[k] / a.hw) - c_first;  // hw % VEC == 0: the vector stays inside one channel
+    const float sc = s_sc[ci], sh = s_sh[ci];
+    float v[VEC];
+    Elem<T>::unpack(xv[k], v);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) v[i] += rv[i];
+    for (int i = 0; i < VEC; ++i) {
+      v[i] = fmaf(v[i], sc, sh);
+      if (a.relu) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (a.residual != nullptr) {
+      float r[VEC];
+      Elem<T>::unpack(rv[k], r);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] += r[i];
+    }
+    *reinterpret_cast<uint4*>(static_cast<T*>(a.out) + base + e[k]) = Elem<T>::pack(v);
   }
-  *reinterpret_cast<uint4*>(static_cast<T*>(a.out) + off) = Elem<T>::pack(v);
 }
 
 int conv_ck(int c_in) { return c_in <= 16 ? 16 : 64; }
@@ -1094,11 +1110,16 @@ int c2s_group_norm_relu(const void* x, const float* stats, int32_t n_sub, const 
   NormArgs a{};
   a.x = x, a.residual = residual, a.out = out, a.stats = stats, a.gamma = gamma, a.beta = beta;
   a.C = channels, a.hw = static_cast<int>(hw), a.n_groups = n_groups, a.n_sub = n_sub, a.relu = relu, a.eps = eps;
-  dim3 grid(ceil_div(static_cast<long long>(channels) * hw / vec, 256), static_cast<unsigned>(frames));
-  if (dtype == C2S_BF16)
-    group_norm_relu_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
-  else
-    group_norm_relu_kernel<float><<<grid, 256, 0, stream>>>(a);
+  // four vectors per thread unless the planes are so small that a block would touch more than 256 channels
+  const int items = (256LL * 4 * vec / hw + 2 <= 256) ? 4 : 1;
+  dim3 grid(ceil_div(static_cast<long long>(channels) * hw, 256LL * items * vec), static_cast<unsigned>(frames));
+  if (dtype == C2S_BF16) {
+    if (items == 4) group_norm_relu_kernel<__nv_bfloat16, 4><<<grid, 256, 0, stream>>>(a);
+    else group_norm_relu_kernel<__nv_bfloat16, 1><<<grid, 256, 0, stream>>>(a);
+  } else {
+    if (items == 4) group_norm_relu_kernel<float, 4><<<grid, 256, 0, stream>>>(a);
+    else group_norm_relu_kernel<float, 1><<<grid, 256, 0, stream>>>(a);
+  }
   C2S_LAUNCH_CHECK("group_norm_relu");
   return C2S_OK;
 }
