@@ -63,11 +63,12 @@ def test_bad_arguments_return_status_codes_not_aborts(lib):
 
 def test_workspace_sizes(lib):
     d = _lib.AggDesc(B=2, T=5, C=8, H=8, W=8, n_heads=4, ha=4, wa=4, mode=_lib.AGG_ATT_GROUP, dtype=_lib.F32)
-    assert lib.c2s_agg_workspace_bytes(ctypes.byref(d)) == 0  # the shipped models need no scratch
+    order = 2 * 4  # B int32: the sample order of the pipelined kernel (optional) sits behind the maps, 16-byte aligned
+    assert lib.c2s_agg_workspace_bytes(ctypes.byref(d)) == order  # the shipped models stage no attention map
     d.mode = _lib.AGG_ATT_MEAN
-    assert lib.c2s_agg_workspace_bytes(ctypes.byref(d)) == 2 * 5 * 4 * 4 * 4
+    assert lib.c2s_agg_workspace_bytes(ctypes.byref(d)) == 2 * 5 * 4 * 4 * 4 + order
     d.mode, d.ha, d.wa, d.H, d.W = _lib.AGG_ATT_GROUP, 8, 8, 4, 4  # AvgPool2d branch
-    assert lib.c2s_agg_workspace_bytes(ctypes.byref(d)) == 4 * 2 * 5 * 4 * 4 * 4
+    assert lib.c2s_agg_workspace_bytes(ctypes.byref(d)) == 4 * 2 * 5 * 4 * 4 * 4 + order
     l = _lib.LtaeDesc(B=2, T=61, C=128, H=16, W=16, n_head=16, d_k=4, d_model=256, c_out=128, has_inconv=1,
                       pe_mode=_lib.PE_SINUSOID, pe_abs=0, pos_dtype=0, dtype=_lib.BF16, flags=0, gn_eps=1e-5, bn_eps=1e-5)
     n = lib.c2s_ltae_workspace_bytes(ctypes.byref(l))
