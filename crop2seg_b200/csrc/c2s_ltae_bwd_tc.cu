@@ -93,7 +93,9 @@ __device__ __forceinline__ uint32_t ldg_u8_now(const uint8_t* p) {
   return v;
 }
 
-template <int C>
+// FULL = false: the attention-only encoder of W-TAE (LTAE4WTAE, tae.py:507-635): no value path, so no gzn, no zn / sa rows,
+// no direct gamma / beta terms; g_at is the gradient of the returned attention alone.
+template <int C, bool FULL>
 __global__ void __launch_bounds__(256, 1)
 ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_gx, const BwdTcArgs a) {
   using S = BtSmem<C>;
@@ -217,8 +219,8 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
     }
     // this pixel's grad_o row as the A operand [h][i] of the positional product (rows g / g + 8, i = 2 j .. and + 8)
-    float2 go0, go1, go2, go3;
-    {
+    float2 go0 = make_float2(0.f, 0.f), go1 = go0, go2 = go0, go3 = go0;
+    if constexpr (FULL) {
       const float* gor = a.g_o + (row0 + p) * kD;
       go0 = ldg_f2(gor + 16 * g + 2 * j), go1 = ldg_f2(gor + 16 * (g + 8) + 2 * j);
       go2 = ldg_f2(gor + 16 * g + 2 * j + 8), go3 = ldg_f2(gor + 16 * (g + 8) + 2 * j + 8);
@@ -263,7 +265,7 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
     // ---- gzn[pixel][h][c] = sum_i Wc[16 h + i][c] grad_o[pixel][16 h + i]: heads 2 warp, 2 warp + 1; M = c, N = pixel -----
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
+    for (int hh = 0; hh < (FULL ? 2 : 0); ++hh) {
       const int h = 2 * warp + hh;
       const float* gor = a.g_o + (row0 + g) * kD + 16 * h + 2 * j;
       const float2 b0f = ldg_f2(gor), b1f = ldg_f2(gor + 8);
@@ -383,8 +385,8 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       split_bf16(u0.z * r0, u0.w * r0, ahi[1], alo[1]);  // (row g + 8, k 2j, 2j+1)
       split_bf16(u1.x * r1, u1.y * r1, ahi[2], alo[2]);  // (row g,     k 2j+8, 2j+9)
       split_bf16(u1.z * r1, u1.w * r1, ahi[3], alo[3]);  // (row g + 8, k 2j+8, 2j+9)
-      ldsm_x4(az, gz_frag + ks * 32);                    // gzn[h][c] as the same A fragment
-      {
+      if constexpr (FULL) {
+        ldsm_x4(az, gz_frag + ks * 32);                  // gzn[h][c] as the same A fragment
         const uint32_t gp0 = s_gp[c_lo >> 1], gp1 = s_gp[(c_lo + 8) >> 1];
         const uint32_t rr0 = pack_bf16(r0, r0), rr1 = pack_bf16(r1, r1);
         az[0] = mul_bf16x2(mul_bf16x2(az[0], gp0), rr0);
@@ -399,8 +401,10 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       for (int ntp = 0; ntp < 4; ++ntp) {
         mma_bf16(sacc[2 * ntp], ahi, bfr[ntp][0], bfr[ntp][1]);
         mma_bf16(sacc[2 * ntp + 1], ahi, bfr[ntp][2], bfr[ntp][3]);
-        mma_bf16(gacc[2 * ntp], az, bfr[ntp][0], bfr[ntp][1]);
-        mma_bf16(gacc[2 * ntp + 1], az, bfr[ntp][2], bfr[ntp][3]);
+        if constexpr (FULL) {
+          mma_bf16(gacc[2 * ntp], az, bfr[ntp][0], bfr[ntp][1]);
+          mma_bf16(gacc[2 * ntp + 1], az, bfr[ntp][2], bfr[ntp][3]);
+        }
       }
 #pragma unroll
       for (int ntp = 0; ntp < 4; ++ntp) {
@@ -408,12 +412,14 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mma_bf16(sacc[2 * ntp + 1], alo, bfr[ntp][2], bfr[ntp][3]);
       }
       // one more column: the group means, so that column 0 collects sum_c (gamma gzn r)[h, c] mean_c  (xh = x r - mean r)
-      const float mu0 = s_rm[32 + g0], mu1 = s_rm[32 + g1];
-      mma_bf16(cacc, az, g == 0 ? pack_bf16(mu0, mu0) : 0u, g == 0 ? pack_bf16(mu1, mu1) : 0u);
+      if constexpr (FULL) {
+        const float mu0 = s_rm[32 + g0], mu1 = s_rm[32 + g1];
+        mma_bf16(cacc, az, g == 0 ? pack_bf16(mu0, mu0) : 0u, g == 0 ? pack_bf16(mu1, mu1) : 0u);
+      }
     }
     // positional term and the constant of a head:  sum_i go[16 h + i] (PE16[t][i] + bc[16 h + i] + (Wc beta)[16 h + i])
-    float gsa0, gsa1;
-    {
+    float gsa0 = 0.f, gsa1 = 0.f;
+    if constexpr (FULL) {
       const float* wb0 = s_wb + 16 * g + 2 * j;
       const float* wb1 = s_wb + 16 * (g + 8) + 2 * j;
       gsa0 = go0.x * wb0[0] + go0.y * wb0[1] + go2.x * wb0[8] + go2.y * wb0[9];
@@ -523,7 +529,7 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       sgs0 += __shfl_xor_sync(0xffffffffu, sgs0, 2);
       sgs1 += __shfl_xor_sync(0xffffffffu, sgs1, 1);
       sgs1 += __shfl_xor_sync(0xffffffffu, sgs1, 2);
-      if (j == 0) {
+      if (FULL && j == 0) {
         a.sa_rows[(row0 + p) * kMaxHeads + g] = sa0;
         a.sa_rows[(row0 + p) * kMaxHeads + g + 8] = sa1;
       }
@@ -532,7 +538,7 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // ---- au[h, c] = sum_t gs[h, t] xh[t, c], az[h, c] = sum_t at[h, t] xh[t, c], 32 channels at a time; zn rows, grad_U,
     //      direct gamma / beta terms and the two GroupNorm-backward means of every group ----------------------------------
     {
-      float* zn_row = a.zn_rows + (row0 + p) * kH * C;
+      float* zn_row = FULL ? a.zn_rows + (row0 + p) * kH * C : nullptr;
 #pragma unroll 1
       for (int ch = 0; ch < C / 32; ++ch) {
         float au[4][4], azv[4][4];
@@ -551,8 +557,10 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           for (int q = 0; q < 2; ++q) {
             mma_bf16(au[2 * q], ags, v[q][0], v[q][2]);
             mma_bf16(au[2 * q + 1], ags, v[q][1], v[q][3]);
-            mma_bf16(azv[2 * q], aat, v[q][0], v[q][2]);
-            mma_bf16(azv[2 * q + 1], aat, v[q][1], v[q][3]);
+            if constexpr (FULL) {
+              mma_bf16(azv[2 * q], aat, v[q][0], v[q][2]);
+              mma_bf16(azv[2 * q + 1], aat, v[q][1], v[q][3]);
+            }
           }
         }
 #pragma unroll
@@ -568,15 +576,17 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             auv[i] = fmaf(au[nt][i], r, -m * (i < 2 ? sgs0 : sgs1));
             azz[i] = fmaf(azv[nt][i], r, -m * (i < 2 ? sa0 : sa1));
           }
-          *reinterpret_cast<float2*>(zn_row + g * C + c) = make_float2(fmaf(gm.x, azz[0], bt.x * sa0), fmaf(gm.y, azz[1], bt.y * sa0));
-          *reinterpret_cast<float2*>(zn_row + (g + 8) * C + c) =
-              make_float2(fmaf(gm.x, azz[2], bt.x * sa1), fmaf(gm.y, azz[3], bt.y * sa1));
+          if constexpr (FULL) {
+            *reinterpret_cast<float2*>(zn_row + g * C + c) = make_float2(fmaf(gm.x, azz[0], bt.x * sa0), fmaf(gm.y, azz[1], bt.y * sa0));
+            *reinterpret_cast<float2*>(zn_row + (g + 8) * C + c) =
+                make_float2(fmaf(gm.x, azz[2], bt.x * sa1), fmaf(gm.y, azz[3], bt.y * sa1));
+          }
           atomicAdd(s_gu + c * GP + g, auv[0]);
           atomicAdd(s_gu + (c + 1) * GP + g, auv[1]);
           atomicAdd(s_gu + c * GP + g + 8, auv[2]);
           atomicAdd(s_gu + (c + 1) * GP + g + 8, auv[3]);
-          const uint32_t z0 = *reinterpret_cast<const uint32_t*>(gz_ptr + g * S::kGzRow + c * 2);
-          const uint32_t z1 = *reinterpret_cast<const uint32_t*>(gz_ptr + (g + 8) * S::kGzRow + c * 2);
+          const uint32_t z0 = FULL ? *reinterpret_cast<const uint32_t*>(gz_ptr + g * S::kGzRow + c * 2) : 0u;
+          const uint32_t z1 = FULL ? *reinterpret_cast<const uint32_t*>(gz_ptr + (g + 8) * S::kGzRow + c * 2) : 0u;
           const float zg[4] = {bf16_lo(z0), bf16_hi(z0), bf16_lo(z1), bf16_hi(z1)};
           // score weights of (rows g, g + 8; channels c, c + 1): the A fragment words of k-step c / 16, half (c / 8) & 1
           const float4 uq = s_uf[(c >> 4) * 64 + ((c >> 3) & 1) * 32 + lane];
@@ -593,7 +603,7 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             q1 += __shfl_xor_sync(0xffffffffu, q1, o);
             q2 += __shfl_xor_sync(0xffffffffu, q2, o);
           }
-          if (g == 0) {
+          if (FULL && g == 0) {
             atomicAdd(s_ggb + c, gg0);
             atomicAdd(s_ggb + c + 1, gg1);
             atomicAdd(s_ggb + C + c, gb0);
@@ -642,13 +652,15 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             for (int i = 0; i < 4; ++i) accu[mt][n2][i] = 0.f, accz[mt][n2][i] = 0.f;
         const uint2 ub0 = s_ub[(2 * np) * 32 + lane], ub1 = s_ub[(2 * np + 1) * 32 + lane];
         uint32_t zb[4];  // gzn as B[k = h][n = c]: (h 0-7, block 2 np), (h 8-15, 2 np), (h 0-7, 2 np + 1), (h 8-15, 2 np + 1)
-        ldsm_x4_trans(zb, gz_frag + np * 32);
+        if constexpr (FULL) ldsm_x4_trans(zb, gz_frag + np * 32);
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
           mma_bf16(accu[mt][0], agsT[mt], ub0.x, ub0.y);
           mma_bf16(accu[mt][1], agsT[mt], ub1.x, ub1.y);
-          mma_bf16(accz[mt][0], aatT[mt], zb[0], zb[1]);
-          mma_bf16(accz[mt][1], aatT[mt], zb[2], zb[3]);
+          if constexpr (FULL) {
+            mma_bf16(accz[mt][0], aatT[mt], zb[0], zb[1]);
+            mma_bf16(accz[mt][1], aatT[mt], zb[2], zb[3]);
+          }
         }
 #pragma unroll
         for (int n2 = 0; n2 < 2; ++n2) {
@@ -712,10 +724,11 @@ ltae_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int c = i >> 4, h = i & 15;
     atomicAdd(a.g_u + i, s_gu[c * GP + h]);
   }
-  for (int i = tid; i < C; i += 256) {
-    atomicAdd(a.g_gamma + i, s_ggb[i]);
-    atomicAdd(a.g_beta + i, s_ggb[C + i]);
-  }
+  if constexpr (FULL)
+    for (int i = tid; i < C; i += 256) {
+      atomicAdd(a.g_gamma + i, s_ggb[i]);
+      atomicAdd(a.g_beta + i, s_ggb[C + i]);
+    }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the last stores have left shared memory
 }
 
@@ -734,15 +747,15 @@ EncodeTiledFn bt_encode_fn() {
   return fn;
 }
 
-template <int C>
+template <int C, bool FULL>
 int bt_launch(const CUtensorMap& map_x, const CUtensorMap& map_gx, const BwdTcArgs& a, cudaStream_t stream, const char* name) {
   using S = BtSmem<C>;
-  C2S_SMEM_ATTR((ltae_bwd_tc_kernel<C>), S::kTotal);
+  C2S_SMEM_ATTR((ltae_bwd_tc_kernel<C, FULL>), S::kTotal);
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     sms = 148;
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-  ltae_bwd_tc_kernel<C><<<static_cast<unsigned>(grid), 256, S::kTotal, stream>>>(map_x, map_gx, a);
+  ltae_bwd_tc_kernel<C, FULL><<<static_cast<unsigned>(grid), 256, S::kTotal, stream>>>(map_x, map_gx, a);
   C2S_LAUNCH_CHECK(name);
   return C2S_OK;
 }
@@ -750,14 +763,15 @@ int bt_launch(const CUtensorMap& map_x, const CUtensorMap& map_gx, const BwdTcAr
 }  // namespace
 
 bool ltae_bwd_tc_eligible(const c2s_ltae_desc& d, const void* x, const c2s_ltae_bwd_io& io) {
-  if (d.flags & C2S_LTAE_ATTN_ONLY) return false;
+  const bool attn_only = (d.flags & C2S_LTAE_ATTN_ONLY) != 0;
+  if (attn_only && io.grad_attn == nullptr) return false;
   if (d.dtype != C2S_BF16 || d.n_head != kH || d.d_model != kD || !d.has_inconv) return false;
   if (d.C != 64 && d.C != 128) return false;
   if (d.T > kTP || d.T < 1 || (d.H * d.W) % kPix != 0) return false;
   if (d.pe_mode == C2S_PE_SINUSOID_LINEAR) return false;  // table differs per head chunk
   if (io.grad_pe != nullptr) return false;                // learnable tables: the general kernel forms grad_pe
   if (reinterpret_cast<uintptr_t>(x) % 16 != 0 || reinterpret_cast<uintptr_t>(io.grad_x) % 16 != 0) return false;
-  if (reinterpret_cast<uintptr_t>(io.grad_o) % 8 != 0 || reinterpret_cast<uintptr_t>(io.zn_rows) % 8 != 0) return false;
+  if (!attn_only && (reinterpret_cast<uintptr_t>(io.grad_o) % 8 != 0 || reinterpret_cast<uintptr_t>(io.zn_rows) % 8 != 0)) return false;
   return true;
 }
 
@@ -791,8 +805,12 @@ int ltae_bwd_tc_launch(const c2s_ltae_desc& d, const BwdTcArgs& a0, void* grad_x
   a.tiles_per_b = hw / kPix;
   if (static_cast<long long>(d.B) * a.tiles_per_b > 0x3fffffffll) C2S_UNSUPPORTED("c2s_ltae_backward: too many pixel tiles");
   a.n_tiles = d.B * a.tiles_per_b;
-  if (C == 128) return bt_launch<128>(maps[0], maps[1], a, stream, "ltae_backward<tc,C=128>");
-  return bt_launch<64>(maps[0], maps[1], a, stream, "ltae_backward<tc,C=64>");
+  if (a.g_o == nullptr) {  // attention-only encoder
+    if (C == 128) return bt_launch<128, false>(maps[0], maps[1], a, stream, "ltae_backward<tc,C=128,attention>");
+    return bt_launch<64, false>(maps[0], maps[1], a, stream, "ltae_backward<tc,C=64,attention>");
+  }
+  if (C == 128) return bt_launch<128, true>(maps[0], maps[1], a, stream, "ltae_backward<tc,C=128>");
+  return bt_launch<64, true>(maps[0], maps[1], a, stream, "ltae_backward<tc,C=64>");
 }
 
 }  // namespace c2s

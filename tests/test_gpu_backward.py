@@ -347,3 +347,50 @@ def test_ltae_tensor_core_backward_matches_the_general_kernel_and_the_oracle(c_i
         ref = ref_g[name]
         diff = float(np.abs(g_ - ref).max())
         assert diff <= 3e-2 * max(float(np.abs(ref).max()), 1e-3 * gmax), (name, diff)
+
+
+@pytest.mark.parametrize("c_in,lengths,hw", [(128, [61, 27, 5], (4, 4)), (64, [40, 61, 33, 1], (32, 16))])
+def test_attention_only_encoder_backward_on_the_tensor_cores(c_in, lengths, hw):
+    """LTAE4WTAE (W-TAE, tae.py:507-635) in training mode: the attention-only variant of the tensor-core stage A against the
+    fp32 CUDA-core kernel on the same call (grad_x and every parameter gradient)."""
+    kw = dict(in_channels=c_in, n_head=16, d_k=4, d_model=256)
+    m, rng = _ltae(kw, 11 + c_in, kind="wtae")
+    m.train()
+    m.assume_zero_padded = True
+    b, t, (h, w) = len(lengths), max(lengths), hw
+    x, pos, pad = synth_inputs(rng, b, t, c_in, h, w, lengths)
+    x = bf16_round(x + 0.3 * rng.standard_normal(x.shape).astype(np.float32) * (~pad)[:, :, None, None, None])
+    attn_keep = (rng.uniform(size=(16, b, t, h, w)) >= 0.1).astype(np.uint8)
+    wa = rng.standard_normal((16, b, t, h, w)).astype(np.float32)
+
+    def run(general):
+        for p_ in m.parameters():
+            p_.grad = None
+        xd = to_dev(x, dtype=torch.bfloat16).requires_grad_(True)
+        kernels = []
+        orig = ops.ltae_backward
+
+        def spy(*a_, **k_):
+            r = orig(*a_, **k_)
+            kernels.append(_lib.last_kernel())
+            return r
+        with _lib.option(_lib.OPT_LTAE_BWD_KERNEL, 1 if general else 0):
+            with c2s.modules.injected_dropout(to_dev(attn_keep), None):
+                attn = m(xd, batch_positions=to_dev(pos), pad_mask=to_dev(pad))
+            ops.ltae_backward = spy
+            try:
+                (attn * to_dev(wa)).sum().backward()
+            finally:
+                ops.ltae_backward = orig
+        return xd.grad.float().cpu().numpy(), {n_: p_.grad.cpu().numpy().copy() for n_, p_ in m.named_parameters()
+                                               if p_.grad is not None}, kernels
+
+    gx_tc, gp_tc, k_tc = run(False)
+    gx_gen, gp_gen, k_gen = run(True)
+    assert k_tc == [f"ltae_backward<tc,C={c_in},attention>"] and k_gen == ["ltae_backward<general>"]
+    assert np.isfinite(gx_tc).all() and rel_err(gx_tc, gx_gen) < 1.5e-2
+    assert set(gp_tc) == set(gp_gen)
+    gmax = max(float(np.abs(v).max()) for v in gp_gen.values())
+    for name, ref in gp_gen.items():
+        diff = float(np.abs(gp_tc[name] - ref).max())
+        assert diff <= 3e-2 * max(float(np.abs(ref).max()), 1e-3 * gmax), (name, diff)
