@@ -324,13 +324,19 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 // that permutation: longest-processing-time-first, the tail is made of the shortest series.
 __global__ void __launch_bounds__(1024) agg_order_kernel(const uint8_t* __restrict__ pad, int* __restrict__ order, int B, int T) {
   __shared__ short len[1024];
-  const int i = threadIdx.x;
-  int n = 0;
-  if (i < B)
-    for (int t = 0; t < T; ++t) n += pad[i * T + t] == 0;
-  len[i] = static_cast<short>(i < B ? n : -1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int s = warp; s < B; s += 32) {  // one warp per sample: T / 32 coalesced byte loads and a ballot instead of T loads per thread
+    int n = 0;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      const int t = t0 + lane;
+      n += __popc(__ballot_sync(0xffffffffu, t < T && pad[s * T + t] == 0));
+    }
+    if (lane == 0) len[s] = static_cast<short>(n);
+  }
   __syncthreads();
+  const int i = threadIdx.x;
   if (i >= B) return;
+  const int n = len[i];
   int rank = 0;
   for (int q = 0; q < B; ++q) rank += (len[q] > n) || (len[q] == n && q < i);
   order[rank] = i;

@@ -119,50 +119,56 @@ __device__ __forceinline__ int pos_as_doy(const P* pos, size_t i) {
   return static_cast<int>(v > 364 ? 364 : v);
 }
 
-// pe[b,t,d] for one (b,t) per block                                  (positional_encoding.py:25-43, 58-73)
+constexpr int kPosRows = 4;
+// pe[b,t,d] for kPosRows (b,t) rows per block                                 (positional_encoding.py:25-43, 58-73)
 template <typename P>
 __global__ void pos_table_kernel(const P* __restrict__ pos, int pos_stride, const float* __restrict__ denom,
                                  const float* __restrict__ fc_w, const float* __restrict__ fc_b,
                                  const float* __restrict__ abs_w, const float* __restrict__ abs_b,
                                  float* __restrict__ pe, int D, int dh, int pe_mode, int pe_abs,
                                  const float* __restrict__ qk, const float* __restrict__ ub,
-                                 float* __restrict__ cpos, int n_head) {
+                                 float* __restrict__ cpos, int n_head, size_t n_bt) {
   extern __shared__ float base[];  // [dh] un-tiled sinusoid table (add_linear only), then [D] the finished row
   float* row = base + dh;
-  const size_t bt = blockIdx.x;
-  const size_t pi = bt * pos_stride;
-  if (pe_mode == C2S_PE_SINUSOID_LINEAR || pe_mode == C2S_PE_SINUSOID) {  // the table has dh distinct columns, tiled h times
-    const float p = pos_as_float(pos, pi);
-    for (int i = threadIdx.x; i < dh; i += blockDim.x) {
-      const float a = p / denom[i];
-      base[i] = (i & 1) ? cosf(a) : sinf(a);
+  // kPosRows (b, t) rows per block: the qk rows of the cpos products stay in L1 / registers across them
+  for (int rr = 0; rr < kPosRows; ++rr) {
+    const size_t bt = static_cast<size_t>(blockIdx.x) * kPosRows + rr;
+    if (bt >= n_bt) break;  // uniform
+    const size_t pi = bt * pos_stride;
+    if (pe_mode == C2S_PE_SINUSOID_LINEAR || pe_mode == C2S_PE_SINUSOID) {  // the table has dh distinct columns, tiled h times
+      const float p = pos_as_float(pos, pi);
+      for (int i = threadIdx.x; i < dh; i += blockDim.x) {
+        const float a = p / denom[i];
+        base[i] = (i & 1) ? cosf(a) : sinf(a);
+      }
+      __syncthreads();
+    }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const int i = d % dh;
+      float v = 0.f;
+      if (pe_mode == C2S_PE_SINUSOID) {
+        v = base[i];
+      } else if (pe_mode == C2S_PE_SINUSOID_LINEAR) {
+        v = fc_b[d];
+        for (int k = 0; k < D; ++k) v = fmaf(fc_w[static_cast<size_t>(d) * D + k], base[k % dh], v);
+      } else if (pe_mode == C2S_PE_DOY_TABLE) {
+        v = fc_w[static_cast<size_t>(i) * 365 + pos_as_doy(pos, pi)] + fc_b[i];
+      }
+      if (pe_abs) v += abs_w[static_cast<size_t>(i) * 365 + pos_as_doy(pos, pi + 1)] + abs_b[i];
+      pe[bt * D + d] = v;
+      row[d] = v;
     }
     __syncthreads();
-  }
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const int i = d % dh;
-    float v = 0.f;
-    if (pe_mode == C2S_PE_SINUSOID) {
-      v = base[i];
-    } else if (pe_mode == C2S_PE_SINUSOID_LINEAR) {
-      v = fc_b[d];
-      for (int k = 0; k < D; ++k) v = fmaf(fc_w[static_cast<size_t>(d) * D + k], base[k % dh], v);
-    } else if (pe_mode == C2S_PE_DOY_TABLE) {
-      v = fc_w[static_cast<size_t>(i) * 365 + pos_as_doy(pos, pi)] + fc_b[i];
-    }
-    if (pe_abs) v += abs_w[static_cast<size_t>(i) * 365 + pos_as_doy(pos, pi + 1)] + abs_b[i];
-    pe[bt * D + d] = v;
-    row[d] = v;
-  }
-  __syncthreads();
-  // cpos[b,t,hh] = ub[hh] + qk[hh,:] . pe[b,t,:]: 16 lanes per head
-  const int hh = threadIdx.x >> 4, part = threadIdx.x & 15;
-  float s = 0.f;
-  if (hh < n_head)
-    for (int d = part; d < D; d += 16) s = fmaf(qk[hh * D + d], row[d], s);
+    // cpos[b,t,hh] = ub[hh] + qk[hh,:] . pe[b,t,:]: 16 lanes per head
+    const int hh = threadIdx.x >> 4, part = threadIdx.x & 15;
+    float s = 0.f;
+    if (hh < n_head)
+      for (int d = part; d < D; d += 16) s = fmaf(__ldg(qk + hh * D + d), row[d], s);
 #pragma unroll
-  for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (part == 0 && hh < kMaxHeads) cpos[bt * kMaxHeads + hh] = hh < n_head ? s + ub[hh] : 0.f;
+    for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (part == 0 && hh < kMaxHeads) cpos[bt * kMaxHeads + hh] = hh < n_head ? s + ub[hh] : 0.f;
+    __syncthreads();  // the next row overwrites base / row
+  }
 }
 
 // without a positional encoder: cpos[b,t,hh] = ub[hh]
@@ -217,15 +223,15 @@ int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* p
     const int stride = d.pe_abs ? 2 : 1;
     const size_t smem = static_cast<size_t>(dh + D) * sizeof(float);
     if (d.pos_dtype == 0) {
-      pos_table_kernel<long long><<<static_cast<unsigned>(n_bt), kPrepThreads, smem, stream>>>(
+      pos_table_kernel<long long><<<static_cast<unsigned>(ceil_div(n_bt, kPosRows)), kPrepThreads, smem, stream>>>(
           static_cast<const long long*>(positions), stride, p.pe_denom, p.pe_fc_weight, p.pe_fc_bias,
           p.pe_abs_fc_weight, p.pe_abs_fc_bias, ws + lay.pe, D, dh, d.pe_mode, d.pe_abs, qk, ws + lay.ub,
-          ws + lay.cpos, h);
+          ws + lay.cpos, h, n_bt);
     } else {
-      pos_table_kernel<float><<<static_cast<unsigned>(n_bt), kPrepThreads, smem, stream>>>(
+      pos_table_kernel<float><<<static_cast<unsigned>(ceil_div(n_bt, kPosRows)), kPrepThreads, smem, stream>>>(
           static_cast<const float*>(positions), stride, p.pe_denom, p.pe_fc_weight, p.pe_fc_bias,
           p.pe_abs_fc_weight, p.pe_abs_fc_bias, ws + lay.pe, D, dh, d.pe_mode, d.pe_abs, qk, ws + lay.ub,
-          ws + lay.cpos, h);
+          ws + lay.cpos, h, n_bt);
     }
     C2S_LAUNCH_CHECK("ltae_pos_table");
   }
