@@ -888,17 +888,18 @@ struct NormArgs {
 template <typename T, int kNormItems>
 __global__ void __launch_bounds__(256) group_norm_relu_kernel(const NormArgs a) {
   constexpr int VEC = Elem<T>::kVec;
-  constexpr int SPAN = 256 * kNormItems * VEC;  // elements per block
+  constexpr uint32_t SPAN = 256 * kNormItems * VEC;  // elements per block
   __shared__ float s_sc[256], s_sh[256];  // scale / shift of the channels this block touches (the host checks <= 256)
   const int f = blockIdx.y;
-  const size_t per_frame = static_cast<size_t>(a.C) * a.hw;
-  const size_t e0 = static_cast<size_t>(blockIdx.x) * SPAN;
-  const int c_first = static_cast<int>(e0 / a.hw);
-  size_t e_last = e0 + SPAN - 1;
+  // 32-bit arithmetic inside a frame (the host checks C * hw < 2^31): 64-bit divisions cost ~100 instructions per vector
+  const uint32_t hw = static_cast<uint32_t>(a.hw), per_frame = static_cast<uint32_t>(a.C) * hw;
+  const uint32_t e0 = blockIdx.x * SPAN;
+  const uint32_t c_first = e0 / hw;
+  uint32_t e_last = e0 + SPAN - 1;
   e_last = e_last < per_frame ? e_last : per_frame - 1;
-  const int n_ch = static_cast<int>(e_last / a.hw) - c_first + 1;
+  const int n_ch = static_cast<int>(e_last / hw - c_first) + 1;
   if (static_cast<int>(threadIdx.x) < n_ch) {
-    const int c = c_first + threadIdx.x;
+    const int c = static_cast<int>(c_first) + threadIdx.x;
     const int cpg = a.C / a.n_groups, g = c / cpg, spg = a.n_sub / a.n_groups;
     double t1 = 0.0, t2 = 0.0;
     for (int k = 0; k < spg; ++k) {
@@ -916,10 +917,10 @@ __global__ void __launch_bounds__(256) group_norm_relu_kernel(const NormArgs a) 
   // the loads go out before the barrier: they travel while the scale / shift of the block is formed
   const size_t base = static_cast<size_t>(f) * per_frame;
   uint4 xv[kNormItems], rv[kNormItems];
-  size_t e[kNormItems];
+  uint32_t e[kNormItems];
 #pragma unroll
   for (int k = 0; k < kNormItems; ++k) {
-    e[k] = e0 + (static_cast<size_t>(k) * 256 + threadIdx.x) * VEC;
+    e[k] = e0 + (static_cast<uint32_t>(k) * 256 + threadIdx.x) * VEC;
     xv[k] = rv[k] = make_uint4(0, 0, 0, 0);
     if (e[k] < per_frame) {
       xv[k] = *reinterpret_cast<const uint4*>(static_cast<const T*>(a.x) + base + e[k]);  // plain load: out may alias x
@@ -930,7 +931,7 @@ __global__ void __launch_bounds__(256) group_norm_relu_kernel(const NormArgs a) 
 #pragma unroll
   for (int k = 0; k < kNormItems; ++k) {
     if (e[k] >= per_frame) continue;
-    const int ci = static_cast<int>(e[k] / a.hw) - c_first;  // hw % VEC == 0: the vector stays inside one channel
+    const uint32_t ci = e[k] / hw - c_first;  // hw % VEC == 0: the vector stays inside one channel
     const float sc = s_sc[ci], sh = s_sh[ci];
     float v[VEC];
     Elem<T>::unpack(xv[k], v);
@@ -1101,6 +1102,8 @@ int c2s_group_norm_relu(const void* x, const float* stats, int32_t n_sub, const 
                 "c2s_group_norm_relu: bad shape");
   C2S_CHECK_ARG(dtype == C2S_F32 || dtype == C2S_BF16, "c2s_group_norm_relu: unknown dtype %d", dtype);
   const int vec = dtype == C2S_BF16 ? 8 : 4;
+  if (static_cast<long long>(channels) * hw >= (1ll << 31)) C2S_UNSUPPORTED("c2s_group_norm_relu: a frame of %lld elements is too large",
+                                                                              static_cast<long long>(channels) * hw);
   C2S_CHECK_ARG(hw % vec == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
                     reinterpret_cast<uintptr_t>(residual) % 16 == 0,
                 "c2s_group_norm_relu: planes must be whole, aligned 16-byte vectors");
