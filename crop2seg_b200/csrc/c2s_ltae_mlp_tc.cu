@@ -222,6 +222,182 @@ ltae_mlp_tc_kernel(const __grid_constant__ CUtensorMap map_o_hi, const __grid_co
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(a.tmem_cols) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised version for c_out = 64 / 128 (the shipped MLPs): one CTA per SM walks over the 128-row tiles.
+//   warp 0 (one thread)  TMA producer: the weights (hi + lo, all four K chunks) once, then the o chunks of tile after tile
+//                        into a ring of 4 (c_out = 64) or 2 (c_out = 128) stages (hi + lo, 32 KB each);
+//   warp 1 (one thread)  issues the 48 tcgen05.mma of a tile into one of TWO accumulators in tensor memory, frees ring
+//                        stages and hands accumulators over with tcgen05.commit;
+//   warps 2-5            epilogue: 32 TMEM lanes (= pixel rows) each, 32 channels at a time entirely in registers (the
+//                        GroupNorm groups of 4 / 8 channels never straddle such a chunk): bias, BatchNorm fold, ReLU, dropout
+//                        mask, output GroupNorm, bf16 stores -- while the next tile's loads and products are under way.
+// The one-tile-per-CTA kernel above (no overlap, weights re-loaded per tile, epilogue through shared memory with run-time
+// loop bounds) took 0.74 ms at the Time-Unet placement (1 M rows: 4x its HBM time) and 36 us at the U-TAE placement.
+constexpr int kTc2Threads = 192;
+__host__ __device__ constexpr int tc2_stages(int co) { return co <= 64 ? 4 : 2; }  // 128 KB of weights leave room for two
+
+template <int CO>
+__global__ void __launch_bounds__(kTc2Threads, 1)
+ltae_mlp_tc2_kernel(const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                    const MlpArgs a, int n_tiles) {
+  constexpr uint32_t A_TILE = kRows * kChunk * 2;  // 16 KB: 128 rows x 128 B
+  constexpr uint32_t B_TILE = CO * kChunk * 2;     // one K chunk of the weights
+  constexpr uint32_t W_BYTES = kNumChunks * 2 * B_TILE;
+  constexpr int COG = CO / 16;                     // channels per output GroupNorm group
+  constexpr int kStages2 = tc2_stages(CO);
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bars[1 + 2 * kStages2 + 4];  // wfull, full[S], empty[S], tfull[2], tempty[2]
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_par[5 * CO];                  // bm, bn scale, bn shift, on_w, on_b
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem0 = (s32(smem) + 1023u) & ~1023u;
+  const uint32_t w_base = smem0, ring = smem0 + W_BYTES;
+  const uint32_t bar0 = s32(&bars[0]);
+  auto full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto empty = [&](int s) { return bar0 + 8u * (1 + kStages2 + s); };
+  auto tfull = [&](int b) { return bar0 + 8u * (1 + 2 * kStages2 + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (1 + 2 * kStages2 + 2 + b); };
+
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    for (int s = 0; s < kStages2; ++s) mbar_init(full(s), 1), mbar_init(empty(s), 1);
+    for (int b = 0; b < 2; ++b) mbar_init(tfull(b), 1), mbar_init(tempty(b), 4);  // one arrival per epilogue warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "r"(2 * CO) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < CO; i += kTc2Threads) {
+    s_par[i] = a.bm[i];
+    s_par[CO + i] = a.bnf != nullptr ? a.bnf[i] : 1.f;
+    s_par[2 * CO + i] = a.bnf != nullptr ? a.bnf[CO + i] : 0.f;
+    s_par[3 * CO + i] = a.on_w != nullptr ? a.on_w[i] : 1.f;
+    s_par[4 * CO + i] = a.on_b != nullptr ? a.on_b[i] : 0.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = tmem_base_s;
+
+  if (warp == 0) {
+    // ---- TMA producer ---------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      mbar_expect_tx(bar0, W_BYTES);
+      for (int kc = 0; kc < kNumChunks; ++kc) {
+        tma_load_2d(w_base + (2 * kc) * B_TILE, &map_w_hi, kc * kChunk, 0, bar0);
+        tma_load_2d(w_base + (2 * kc + 1) * B_TILE, &map_w_lo, kc * kChunk, 0, bar0);
+      }
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < kNumChunks; ++kc, ++g) {
+          const uint32_t s = g % kStages2;
+          if (g >= kStages2) mbar_wait(empty(s), ((g / kStages2) - 1u) & 1u);
+          const uint32_t base = ring + s * 2 * A_TILE;
+          mbar_expect_tx(full(s), 2 * A_TILE);
+          tma_load_2d(base, &map_o_hi, kc * kChunk, tile * kRows, full(s));
+          tma_load_2d(base + A_TILE, &map_o_lo, kc * kChunk, tile * kRows, full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ---------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(CO);
+      mbar_wait(bar0, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        if (it >= 2) mbar_wait(tempty(buf), ((it >> 1) - 1u) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_acc + buf * CO;
+        for (int kc = 0; kc < kNumChunks; ++kc, ++g) {
+          const uint32_t s = g % kStages2;
+          mbar_wait(full(s), (g / kStages2) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = ring + s * 2 * A_TILE;
+          const uint64_t d_ohi = umma_desc_k_sw128(base), d_olo = umma_desc_k_sw128(base + A_TILE);
+          const uint64_t d_whi = umma_desc_k_sw128(w_base + (2 * kc) * B_TILE), d_wlo = umma_desc_k_sw128(w_base + (2 * kc + 1) * B_TILE);
+#pragma unroll
+          for (int k = 0; k < kChunk / 16; ++k) {
+            const uint64_t adv = static_cast<uint64_t>(k * 2);
+            umma_bf16(d_tmem, d_ohi + adv, d_whi + adv, idesc, (kc | k) != 0);
+            umma_bf16(d_tmem, d_olo + adv, d_whi + adv, idesc, 1);
+            umma_bf16(d_tmem, d_ohi + adv, d_wlo + adv, idesc, 1);
+          }
+          umma_commit(empty(s));  // the stage is free once the products issued so far have read it
+        }
+        umma_commit(tfull(buf));
+      }
+    }
+  } else {
+    // ---- epilogue: TMEM lanes 32 q .. 32 q + 31 = pixel rows of the tile ------------------------------------------------
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      const int row = tile * kRows + q * 32 + lane;
+      const bool live = row < a.n_rows;
+      const int b = live ? row / a.hw : 0, pix = live ? row - b * a.hw : 0;
+      mbar_wait(tfull(buf), (it >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c0 = 0; c0 < CO; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + buf * CO + c0, v);
+        if (c0 + 32 >= CO) {  // the accumulator is in registers: the tile after next may overwrite it
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty(buf)) : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += s_par[c0 + i];
+        if (a.bnf == nullptr) {  // training: BatchNorm statistics need every row of the batch first
+          if (live) {
+            float4* dst = reinterpret_cast<float4*>(a.ypre + static_cast<size_t>(row) * CO + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], s_par[CO + c0 + i], s_par[2 * CO + c0 + i]), 0.f);
+        if (a.mlp_keep != nullptr && live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] *= a.mlp_keep[(static_cast<size_t>(b) * CO + c0 + i) * a.hw + pix] ? a.mlp_keep_scale : 0.f;
+        }
+        if (!live) continue;
+        __nv_bfloat16* ob = a.out + (static_cast<size_t>(b) * CO + c0) * a.hw + pix;
+#pragma unroll
+        for (int g0 = 0; g0 < 32; g0 += COG) {  // output GroupNorm over COG consecutive channels (tae.py:488), two passes
+          float m = 0.f;
+#pragma unroll
+          for (int k = 0; k < COG; ++k) m += v[g0 + k];
+          m /= static_cast<float>(COG);
+          float var = 0.f;
+#pragma unroll
+          for (int k = 0; k < COG; ++k) {
+            const float d = v[g0 + k] - m;
+            var = fmaf(d, d, var);
+          }
+          const float rstd = 1.f / sqrtf(var / static_cast<float>(COG) + a.gn_eps);
+#pragma unroll
+          for (int k = 0; k < COG; ++k)
+            ob[static_cast<size_t>(g0 + k) * a.hw] =
+                __float2bfloat16_rn(fmaf((v[g0 + k] - m) * rstd, s_par[3 * CO + c0 + g0 + k], s_par[4 * CO + c0 + g0 + k]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(2 * CO) : "memory");
+}
+
 // W[rows][cols] fp32 -> bf16 hi and lo planes, same row-major layout
 __global__ void split_rows_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                   size_t n) {
@@ -312,6 +488,22 @@ int ltae_mlp_tc_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, float*
   a.ypre = ypre, a.out = static_cast<__nv_bfloat16*>(out);
   a.n_rows = static_cast<int>(rows), a.hw = d.H * d.W, a.c_out = d.c_out;
   a.tmem_cols = d.c_out <= 32 ? 32 : (d.c_out <= 64 ? 64 : (d.c_out <= 128 ? 128 : 256));
+  if (d.c_out == 64 || d.c_out == 128) {  // persistent, warp-specialised kernel
+    const int n_tiles = ceil_div(rows, kRows);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    const size_t smem2 = static_cast<size_t>(kNumChunks) * 2 * d.c_out * kChunk * 2 + static_cast<size_t>(tc2_stages(d.c_out)) * 2 * kRows * kChunk * 2 + 1024;
+    if (d.c_out == 64) {
+      C2S_SMEM_ATTR(ltae_mlp_tc2_kernel<64>, smem2);
+      ltae_mlp_tc2_kernel<64><<<grid, kTc2Threads, smem2, stream>>>(m_ohi, m_olo, m_whi, m_wlo, a, n_tiles);
+    } else {
+      C2S_SMEM_ATTR(ltae_mlp_tc2_kernel<128>, smem2);
+      ltae_mlp_tc2_kernel<128><<<grid, kTc2Threads, smem2, stream>>>(m_ohi, m_olo, m_whi, m_wlo, a, n_tiles);
+    }
+    C2S_LAUNCH_CHECK("ltae_mlp<tcgen05>");
+    return C2S_OK;
+  }
   const size_t stage = 2 * static_cast<size_t>(kRows) * kChunk * 2 + 2 * static_cast<size_t>(d.c_out) * kChunk * 2;
   size_t smem = 2 * stage;
   const size_t ys_bytes = static_cast<size_t>(kRows) * (d.c_out + 1) * sizeof(float);
