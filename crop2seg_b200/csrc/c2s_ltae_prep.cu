@@ -171,6 +171,45 @@ __global__ void pos_table_kernel(const P* __restrict__ pos, int pos_stride, cons
   }
 }
 
+// The shipped encoders (plain sinusoid, 16 table columns tiled over 16 heads, d_model 256): one WARP per (b, t) row.  The
+// table repeats per head, so cpos[b,t,hh] = ub[hh] + sum_i base[i] * QS[hh][i] with QS[hh][i] = sum_h' qk[hh][16 h' + i]
+// (formed once per block): 16 multiply-adds per head instead of 256, no block-wide barrier per row.
+template <typename P>
+__global__ void __launch_bounds__(256) pos_table_sin16_kernel(const P* __restrict__ pos, const float* __restrict__ denom,
+                                                              float* __restrict__ pe, const float* __restrict__ qk,
+                                                              const float* __restrict__ ub, float* __restrict__ cpos,
+                                                              size_t n_bt) {
+  __shared__ float qs[16][17];
+  __shared__ float s_den[16], s_ub[16];
+  {
+    const int hh = threadIdx.x >> 4, i = threadIdx.x & 15;
+    float s = 0.f;
+#pragma unroll
+    for (int h2 = 0; h2 < 16; ++h2) s += qk[hh * 256 + h2 * 16 + i];
+    qs[hh][i] = s;
+    if (threadIdx.x < 16) s_den[threadIdx.x] = denom[threadIdx.x], s_ub[threadIdx.x] = ub[threadIdx.x];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t bt = static_cast<size_t>(blockIdx.x) * 8 + warp; bt < n_bt; bt += static_cast<size_t>(gridDim.x) * 8) {
+    const float p = pos_as_float(pos, bt);
+    const int i = lane & 15;
+    const float a = p / s_den[i];
+    const float base = (i & 1) ? cosf(a) : sinf(a);  // lanes 16-31 hold the same 16 columns
+    // pe[bt][d] = base[d % 16]: lane writes d = 8 lane .. 8 lane + 7, i.e. columns (8 lane) % 16 .. + 7
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __shfl_sync(0xffffffffu, base, ((8 * lane) & 15) + k);
+    float4* dst = reinterpret_cast<float4*>(pe + bt * 256 + 8 * lane);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s = fmaf(qs[i][k], __shfl_sync(0xffffffffu, base, k), s);
+    if (lane < 16) cpos[bt * kMaxHeads + lane] = s + s_ub[lane];
+  }
+}
+
 // without a positional encoder: cpos[b,t,hh] = ub[hh]
 __global__ void fill_cpos_kernel(const float* __restrict__ ub, float* __restrict__ cpos, int n_head, size_t n_bt) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -219,7 +258,16 @@ int ltae_prepare(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void* p
   }
   }  // !reuse
   const size_t n_bt = static_cast<size_t>(d.B) * d.T;
-  if (has_pe) {
+  if (has_pe && d.pe_mode == C2S_PE_SINUSOID && !d.pe_abs && dh == 16 && D == 256 && h == kMaxHeads) {
+    const unsigned blocks = static_cast<unsigned>(ceil_div(n_bt, 8) < 1184 ? ceil_div(n_bt, 8) : 1184);
+    if (d.pos_dtype == 0)
+      pos_table_sin16_kernel<long long><<<blocks, 256, 0, stream>>>(static_cast<const long long*>(positions), p.pe_denom,
+                                                                    ws + lay.pe, qk, ws + lay.ub, ws + lay.cpos, n_bt);
+    else
+      pos_table_sin16_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(positions), p.pe_denom, ws + lay.pe, qk,
+                                                                ws + lay.ub, ws + lay.cpos, n_bt);
+    C2S_LAUNCH_CHECK("ltae_pos_table");
+  } else if (has_pe) {
     const int stride = d.pe_abs ? 2 : 1;
     const size_t smem = static_cast<size_t>(dh + D) * sizeof(float);
     if (d.pos_dtype == 0) {
