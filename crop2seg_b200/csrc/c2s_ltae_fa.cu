@@ -781,15 +781,15 @@ __global__ void fa_build_ufrag_kernel(const float* __restrict__ u /*[C][16]*/, f
 // masks[b] = {frames the kernel reads, padded frames} as bit sets over t < T <= 64
 __global__ void fa_masks_kernel(const uint8_t* __restrict__ pad, unsigned long long* __restrict__ masks, int B, int T,
                                 int zero_padded) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per sample: two coalesced byte loads and two ballots instead of T dependent loads per thread
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
-  unsigned long long live = 0, pd = 0;
-  for (int t = 0; t < T; ++t) {
-    const bool is_pad = pad != nullptr && pad[b * T + t] != 0;
-    if (is_pad) pd |= 1ull << t;
-    if (!(is_pad && zero_padded)) live |= 1ull << t;
-  }
-  masks[2 * b] = live, masks[2 * b + 1] = pd;
+  const bool p0 = pad != nullptr && lane < T && pad[b * T + lane] != 0;
+  const bool p1 = pad != nullptr && lane + 32 < T && pad[b * T + 32 + lane] != 0;
+  const unsigned long long pd = static_cast<unsigned long long>(__ballot_sync(0xffffffffu, p0)) |
+                                (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, p1)) << 32);
+  const unsigned long long all = T >= 64 ? ~0ull : ((1ull << T) - 1ull);
+  if (lane == 0) masks[2 * b] = zero_padded ? (all & ~pd) : all, masks[2 * b + 1] = pd;
 }
 
 // out = {s, 1/s} with s the power of two that brings max |w| into [1, 2)
@@ -898,7 +898,7 @@ int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void
     fa_build_ufrag_kernel<<<ceil_div((C / 16) * 256, 256), 256, 0, stream>>>(ws + lay.u, ufrag, C);
     C2S_LAUNCH_CHECK("ltae_fa_build_ufrag");
   }
-  fa_masks_kernel<<<ceil_div(d.B, 128), 128, 0, stream>>>(pad_mask, masks, d.B, d.T, (d.flags & C2S_LTAE_ZERO_PADDED) != 0);
+  fa_masks_kernel<<<ceil_div(d.B, 4), 128, 0, stream>>>(pad_mask, masks, d.B, d.T, (d.flags & C2S_LTAE_ZERO_PADDED) != 0);
   C2S_LAUNCH_CHECK("ltae_fa_masks");
   if (!attn_only && !reuse) {
     fa_weight_scale_kernel<<<1, 1024, 0, stream>>>(p.inconv_weight, kD * C, wscale);
