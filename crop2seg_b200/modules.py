@@ -57,7 +57,8 @@ def _draw_keep(shape, p, device, which):
         if tuple(m.shape) != tuple(shape):
             raise RuntimeError(f"crop2seg_b200: injected dropout mask has shape {tuple(m.shape)}, expected {tuple(shape)}")
         return m.to(device=device, dtype=torch.uint8)
-    return (torch.rand(shape, device=device) >= p).to(torch.uint8)
+    # one launch (Philox Bernoulli straight into the uint8 mask) instead of rand + compare + cast
+    return torch.empty(shape, dtype=torch.uint8, device=device).bernoulli_(1.0 - p)
 
 
 #: construction-time defaults of the encoder attributes, set by ``crop2seg_b200.install(...)``

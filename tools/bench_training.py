@@ -69,7 +69,7 @@ def main():
     enc.assume_zero_padded = True
     model = torch.nn.parallel.DistributedDataParallel(enc, device_ids=[local_rank]) if world > 1 else enc
     agg = c2s.TemporalAggregator(mode="att_group")
-    opt = torch.optim.Adam(enc.parameters(), lr=1e-3, capturable=args.graph)  # train.py: Adam, lr 1e-3
+    opt = torch.optim.Adam(enc.parameters(), lr=1e-3, capturable=args.graph, fused=not args.graph)  # train.py: Adam, lr 1e-3
     projs = [torch.randn((B, 128, LTAE_RES, LTAE_RES), device=dev, generator=gen).to(torch.bfloat16)] + \
             [torch.randn((B, c, r, r), device=dev, generator=gen).to(torch.bfloat16) for c, r in LEVELS]
 
