@@ -52,16 +52,19 @@ def gather_shards(local, world_size: int, group=None):
 
 
 class GradientBucket:
-    """One flat fp32 buffer that holds every gradient of ``params`` (each ``p.grad`` is a view into it), so that the
-    data-parallel training step of the hot path needs exactly ONE collective: ``all_reduce()`` averages the buffer over
-    the ranks in place (NCCL over NVLink / NVSwitch), with no per-parameter hooks, no flatten / unflatten copies and no
-    bucket bookkeeping on the host.  SURVEY.md section 8e: training = replicas + one gradient all-reduce; BatchNorm
-    statistics stay per replica like in the reference (train.py builds no SyncBatchNorm).
+    """One flat fp32 buffer for every gradient of ``params``, so that the data-parallel training step of the hot path
+    needs exactly ONE collective: ``all_reduce()`` packs the gradients autograd produced into the buffer with one
+    multi-tensor copy, averages the buffer over the ranks in place (NCCL over NVLink / NVSwitch) and leaves every
+    ``p.grad`` as a view into it -- no per-parameter hooks, no bucket bookkeeping on the host.  SURVEY.md section 8e:
+    training = replicas + one gradient all-reduce; BatchNorm statistics stay per replica like in the reference (train.py
+    builds no SyncBatchNorm).
 
         bucket = GradientBucket(encoder.parameters())
-        loss.backward(); bucket.all_reduce(); optimizer.step(); bucket.zero()
+        bucket.zero(); loss.backward(); bucket.all_reduce(); optimizer.step()
 
-    ``optimizer.zero_grad(set_to_none=True)`` would detach the views: use ``bucket.zero()`` (one memset) instead.
+    ``zero()`` drops the gradients (``p.grad = None``): autograd then hands its tensors over instead of ADDING them into
+    existing ones -- with gradients pre-attached as views that was one small ``add_`` launch per parameter and step (16 for
+    the encoder) plus a memset.  On a single rank ``all_reduce()`` is a no-op and nothing is copied at all.
     """
 
     def __init__(self, params, group=None):
@@ -73,30 +76,40 @@ class GradientBucket:
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.group = group
+        self.views = []
         off = 0
         for p in self.params:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("GradientBucket: parameters must be float32 on one device")
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
     def zero(self) -> None:
-        self.flat.zero_()
-        for p in self.params:  # an optimizer may have replaced a view (set_to_none): re-attach
-            if p.grad is None or p.grad.untyped_storage().data_ptr() != self.flat.untyped_storage().data_ptr():
-                self._reattach()
-                break
-
-    def _reattach(self) -> None:
-        off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            p.grad = None
+
+    def pack(self) -> None:
+        """Gather the parameters' gradients into the flat buffer (one multi-tensor copy) and re-point them at it."""
+        import torch
+        src, dst, missing = [], [], []
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                missing.append(v)
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g.detach().to(torch.float32)), dst.append(v)
+        if missing:
+            torch._foreach_zero_(missing)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def all_reduce(self) -> None:
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return
+        self.pack()
         dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM,
                         group=self.group)
         if dist.get_backend(self.group) != "nccl":  # gloo has no AVG
