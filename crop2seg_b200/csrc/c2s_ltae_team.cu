@@ -60,7 +60,8 @@ struct TeamSmem {
   static constexpr int oRm = oPa + kPix * kPaPix * 4;               // float [TW][2][16]: rstd, mean * rstd per group
   static constexpr int oOst = oRm + TW * 2 * 16 * 4;
   static constexpr int oRed = oOst + kPix * kOst;                   // float [8 px][2 warps][max | sum][16] (WPP = 2)
-  static constexpr int oCpos = oRed + (WPP == 2 ? kPix * 2 * 2 * kH * 4 : 0);  // float [16][kAP]
+  static constexpr int oSa = oRed + (WPP == 2 ? kPix * 2 * 2 * kH * 4 : 0);    // float [8 px][16]: sum_t of the returned attention
+  static constexpr int oCpos = oSa + (WPP == 2 ? kPix * kH * 4 : 0);  // float [16][kAP]
   static constexpr int oPeHi = oCpos + kH * kAP * 4;                // bf16 [16][kPeRow]
   static constexpr int oPeLo = oPeHi + 16 * kPeRow * 2;
   static constexpr int oBar = oPeLo + 16 * kPeRow * 2;              // 4 mbarriers + release counter
@@ -100,7 +101,8 @@ __device__ __forceinline__ void team_bar(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int C>
+// DROP: training-mode dropout on the returned attention (a second instantiation: the eval kernel carries none of it)
+template <int C, bool DROP>
 __global__ void __launch_bounds__(512, 1)
 ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constant__ CUtensorMap map4,
                  const __grid_constant__ CUtensorMap map1, const FaArgs a) {
@@ -136,6 +138,7 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
   float* s_rm = reinterpret_cast<float*>(tb + S::oRm) + tw * 32;  // this warp's copy of rstd[16], mean * rstd[16]
   unsigned char* ost = tb + S::oOst + p * S::kOst;
   float* s_red = reinterpret_cast<float*>(tb + S::oRed);
+  float* s_sa = reinterpret_cast<float*>(tb + S::oSa);
   const uint32_t pair_bar = 3 + p;               // named barrier of the two warps of a pixel (WPP = 2)
   float* s_cpos = reinterpret_cast<float*>(tb + S::oCpos);
   __nv_bfloat16* s_pe_hi = reinterpret_cast<__nv_bfloat16*>(tb + S::oPeHi);
@@ -400,6 +403,7 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
     TEAM_DBG(4);  // scores
     // ---- softmax over t for rows h = g and g + 8 (base 2; normalisation deferred) ------------------- tae.py:831-836
     float inv0, inv1;
+    float sa0 = 1.f, sa1 = 1.f;  // sum_t of the returned attention of rows g / g + 8: 1 unless dropout acts on it (tae.py:837)
     {
       // padded frames and frames behind T: their scores are REPLACED (masked_fill, tae.py:831), whatever the slab holds
       const unsigned long long ov = (padm | beyond) >> (FPW * half);
@@ -457,6 +461,44 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
         d0 = lo0 + hi0, d1 = lo1 + hi1;
       }
       inv0 = 1.f / d0, inv1 = 1.f / d1;  // T >= 1: the maximum contributes exp2(0) = 1
+      if constexpr (DROP) {  // training: the returned attention is a * keep / (1 - p)
+        float p0 = 0.f, p1 = 0.f;
+        const uint8_t* kp0 = a.attn_keep + ((static_cast<size_t>(g) * a.B + b) * a.T) * a.hw + pix0 + p;
+        const size_t h8 = static_cast<size_t>(8) * a.B * a.T * a.hw;
+#pragma unroll
+        for (int nt = 0; nt < FN; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int t = FPW * half + nt * 8 + 2 * j + e;
+            bool k0 = false, k1 = false;
+            if (t < a.T) {
+              const uint8_t* kp = kp0 + static_cast<size_t>(t) * a.hw;
+              k0 = kp[0] != 0, k1 = kp[h8] != 0;
+            }
+            sacc[nt][e] = k0 ? sacc[nt][e] : 0.f;
+            sacc[nt][2 + e] = k1 ? sacc[nt][2 + e] : 0.f;
+            p0 += sacc[nt][e], p1 += sacc[nt][2 + e];
+          }
+        }
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+        if constexpr (WPP == 2) {  // the pair adds its halves in the same order on both sides
+          float* red = s_red + (p * 2 + half) * 2 * kH;
+          const float* red_other = s_red + (p * 2 + (half ^ 1)) * 2 * kH;
+          team_bar(pair_bar, 64);  // the partner has read the softmax sums
+          if (j == 0) red[kH + g] = p0, red[kH + g + 8] = p1;
+          team_bar(pair_bar, 64);
+          const float lo0 = half ? red_other[kH + g] : p0, hi0 = half ? p0 : red_other[kH + g];
+          const float lo1 = half ? red_other[kH + g + 8] : p1, hi1 = half ? p1 : red_other[kH + g + 8];
+          p0 = lo0 + hi0, p1 = lo1 + hi1;
+        }
+        inv0 *= a.attn_keep_scale, inv1 *= a.attn_keep_scale;
+        sa0 = p0 * inv0, sa1 = p1 * inv1;
+      }
+      if constexpr (DROP && WPP == 2)  // (dropout is served by the two-warps-per-pixel team only)
+        if (half == 0 && j == 0) s_sa[p * kH + g] = sa0, s_sa[p * kH + g + 8] = sa1;  // read behind the team barriers of the epilogue
     }
 
     TEAM_DBG(5);  // softmax
@@ -622,11 +664,12 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
         for (int nt = 0; nt < CW / 8; ++nt) {
           const int c = CW * half + nt * 8 + 2 * j;
           const int grp = c / CPG;
-          const float r = s_rm[grp] * inv, m = s_rm[16 + grp];
+          const float sa = rnd ? sa1 : sa0;
+          const float r = s_rm[grp] * inv, m = DROP ? s_rm[16 + grp] * sa : s_rm[16 + grp];
           const float2 gm = *reinterpret_cast<const float2*>(s_gam + c), bt = *reinterpret_cast<const float2*>(s_gam + C + c);
-          // sum_t a (x rstd - mean rstd) gamma + beta sum_t a, with sum_t a = 1
-          const float z0 = fmaf(gm.x, fmaf(zacc[nt][2 * rnd], r, -m), bt.x);
-          const float z1 = fmaf(gm.y, fmaf(zacc[nt][2 * rnd + 1], r, -m), bt.y);
+          // sum_t a (x rstd - mean rstd) gamma + beta sum_t a, with sum_t a = 1 unless dropout acts on the attention
+          const float z0 = fmaf(gm.x, fmaf(zacc[nt][2 * rnd], r, -m), DROP ? bt.x * sa : bt.x);
+          const float z1 = fmaf(gm.y, fmaf(zacc[nt][2 * rnd + 1], r, -m), DROP ? bt.y * sa : bt.y);
           uint32_t hi, lo;
           split_f16(z0, z1, hi, lo);
           *reinterpret_cast<uint32_t*>(zb + c * 2) = hi;
@@ -683,7 +726,8 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
         for (int e = 0; e < 4; ++e) {  // accumulator: rows i = g, g + 8; columns pixel 2j, 2j + 1
           const int i = g + (e >> 1) * 8, pp = 2 * j + (e & 1);
           const int d = h * 16 + i;
-          v[e] = fmaf(sum[e], inv_sc, s_bc[d] + s_pa[pp * S::kPaPix + ((e >> 1) * kH + h) * 8 + g]);
+          const float bcs = (DROP && WPP == 2) ? s_bc[d] * s_sa[pp * kH + h] : s_bc[d];
+          v[e] = fmaf(sum[e], inv_sc, bcs + s_pa[pp * S::kPaPix + ((e >> 1) * kH + h) * 8 + g]);
           if (a.save_o != nullptr) a.save_o[(row0 + pp) * kD + d] = v[e];
         }
         // rows of o for the tcgen05 MLP kernel: stmatrix.trans turns (i, pixel pair) fragments into 16-byte pieces
@@ -711,16 +755,16 @@ ltae_team_kernel(const __grid_constant__ CUtensorMap map16, const __grid_constan
   }
 }
 
-template <int C>
+template <int C, bool DROP>
 int team_launch(const CUtensorMap& map16, const CUtensorMap& map4, const CUtensorMap& map1, const FaArgs& a,
                 cudaStream_t stream, const char* name) {
   using S = TeamSmem<C>;
-  C2S_SMEM_ATTR((ltae_team_kernel<C>), S::kTotal);
+  C2S_SMEM_ATTR((ltae_team_kernel<C, DROP>), S::kTotal);
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int teams = (a.n_tiles + S::TEAMS - 1) / S::TEAMS;
   const int grid = teams < sms ? teams : sms;
-  ltae_team_kernel<C><<<static_cast<unsigned>(grid), 512, S::kTotal, stream>>>(map16, map4, map1, a);
+  ltae_team_kernel<C, DROP><<<static_cast<unsigned>(grid), 512, S::kTotal, stream>>>(map16, map4, map1, a);
   C2S_LAUNCH_CHECK(name);
   return C2S_OK;
 }
@@ -729,7 +773,8 @@ int team_launch(const CUtensorMap& map16, const CUtensorMap& map4, const CUtenso
 
 bool ltae_team_eligible(int C, const FaArgs& a) {
   if (C != 64 && C != 128) return false;
-  if (a.attn_only || a.attn_keep != nullptr) return false;  // LTAE4WTAE and training-mode dropout: c2s_ltae_fa.cu
+  if (a.attn_only) return false;                     // LTAE4WTAE: c2s_ltae_fa.cu
+  if (a.attn_keep != nullptr && C != 128) return false;  // training-mode dropout: the two-warps-per-pixel team only
   // C = 64: two slabs leave no room for the attention staging
   if (C == 64 && a.attn != nullptr && !a.skip_attn_store) return false;
   return true;
@@ -737,8 +782,9 @@ bool ltae_team_eligible(int C, const FaArgs& a) {
 
 int ltae_team_launch(int C, const CUtensorMap& map16, const CUtensorMap& map4, const CUtensorMap& map1, const FaArgs& a,
                      cudaStream_t stream) {
-  if (C == 64) return team_launch<64>(map16, map4, map1, a, stream, "ltae_forward<team,C=64>");
-  if (C == 128) return team_launch<128>(map16, map4, map1, a, stream, "ltae_forward<team,C=128>");
+  if (C == 64) return team_launch<64, false>(map16, map4, map1, a, stream, "ltae_forward<team,C=64>");
+  if (C == 128 && a.attn_keep != nullptr) return team_launch<128, true>(map16, map4, map1, a, stream, "ltae_forward<team,C=128>");
+  if (C == 128) return team_launch<128, false>(map16, map4, map1, a, stream, "ltae_forward<team,C=128>");
   set_error("ltae_team_launch: C=%d has no team kernel", C);
   return C2S_ERR_UNSUPPORTED;
 }
