@@ -11,7 +11,7 @@ import threading
 
 from .build import LIB_PATH
 
-C2S_ABI_VERSION = 11
+C2S_ABI_VERSION = 12
 
 # enum c2s_dtype / c2s_agg_mode / c2s_pe_mode / c2s_ltae_flags
 F32, BF16 = 0, 1
@@ -74,7 +74,7 @@ LTAE_MASK_FIELDS = ("attn_keep", "mlp_keep")  # uint8 dropout keep masks (traini
 
 
 class LtaeParams(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_PARAM_FIELDS + LTAE_MASK_FIELDS + ("save_o",)]
+    _fields_ = [(n, ctypes.c_void_p) for n in LTAE_PARAM_FIELDS + LTAE_MASK_FIELDS + ("save_o", "save_y")]
 
 
 LTAE_BWD_IO_FIELDS = ("grad_o", "grad_attn", "grad_x", "grad_u", "grad_cpos", "grad_gamma", "grad_beta", "zn_rows",
@@ -85,7 +85,7 @@ class LtaeBwdIo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in LTAE_BWD_IO_FIELDS]
 
 
-LTAE_MLP_BWD_IO_FIELDS = ("o_rows", "grad_out", "bn_mean", "bn_var", "grad_o", "grad_mlp_weight", "grad_mlp_bias",
+LTAE_MLP_BWD_IO_FIELDS = ("o_rows", "y_rows", "grad_out", "bn_mean", "bn_var", "grad_o", "grad_mlp_weight", "grad_mlp_bias",
                           "grad_bn_weight", "grad_bn_bias", "grad_out_norm_weight", "grad_out_norm_bias")
 
 

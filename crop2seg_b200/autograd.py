@@ -118,7 +118,7 @@ def _cuda_backward(ctx, cfg, x, positions, pad_mask, attn_keep, mlp_keep, params
             m_res = ops.ltae_mlp_backward(
                 ctx.o_rows, g_out.to(x.dtype), raw, mean, var, n_head=h, d_model=D, c_out=cfg["c_out"],
                 bn_batch_stats=cfg["bn_batch_stats"], gn_eps=cfg["gn_eps"], bn_eps=cfg["bn_eps"], mlp_keep=mlp_keep,
-                mlp_drop_p=1.0 - 1.0 / cfg["mlp_keep_scale"])
+                mlp_drop_p=1.0 - 1.0 / cfg["mlp_keep_scale"], y_rows=ctx.y_rows)
             g_o = m_res["grad_o"]
             for k in ("mlp_weight", "mlp_bias", "bn_weight", "bn_bias", "out_norm_weight", "out_norm_bias"):
                 if need[k]:
@@ -192,9 +192,11 @@ class LtaeFunction(torch.autograd.Function):
             bn_batch_stats=cfg["bn_batch_stats"], gn_eps=cfg["gn_eps"], bn_eps=cfg["bn_eps"],
             attn_keep=attn_keep, attn_drop_p=1.0 - 1.0 / cfg["attn_keep_scale"],
             mlp_keep=mlp_keep, mlp_drop_p=1.0 - 1.0 / cfg["mlp_keep_scale"],
-            save_o=ctx.cuda_backward and not cfg["attn_only"])
+            save_o=ctx.cuda_backward and not cfg["attn_only"],
+            save_y=ctx.cuda_backward and not cfg["attn_only"] and cfg["bn_batch_stats"])
         out, attn, stats = res[:3]
         ctx.o_rows = res[3] if len(res) > 3 else None
+        ctx.y_rows = res[4] if len(res) > 4 else None  # pre-BatchNorm rows (training mode): the backward does not recompute them
         ctx.cfg = cfg
         # the running statistics are updated in place right after a training-mode forward and are not needed by
         # its backward (batch statistics are recomputed), so they are not saved in that case

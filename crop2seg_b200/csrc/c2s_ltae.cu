@@ -486,7 +486,7 @@ int launch_general(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void*
   a.gamma = p.in_norm_weight, a.beta = p.in_norm_bias;
   a.bnf = (attn_only || train) ? nullptr : ws + lay.bnf;
   a.on_w = p.out_norm_weight, a.on_b = p.out_norm_bias;
-  a.ypre = train ? ws + lay.ypre : nullptr;
+  a.ypre = train ? (p.save_y != nullptr ? p.save_y : ws + lay.ypre) : nullptr;
   a.save_o = p.save_o;
   a.attn_keep = p.attn_keep, a.mlp_keep = p.mlp_keep;
   a.attn_keep_scale = d.attn_keep_scale, a.mlp_keep_scale = d.mlp_keep_scale;
@@ -614,7 +614,7 @@ int c2s_ltae_forward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, const v
   if (status != C2S_OK) return status;
 
   const int hw = d.H * d.W;
-  float* ypre = train ? ws + lay.ypre : nullptr;
+  float* ypre = train ? (p.save_y != nullptr ? p.save_y : ws + lay.ypre) : nullptr;  // caller-owned when the backward wants it
   if (use_fa) {
     status = ltae_fa_forward(d, p, x, pad_mask, out, attn, ws, lay, ws + lay.fa, stream);
     if (status != C2S_OK) return status;

@@ -944,7 +944,7 @@ int ltae_fa_forward(const c2s_ltae_desc& d, const c2s_ltae_params& p, const void
   a.gamma = p.in_norm_weight, a.beta = p.in_norm_bias;
   a.bnf = (attn_only || train) ? nullptr : ws + lay.bnf;
   a.on_w = p.out_norm_weight, a.on_b = p.out_norm_bias;
-  a.ypre = train ? ws + lay.ypre : nullptr;
+  a.ypre = train ? (p.save_y != nullptr ? p.save_y : ws + lay.ypre) : nullptr;
   a.attn_keep = p.attn_keep, a.mlp_keep = p.mlp_keep;
   a.save_o = p.save_o;
   a.attn_keep_scale = d.attn_keep_scale, a.mlp_keep_scale = d.mlp_keep_scale;

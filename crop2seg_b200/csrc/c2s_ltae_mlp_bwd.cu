@@ -345,12 +345,16 @@ int c2s_ltae_mlp_backward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, co
   float* colsum = g + align64(static_cast<size_t>(n_rows) * co);
   C2S_CUDA(cudaMemsetAsync(colsum, 0, 2 * static_cast<size_t>(co) * sizeof(float), stream));
 
-  // y = o Wm^T + bm
-  status = launch_gemm(io.o_rows, D, 1, p.mlp_weight, 1, D, y, co, p.mlp_bias, n_rows, co, D, 1, false, stream,
-                       "ltae_mlp_backward<recompute y>");
-  if (status != C2S_OK) return status;
+  // y = o Wm^T + bm: the rows the training-mode forward saved (params->save_y), else recomputed
+  const float* y_in = io.y_rows;
+  if (y_in == nullptr) {
+    status = launch_gemm(io.o_rows, D, 1, p.mlp_weight, 1, D, y, co, p.mlp_bias, n_rows, co, D, 1, false, stream,
+                         "ltae_mlp_backward<recompute y>");
+    if (status != C2S_OK) return status;
+    y_in = y;
+  }
   RowsArgs a{};
-  a.y = y, a.g_out = io.grad_out, a.mean = io.bn_mean, a.var = io.bn_var;
+  a.y = y_in, a.g_out = io.grad_out, a.mean = io.bn_mean, a.var = io.bn_var;
   a.bn_w = p.bn_weight, a.bn_b = p.bn_bias, a.on_w = p.out_norm_weight;
   a.keep = p.mlp_keep, a.keep_scale = d.mlp_keep_scale, a.bn_eps = d.bn_eps, a.gn_eps = d.gn_eps;
   a.g_yh = g, a.g_bn_w = io.grad_bn_weight, a.g_bn_b = io.grad_bn_bias;
@@ -364,7 +368,7 @@ int c2s_ltae_mlp_backward(const c2s_ltae_desc* dp, const c2s_ltae_params* pp, co
     mlp_rows_backward_kernel<float><<<ceil_div(n_warps, 8), 256, 0, stream>>>(a);
   C2S_LAUNCH_CHECK("ltae_mlp_backward<rows>");
   if (train) {
-    bn_batch_backward_kernel<<<ceil_div(n_rows, 32), 128, 0, stream>>>(g, y, io.bn_mean, io.bn_var, colsum, d.bn_eps,
+    bn_batch_backward_kernel<<<ceil_div(n_rows, 32), 128, 0, stream>>>(g, y_in, io.bn_mean, io.bn_var, colsum, d.bn_eps,
                                                                      io.grad_mlp_bias, n_rows, co);
     C2S_LAUNCH_CHECK("ltae_mlp_backward<batchnorm>");
   }

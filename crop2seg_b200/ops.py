@@ -211,7 +211,7 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
                  need_attn: bool = True, zero_padded: bool = False, bn_batch_stats: bool = False,
                  gn_eps: float = 1e-5, bn_eps: float = 1e-5, attn_keep: Optional[torch.Tensor] = None,
                  attn_drop_p: float = 0.0, mlp_keep: Optional[torch.Tensor] = None, mlp_drop_p: float = 0.0,
-                 folded_cache: Optional[dict] = None, folded_key=None, save_o: bool = False
+                 folded_cache: Optional[dict] = None, folded_key=None, save_o: bool = False, save_y: bool = False
                  ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[Tuple[torch.Tensor, torch.Tensor]]]:
     """Fused ``LTAE.forward`` / ``LTAE4WTAE.forward`` (tae.py:451-504, 589-635).
 
@@ -271,10 +271,13 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
         m = mlp_keep.to(device=dev, dtype=torch.uint8).contiguous()
         keep.append(m)
         cparams.mlp_keep = m.data_ptr()
-    o_rows = None
+    o_rows = y_rows = None
     if save_o and not attn_only:
         o_rows = torch.empty((b * h * w, d_model), dtype=torch.float32, device=dev)
         cparams.save_o = o_rows.data_ptr()
+    if save_y and not attn_only and bn_batch_stats:  # the pre-BatchNorm rows of the training-mode forward, for its backward
+        y_rows = torch.empty((b * h * w, c_out), dtype=torch.float32, device=dev)
+        cparams.save_y = y_rows.data_ptr()
     pad = _mask_u8(pad_mask, b, t, dev)
     out = None if attn_only else torch.empty((b, c_out, h, w), dtype=x.dtype, device=dev)
     attn = torch.empty((n_head, b, t, h, w), dtype=torch.float32, device=dev) if need_attn else None
@@ -306,6 +309,8 @@ def ltae_forward(x: torch.Tensor, positions: Optional[torch.Tensor], pad_mask: O
                                       _ptr(out), _ptr(attn), _ptr(stats[0]) if stats else None,
                                       _ptr(stats[1]) if stats else None, ws.data_ptr(), ws_bytes, _stream(dev))
     _lib.check(status, "c2s_ltae_forward")
+    if save_y:
+        return out, attn, stats, o_rows, y_rows
     if save_o:
         return out, attn, stats, o_rows
     return out, attn, stats
@@ -443,12 +448,14 @@ def ltae_fold_backward(res: Dict[str, torch.Tensor], want: Dict[str, bool], shap
 def ltae_mlp_backward(o_rows: torch.Tensor, grad_out: torch.Tensor, params: Dict[str, Optional[torch.Tensor]],
                       bn_mean: torch.Tensor, bn_var: torch.Tensor, *, n_head: int, d_model: int, c_out: int,
                       bn_batch_stats: bool, gn_eps: float = 1e-5, bn_eps: float = 1e-5,
-                      mlp_keep: Optional[torch.Tensor] = None, mlp_drop_p: float = 0.0) -> Dict[str, torch.Tensor]:
+                      mlp_keep: Optional[torch.Tensor] = None, mlp_drop_p: float = 0.0,
+                      y_rows: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """``c2s_ltae_mlp_backward``: backward of mlp.0 / mlp.2 / ReLU / dropout / out_norm on the pixel rows.
 
     ``o_rows`` [B*H*W, d_model] are the rows saved by the forward, ``grad_out`` [B, c_out, H, W] the incoming gradient,
-    ``bn_mean`` / ``bn_var`` the statistics the forward normalised with.  Returns ``grad_o`` and the parameter
-    gradients keyed like ``c2s_ltae_params``."""
+    ``bn_mean`` / ``bn_var`` the statistics the forward normalised with, ``y_rows`` [B*H*W, c_out] the pre-BatchNorm rows
+    the training-mode forward saved (``save_y``; recomputed from ``o_rows`` when None).  Returns ``grad_o`` and the
+    parameter gradients keyed like ``c2s_ltae_params``."""
     _require_cuda(grad_out, "grad_out")
     dev = grad_out.device
     b, co, h, w = grad_out.shape
@@ -474,7 +481,12 @@ def ltae_mlp_backward(o_rows: torch.Tensor, grad_out: torch.Tensor, params: Dict
         res[k] = zeros[c_out * d_model + i * cpad:c_out * d_model + i * cpad + c_out]
     o = o_rows.to(**f32).contiguous()
     mean, var = bn_mean.to(**f32).contiguous(), bn_var.to(**f32).contiguous()
-    io = _lib.LtaeMlpBwdIo(o_rows=o.data_ptr(), grad_out=g.data_ptr(), bn_mean=mean.data_ptr(), bn_var=var.data_ptr(),
+    yr = None
+    if y_rows is not None:
+        if tuple(y_rows.shape) != (n, c_out):
+            raise RuntimeError(f"crop2seg_b200: y_rows has shape {tuple(y_rows.shape)}, expected {(n, c_out)}")
+        yr = y_rows.to(**f32).contiguous()
+    io = _lib.LtaeMlpBwdIo(o_rows=o.data_ptr(), y_rows=_ptr(yr), grad_out=g.data_ptr(), bn_mean=mean.data_ptr(), bn_var=var.data_ptr(),
                            grad_o=res["grad_o"].data_ptr(), grad_mlp_weight=res["mlp_weight"].data_ptr(),
                            grad_mlp_bias=res["mlp_bias"].data_ptr(), grad_bn_weight=res["bn_weight"].data_ptr(),
                            grad_bn_bias=res["bn_bias"].data_ptr(), grad_out_norm_weight=res["out_norm_weight"].data_ptr(),

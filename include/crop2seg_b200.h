@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2S_ABI_VERSION 11
+#define C2S_ABI_VERSION 12
 
 enum c2s_status {
   C2S_OK = 0,
@@ -187,6 +187,9 @@ typedef struct c2s_ltae_params {
   /* training: if not NULL, c2s_ltae_forward also writes the rows o[B*H*W][d_model] that enter the MLP
    * (tae.py:479-486, the concatenated heads); c2s_ltae_backward's caller needs them for the MLP gradients */
   float* save_o;
+  /* training (C2S_LTAE_BN_BATCH_STATS): if not NULL, the pre-BatchNorm MLP rows y[B*H*W][c_out] are written here instead
+   * of into the workspace, so that c2s_ltae_mlp_backward (c2s_ltae_mlp_bwd_io.y_rows) need not recompute them */
+  float* save_y;
 } c2s_ltae_params;
 
 /* Scratch bytes for c2s_ltae_forward (folded weights + per-sample positional tables). */
@@ -245,6 +248,8 @@ typedef struct c2s_ltae_bwd_io {
  * (autograd through tae.py:442-449, 486-488).  Produces grad_o for c2s_ltae_backward.  acc buffers must be zeroed. */
 typedef struct c2s_ltae_mlp_bwd_io {
   const float* o_rows;          /* in  [B*H*W][d_model] rows saved by c2s_ltae_forward (params->save_o)   */
+  const float* y_rows;          /* in  [B*H*W][c_out] y = o Wm^T + bm saved by c2s_ltae_forward (params->save_y), or
+                                       NULL: recomputed from o_rows                                        */
   const void* grad_out;         /* in  [B][c_out][H][W] in desc->dtype                                     */
   const float* bn_mean;         /* in  [c_out] batch mean of the forward (training) or running_mean        */
   const float* bn_var;          /* in  [c_out] biased batch variance (training) or running_var             */

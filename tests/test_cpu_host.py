@@ -32,20 +32,20 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(LIB_PATH)
     for sym in declared:
         assert hasattr(raw, sym), sym
-    assert lib.c2s_abi_version() == _lib.C2S_ABI_VERSION == 11
+    assert lib.c2s_abi_version() == _lib.C2S_ABI_VERSION == 12
 
 
 def test_header_compiles_as_plain_c(tmp_path):
     src = tmp_path / "abi.c"
     src.write_text('#include "crop2seg_b200.h"\nint main(void){c2s_agg_desc d; c2s_ltae_desc l; (void)d; (void)l; '
-                   'return sizeof(c2s_ltae_params) == 23 * sizeof(void*) && sizeof(c2s_ltae_bwd_io) == 10 * sizeof(void*) ? 0 : 1;}\n')
+                   'return sizeof(c2s_ltae_params) == 24 * sizeof(void*) && sizeof(c2s_ltae_bwd_io) == 10 * sizeof(void*) ? 0 : 1;}\n')
     exe = tmp_path / "abi"
     import subprocess
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
                    check=True)
     assert subprocess.run([str(exe)]).returncode == 0
     assert ctypes.sizeof(_lib.AggDesc) == 40 and ctypes.sizeof(_lib.LtaeDesc) == 76
-    assert ctypes.sizeof(_lib.LtaeParams) == 23 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.LtaeParams) == 24 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.LtaeBwdIo) == 10 * ctypes.sizeof(ctypes.c_void_p)
 
 
